@@ -1,0 +1,109 @@
+"""ctypes binding of include/bm2f_msda.h — the same C ABI the torch extension calls.
+
+Used by the parity tests ("-m gpu tests call through the C-ABI"), by bench.py (tuning sweeps,
+launch counter, host-buffer end-to-end entry) and as the template for non-Python callers
+(INTEGRATION.md).  Pointers are raw integers (``tensor.data_ptr()``); nothing here touches torch.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libbm2f_msda.so")
+
+DTYPE_F32, DTYPE_F64, DTYPE_BF16 = 0, 1, 2
+
+# every symbol include/bm2f_msda.h declares (tests/test_cabi_symbols.py checks the export list)
+SYMBOLS = (
+    "bm2f_msda_abi_version", "bm2f_msda_build_info", "bm2f_msda_last_error", "bm2f_msda_launch_count",
+    "bm2f_msda_set_default_tuning", "bm2f_msda_check_im2col_step", "bm2f_msda_forward",
+    "bm2f_msda_backward", "bm2f_msda_forward_backward_host",
+)
+
+
+class Tuning(ctypes.Structure):
+    _fields_ = [("vec", ctypes.c_int), ("staging", ctypes.c_int), ("strip_w", ctypes.c_int),
+                ("rows", ctypes.c_int), ("ctas_per_sm", ctypes.c_int), ("force_generic", ctypes.c_int),
+                ("order", ctypes.c_int), ("reserved", ctypes.c_int * 9)]
+
+
+class MSDAError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -m bm2f_b200.build`")
+        L = ctypes.CDLL(LIB_PATH)
+        vp, i64p, ci = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int
+        tp = ctypes.POINTER(Tuning)
+        L.bm2f_msda_abi_version.restype = ci
+        L.bm2f_msda_build_info.restype = ctypes.c_char_p
+        L.bm2f_msda_last_error.restype = ctypes.c_char_p
+        L.bm2f_msda_launch_count.restype = ctypes.c_uint64
+        L.bm2f_msda_set_default_tuning.argtypes = [tp]
+        L.bm2f_msda_set_default_tuning.restype = None
+        L.bm2f_msda_check_im2col_step.argtypes = [ci, ci]
+        L.bm2f_msda_check_im2col_step.restype = ci
+        L.bm2f_msda_forward.argtypes = [vp, i64p, i64p, vp, vp, vp] + [ci] * 8 + [tp, vp]
+        L.bm2f_msda_forward.restype = ci
+        L.bm2f_msda_backward.argtypes = [vp, i64p, i64p, vp, vp, vp, vp, vp, vp] + [ci] * 8 + [tp, vp]
+        L.bm2f_msda_backward.restype = ci
+        L.bm2f_msda_forward_backward_host.argtypes = [vp] * 10 + [ci] * 8 + [tp]
+        L.bm2f_msda_forward_backward_host.restype = ci
+        _lib = L
+    return _lib
+
+
+def last_error() -> str:
+    return lib().bm2f_msda_last_error().decode()
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise MSDAError(f"{what} failed ({rc}): {last_error()}")
+
+
+def make_tuning(**kw):
+    t = Tuning()
+    for k, v in kw.items():
+        setattr(t, k, int(v))
+    return t
+
+
+def _tp(t):
+    return ctypes.byref(t) if t is not None else None
+
+
+def forward(value, shapes, start, loc, attn, out, dims, dtype=DTYPE_F32, tuning=None, stream=0):
+    """All tensor arguments are device addresses (ints).  dims = (N, S, M, D, L, Lq, P)."""
+    _check(lib().bm2f_msda_forward(value, shapes, start, loc, attn, out, *dims, dtype, _tp(tuning), stream),
+           "bm2f_msda_forward")
+
+
+def backward(value, shapes, start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, dims,
+             dtype=DTYPE_F32, tuning=None, stream=0):
+    _check(lib().bm2f_msda_backward(value, shapes, start, loc, attn, grad_out, grad_value, grad_loc, grad_attn,
+                                    *dims, dtype, _tp(tuning), stream), "bm2f_msda_backward")
+
+
+def forward_backward_host(value, shapes, start, loc, attn, grad_out, out, grad_value, grad_loc, grad_attn, dims,
+                          dtype=DTYPE_F32, tuning=None):
+    """Host-pointer entry (pinned buffers recommended); grad_out == 0 runs forward only."""
+    _check(lib().bm2f_msda_forward_backward_host(value, shapes, start, loc, attn, grad_out, out, grad_value,
+                                                 grad_loc, grad_attn, *dims, dtype, _tp(tuning)),
+           "bm2f_msda_forward_backward_host")
+
+
+def launch_count() -> int:
+    return int(lib().bm2f_msda_launch_count())
+
+
+def set_default_tuning(tuning=None):
+    lib().bm2f_msda_set_default_tuning(_tp(tuning))

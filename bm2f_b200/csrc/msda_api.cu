@@ -1,0 +1,516 @@
+// C ABI of libbm2f_msda.so (see include/bm2f_msda.h): argument checks, variant selection,
+// TMA tensor-map encoding and kernel launches.  No torch types here; the torch-facing shim
+// (msda_torch_ext.cpp) and ctypes callers sit on top of this file.
+//
+// Replaces the reference host wrappers ms_deform_attn_cuda_forward/backward and the launchers
+// ms_deformable_im2col_cuda / ms_deformable_col2im_cuda
+// (/root/reference/mask2former/modeling/pixel_decoder/ops/src/cuda/ms_deform_attn_cuda.cu:25-158,
+//  ms_deform_im2col_cuda.cuh:928-1332).
+#include "../../include/bm2f_msda.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "msda_fast.cuh"
+#include "msda_generic.cuh"
+
+namespace {
+
+using namespace bm2f;
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+bm2f_msda_tuning_t g_default_tuning = {};
+std::mutex g_tuning_mu;
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    return fail(BM2F_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+// ---- device facts, cached per device (immutable once written) ----------------------------
+struct DevInfo {
+    std::atomic<int> ready{0};
+    int sms = 0;
+    int cc_major = 0;
+};
+DevInfo g_dev[64];
+
+int device_info(int *sms, int *cc_major)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    if (dev < 0 || dev >= 64) return fail(BM2F_ERR_UNSUPPORTED, "device ordinal %d out of range", dev);
+    DevInfo &d = g_dev[dev];
+    if (!d.ready.load(std::memory_order_acquire)) {
+        int s = 0, maj = 0;
+        if ((e = cudaDeviceGetAttribute(&s, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess)
+            return cuda_fail(e, "cudaDeviceGetAttribute(SM count)");
+        if ((e = cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev)) != cudaSuccess)
+            return cuda_fail(e, "cudaDeviceGetAttribute(cc major)");
+        d.sms = s;
+        d.cc_major = maj;
+        d.ready.store(1, std::memory_order_release);
+    }
+    *sms = d.sms;
+    *cc_major = d.cc_major;
+    return BM2F_OK;
+}
+
+// ---- TMA tensor maps ------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// 2-D fp32 matrix (rows x cols, row-major) -> boxes of (box_rows x box_cols).
+int make_map(CUtensorMap *map, const float *base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+             uint32_t box_cols)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(BM2F_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    const cuuint64_t gdim[2] = {cols, rows};
+    const cuuint64_t gstride[1] = {cols * sizeof(float)};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstride, box,
+                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(BM2F_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return BM2F_OK;
+}
+
+// ---- fast-path variant table ----------------------------------------------------------------
+constexpr int kNWarp = 16;
+
+template <typename T, int VEC, int L_, int SW, bool TMA, int CPS>
+cudaError_t launch_fast(bool bwd, const FastParams &p, const CUtensorMap &ml, const CUtensorMap &mw, int grid,
+                        cudaStream_t st)
+{
+    constexpr int G = (SW < kNWarp) ? kNWarp / SW : 1;
+    constexpr int threads = (kNWarp + (TMA ? 1 : 0)) * 32;
+    if (bwd)
+        msda_bwd_fast_kernel<T, VEC, L_, 4, SW, kNWarp, G, TMA, CPS><<<grid, threads, 0, st>>>(p, ml, mw);
+    else
+        msda_fwd_fast_kernel<T, VEC, L_, 4, SW, kNWarp, G, TMA, CPS><<<grid, threads, 0, st>>>(p, ml, mw);
+    return cudaGetLastError();
+}
+
+struct FastChoice {
+    int vec, sw, tma, cps;
+};
+
+#define BM2F_CASE(T, VEC, L_, SW, TMA, CPS)                                              \
+    if (c.vec == VEC && c.sw == SW && c.tma == TMA && c.cps == CPS) {                    \
+        *found = true;                                                                   \
+        return launch_fast<T, VEC, L_, SW, (TMA != 0), CPS>(bwd, p, ml, mw, grid, st);   \
+    }
+
+// Full sweep grid for the Mask2Former shape (L = 3, P = 4, fp32).
+cudaError_t dispatch_f32_l3(const FastChoice &c, bool bwd, const FastParams &p, const CUtensorMap &ml,
+                            const CUtensorMap &mw, int grid, cudaStream_t st, bool *found)
+{
+#define BM2F_ROW(VEC, SW)        \
+    BM2F_CASE(float, VEC, 3, SW, 0, 1) \
+    BM2F_CASE(float, VEC, 3, SW, 0, 2) \
+    BM2F_CASE(float, VEC, 3, SW, 1, 1) \
+    BM2F_CASE(float, VEC, 3, SW, 1, 2)
+    BM2F_ROW(4, 8) BM2F_ROW(4, 16) BM2F_ROW(4, 32)
+    BM2F_ROW(2, 8) BM2F_ROW(2, 16) BM2F_ROW(2, 32)
+    BM2F_ROW(1, 8) BM2F_ROW(1, 16) BM2F_ROW(1, 32)
+#undef BM2F_ROW
+    return cudaSuccess;
+}
+
+// Other level counts and bf16: the default shape of each staging mode only.
+template <typename T, int L_>
+cudaError_t dispatch_default(const FastChoice &c, bool bwd, const FastParams &p, const CUtensorMap &ml,
+                             const CUtensorMap &mw, int grid, cudaStream_t st, bool *found)
+{
+    BM2F_CASE(T, 4, L_, 16, 0, 2)
+    BM2F_CASE(T, 4, L_, 16, 1, 2)
+    return cudaSuccess;
+}
+#undef BM2F_CASE
+
+bm2f_msda_tuning_t resolve_tuning(const bm2f_msda_tuning_t *t)
+{
+    bm2f_msda_tuning_t r;
+    if (t) {
+        r = *t;
+    } else {
+        std::lock_guard<std::mutex> lk(g_tuning_mu);
+        r = g_default_tuning;
+    }
+    return r;
+}
+
+struct Dims {
+    int N, S, M, D, L, Lq, P;
+};
+
+int check_common(const void *value, const int64_t *shapes, const int64_t *start, const void *loc, const void *attn,
+                 const Dims &d, int dtype)
+{
+    if (!value || !shapes || !start || !loc || !attn) return fail(BM2F_ERR_INVALID, "null tensor pointer");
+    if (d.N <= 0 || d.S <= 0 || d.M <= 0 || d.D <= 0 || d.L <= 0 || d.Lq <= 0 || d.P <= 0)
+        return fail(BM2F_ERR_INVALID, "non-positive dimension (N=%d S=%d M=%d D=%d L=%d Lq=%d P=%d)", d.N, d.S, d.M,
+                    d.D, d.L, d.Lq, d.P);
+    if (dtype != BM2F_DTYPE_F32 && dtype != BM2F_DTYPE_F64 && dtype != BM2F_DTYPE_BF16)
+        return fail(BM2F_ERR_INVALID, "unknown dtype %d", dtype);
+    return BM2F_OK;
+}
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// true when the D = 32 fast kernels can take the problem
+bool fast_eligible(const Dims &d, int dtype, const bm2f_msda_tuning_t &t, const void *value, const void *io,
+                   const void *loc, const void *attn)
+{
+    if (t.force_generic) return false;
+    if (d.D != 32 || d.P != 4 || d.M != kHeads) return false;
+    if (dtype == BM2F_DTYPE_F32) {
+        if (d.L < 1 || d.L > 4) return false;
+    } else if (dtype == BM2F_DTYPE_BF16) {
+        if (d.L != 3) return false;
+    } else {
+        return false;
+    }
+    // 32-bit element offsets inside one image and 32-bit query rows
+    if (static_cast<long long>(d.S) * d.M * d.D >= (1ll << 31)) return false;
+    if (static_cast<long long>(d.N) * d.Lq >= (1ll << 31)) return false;
+    if (!aligned16(value) || !aligned16(io) || !aligned16(loc) || !aligned16(attn)) return false;
+    return true;
+}
+
+int run_fast(bool bwd, FastParams p, const Dims &d, int dtype, const bm2f_msda_tuning_t &t, cudaStream_t st)
+{
+    int sms = 0, cc = 0;
+    int rc = device_info(&sms, &cc);
+    if (rc) return rc;
+    if (cc < 10) return fail(BM2F_ERR_CUDA, "this library contains sm_100a code only; device has cc %d.x", cc);
+
+    FastChoice c;
+    c.vec = t.vec ? t.vec : 4;
+    c.sw = t.strip_w ? t.strip_w : 16;
+    c.tma = t.staging ? (t.staging == 1) : 1;
+    c.cps = t.ctas_per_sm ? t.ctas_per_sm : 2;
+    const bool sweepable = (dtype == BM2F_DTYPE_F32 && d.L == 3);
+    if (!sweepable) { c.vec = 4; c.sw = 16; c.cps = 2; }
+
+    const int grid_max = sms * c.cps;
+    int rows = t.rows;
+    if (rows <= 0) {
+        rows = 32;
+        auto jobs = [&](int r) {
+            return static_cast<long long>(d.N) * d.M * ((d.Lq + c.sw * r - 1) / (c.sw * r));
+        };
+        while (rows > 4 && jobs(rows) < 16ll * grid_max) rows >>= 1;
+    }
+    p.rows = rows;
+    p.order = t.order;
+    // upper bound on the job count (level geometry can only add edge strips); the kernel
+    // recomputes the exact number from the device-resident shape table
+    const long long est = static_cast<long long>(d.N) * d.M * ((d.Lq + c.sw * rows - 1) / (c.sw * rows) + 2 * d.L);
+    const int grid = static_cast<int>(est < grid_max ? est : grid_max);
+
+    CUtensorMap ml, mw;
+    memset(&ml, 0, sizeof(ml));
+    memset(&mw, 0, sizeof(mw));
+    if (c.tma) {
+        const int LP = d.L * d.P;
+        const uint64_t rows_total = static_cast<uint64_t>(d.N) * d.Lq;
+        if ((rc = make_map(&ml, p.loc, rows_total, static_cast<uint64_t>(d.M) * LP * 2, c.sw, LP * 2))) return rc;
+        if ((rc = make_map(&mw, p.attn, rows_total, static_cast<uint64_t>(d.M) * LP, c.sw, LP))) return rc;
+    }
+
+    bool found = false;
+    cudaError_t e = cudaSuccess;
+    if (dtype == BM2F_DTYPE_F32) {
+        switch (d.L) {
+        case 1: e = dispatch_default<float, 1>(c, bwd, p, ml, mw, grid, st, &found); break;
+        case 2: e = dispatch_default<float, 2>(c, bwd, p, ml, mw, grid, st, &found); break;
+        case 3: e = dispatch_f32_l3(c, bwd, p, ml, mw, grid, st, &found); break;
+        case 4: e = dispatch_default<float, 4>(c, bwd, p, ml, mw, grid, st, &found); break;
+        }
+    } else {
+        e = dispatch_default<__nv_bfloat16, 3>(c, bwd, p, ml, mw, grid, st, &found);
+    }
+    if (!found)
+        return fail(BM2F_ERR_UNSUPPORTED, "no fast kernel variant vec=%d strip_w=%d staging=%s ctas_per_sm=%d", c.vec,
+                    c.sw, c.tma ? "tma" : "direct", c.cps);
+    if (e != cudaSuccess) return cuda_fail(e, bwd ? "launch msda_bwd_fast_kernel" : "launch msda_fwd_fast_kernel");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return BM2F_OK;
+}
+
+int run_generic(bool bwd, const GenericParams &p, int dtype, cudaStream_t st)
+{
+    if (dtype == BM2F_DTYPE_BF16)
+        return fail(BM2F_ERR_UNSUPPORTED,
+                    "bf16 is implemented for D=32, L=3, P=4 only (got D=%d L=%d P=%d)", p.D, p.L, p.P);
+    const long long warps = static_cast<long long>(p.N) * p.Lq * p.M;
+    const long long blocks = (warps + 7) / 8;
+    if (blocks >= (1ll << 31)) return fail(BM2F_ERR_UNSUPPORTED, "problem too large for the generic kernel");
+    const int grid = static_cast<int>(blocks);
+    if (dtype == BM2F_DTYPE_F32) {
+        if (bwd) msda_bwd_generic_kernel<float><<<grid, 256, 0, st>>>(p);
+        else msda_fwd_generic_kernel<float><<<grid, 256, 0, st>>>(p);
+    } else {
+        if (bwd) msda_bwd_generic_kernel<double><<<grid, 256, 0, st>>>(p);
+        else msda_fwd_generic_kernel<double><<<grid, 256, 0, st>>>(p);
+    }
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, bwd ? "launch msda_bwd_generic_kernel" : "launch msda_fwd_generic_kernel");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return BM2F_OK;
+}
+
+size_t elem_size(int dtype) { return dtype == BM2F_DTYPE_F64 ? 8 : (dtype == BM2F_DTYPE_BF16 ? 2 : 4); }
+size_t loc_elem_size(int dtype) { return dtype == BM2F_DTYPE_F64 ? 8 : 4; }
+
+}  // namespace
+
+extern "C" {
+
+int bm2f_msda_abi_version(void) { return BM2F_MSDA_ABI_VERSION; }
+
+const char *bm2f_msda_build_info(void)
+{
+    return "bm2f_msda sm_100a fast(D=32,P=4,L<=4: f32; L=3: bf16) + generic(f32,f64); built " __DATE__ " " __TIME__;
+}
+
+const char *bm2f_msda_last_error(void) { return g_err; }
+
+uint64_t bm2f_msda_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+void bm2f_msda_set_default_tuning(const bm2f_msda_tuning_t *tuning)
+{
+    std::lock_guard<std::mutex> lk(g_tuning_mu);
+    if (tuning) g_default_tuning = *tuning;
+    else memset(&g_default_tuning, 0, sizeof(g_default_tuning));
+}
+
+int bm2f_msda_check_im2col_step(int batch, int im2col_step)
+{
+    if (batch <= 0 || im2col_step <= 0)
+        return fail(BM2F_ERR_IM2COL_STEP, "batch(%d) and im2col_step(%d) must be positive", batch, im2col_step);
+    const int step = batch < im2col_step ? batch : im2col_step;
+    if (batch % step != 0)
+        return fail(BM2F_ERR_IM2COL_STEP, "batch(%d) must divide im2col_step(%d)", batch, step);
+    return BM2F_OK;
+}
+
+int bm2f_msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                      const void *sampling_loc, const void *attn_weight, void *output, int batch, int spatial_size,
+                      int num_heads, int channels, int num_levels, int num_query, int num_point, int dtype,
+                      const bm2f_msda_tuning_t *tuning, void *stream)
+{
+    const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+    int rc = check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, d, dtype);
+    if (rc) return rc;
+    if (!output) return fail(BM2F_ERR_INVALID, "null output pointer");
+    if (num_levels > kMaxLevels) return fail(BM2F_ERR_UNSUPPORTED, "num_levels %d > %d", num_levels, kMaxLevels);
+    const bm2f_msda_tuning_t t = resolve_tuning(tuning);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    if (fast_eligible(d, dtype, t, value, output, sampling_loc, attn_weight)) {
+        FastParams p{};
+        p.value = value; p.shapes = spatial_shapes; p.start = level_start_index;
+        p.loc = static_cast<const float *>(sampling_loc); p.attn = static_cast<const float *>(attn_weight);
+        p.out = output;
+        p.N = d.N; p.S = d.S; p.M = d.M; p.Lq = d.Lq;
+        return run_fast(false, p, d, dtype, t, st);
+    }
+    GenericParams g{};
+    g.value = value; g.shapes = spatial_shapes; g.start = level_start_index; g.loc = sampling_loc;
+    g.attn = attn_weight; g.out = output;
+    g.N = d.N; g.S = d.S; g.M = d.M; g.D = d.D; g.L = d.L; g.Lq = d.Lq; g.P = d.P;
+    return run_generic(false, g, dtype, st);
+}
+
+int bm2f_msda_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                       const void *sampling_loc, const void *attn_weight, const void *grad_output, void *grad_value,
+                       void *grad_sampling_loc, void *grad_attn_weight, int batch, int spatial_size, int num_heads,
+                       int channels, int num_levels, int num_query, int num_point, int dtype,
+                       const bm2f_msda_tuning_t *tuning, void *stream)
+{
+    const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+    int rc = check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, d, dtype);
+    if (rc) return rc;
+    if (!grad_output || !grad_value || !grad_sampling_loc || !grad_attn_weight)
+        return fail(BM2F_ERR_INVALID, "null gradient pointer");
+    if (num_levels > kMaxLevels) return fail(BM2F_ERR_UNSUPPORTED, "num_levels %d > %d", num_levels, kMaxLevels);
+    const bm2f_msda_tuning_t t = resolve_tuning(tuning);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    // grad_value accumulates through atomics: zero it first (reference: at::zeros_like, .cu:126)
+    const size_t gv_bytes = static_cast<size_t>(d.N) * d.S * d.M * d.D * elem_size(dtype);
+    cudaError_t e = cudaMemsetAsync(grad_value, 0, gv_bytes, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(grad_value)");
+
+    if (fast_eligible(d, dtype, t, value, grad_value, sampling_loc, attn_weight) && aligned16(grad_output) &&
+        aligned16(grad_sampling_loc) && aligned16(grad_attn_weight)) {
+        FastParams p{};
+        p.value = value; p.shapes = spatial_shapes; p.start = level_start_index;
+        p.loc = static_cast<const float *>(sampling_loc); p.attn = static_cast<const float *>(attn_weight);
+        p.grad_out = grad_output; p.grad_value = grad_value;
+        p.grad_loc = static_cast<float *>(grad_sampling_loc); p.grad_attn = static_cast<float *>(grad_attn_weight);
+        p.N = d.N; p.S = d.S; p.M = d.M; p.Lq = d.Lq;
+        return run_fast(true, p, d, dtype, t, st);
+    }
+    GenericParams g{};
+    g.value = value; g.shapes = spatial_shapes; g.start = level_start_index; g.loc = sampling_loc;
+    g.attn = attn_weight; g.grad_out = grad_output; g.grad_value = grad_value; g.grad_loc = grad_sampling_loc;
+    g.grad_attn = grad_attn_weight;
+    g.N = d.N; g.S = d.S; g.M = d.M; g.D = d.D; g.L = d.L; g.Lq = d.Lq; g.P = d.P;
+    return run_generic(true, g, dtype, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-buffer entry: chunked, double-buffered H2D -> kernels -> D2H.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct HostPath {
+    std::mutex mu;
+    int dev = -1;
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    void *ws[2] = {nullptr, nullptr};
+    size_t ws_bytes = 0;
+    int64_t *tabs = nullptr;  // shapes (2L) + start (L)
+} g_host;
+
+size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+}  // namespace
+
+int bm2f_msda_forward_backward_host(const void *value_host, const int64_t *spatial_shapes_host,
+                                    const int64_t *level_start_index_host, const void *sampling_loc_host,
+                                    const void *attn_weight_host, const void *grad_output_host, void *output_host,
+                                    void *grad_value_host, void *grad_sampling_loc_host, void *grad_attn_weight_host,
+                                    int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                                    int num_query, int num_point, int dtype, const bm2f_msda_tuning_t *tuning)
+{
+    const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+    int rc = check_common(value_host, spatial_shapes_host, level_start_index_host, sampling_loc_host,
+                          attn_weight_host, d, dtype);
+    if (rc) return rc;
+    if (num_levels > kMaxLevels) return fail(BM2F_ERR_UNSUPPORTED, "num_levels %d > %d", num_levels, kMaxLevels);
+    const bool bwd = grad_output_host != nullptr;
+    const size_t e = elem_size(dtype), el = loc_elem_size(dtype);
+    const size_t v_img = static_cast<size_t>(d.S) * d.M * d.D * e;
+    const size_t o_img = static_cast<size_t>(d.Lq) * d.M * d.D * e;
+    const size_t l_img = static_cast<size_t>(d.Lq) * d.M * d.L * d.P * 2 * el;
+    const size_t a_img = static_cast<size_t>(d.Lq) * d.M * d.L * d.P * el;
+
+    // images per chunk: aim at >= 4 chunks so the two streams overlap copies and kernels
+    int chunk = d.N >= 8 ? d.N / 8 : 1;
+    const size_t slot_bytes = static_cast<size_t>(chunk) *
+                              (align256(v_img) + align256(l_img) + align256(a_img) + align256(o_img) +
+                               (bwd ? align256(o_img) + align256(v_img) + align256(l_img) + align256(a_img) : 0)) +
+                              4096;
+
+    std::lock_guard<std::mutex> lk(g_host.mu);
+    int dev = 0;
+    cudaError_t ce = cudaGetDevice(&dev);
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaGetDevice");
+    if (g_host.dev != dev || g_host.ws_bytes < slot_bytes) {
+        for (int i = 0; i < 2; ++i) {
+            if (g_host.ws[i]) cudaFree(g_host.ws[i]);
+            g_host.ws[i] = nullptr;
+            if (!g_host.streams[i] || g_host.dev != dev) {
+                if ((ce = cudaStreamCreateWithFlags(&g_host.streams[i], cudaStreamNonBlocking)) != cudaSuccess)
+                    return cuda_fail(ce, "cudaStreamCreate");
+            }
+            if ((ce = cudaMalloc(&g_host.ws[i], slot_bytes)) != cudaSuccess) {
+                g_host.ws_bytes = 0;
+                return cuda_fail(ce, "cudaMalloc(host-path workspace)");
+            }
+        }
+        if (!g_host.tabs || g_host.dev != dev) {
+            if ((ce = cudaMalloc(reinterpret_cast<void **>(&g_host.tabs), sizeof(int64_t) * 3 * kMaxLevels)) !=
+                cudaSuccess)
+                return cuda_fail(ce, "cudaMalloc(level tables)");
+        }
+        g_host.ws_bytes = slot_bytes;
+        g_host.dev = dev;
+    }
+    cudaStream_t s0 = g_host.streams[0];
+    if ((ce = cudaMemcpyAsync(g_host.tabs, spatial_shapes_host, sizeof(int64_t) * 2 * d.L, cudaMemcpyHostToDevice,
+                              s0)) != cudaSuccess)
+        return cuda_fail(ce, "H2D spatial_shapes");
+    if ((ce = cudaMemcpyAsync(g_host.tabs + 2 * kMaxLevels, level_start_index_host, sizeof(int64_t) * d.L,
+                              cudaMemcpyHostToDevice, s0)) != cudaSuccess)
+        return cuda_fail(ce, "H2D level_start_index");
+    if ((ce = cudaStreamSynchronize(s0)) != cudaSuccess) return cuda_fail(ce, "sync level tables");
+    const int64_t *d_shapes = g_host.tabs, *d_start = g_host.tabs + 2 * kMaxLevels;
+
+    auto hp = [](const void *base, size_t off) { return static_cast<const char *>(base) + off; };
+    auto hpw = [](void *base, size_t off) { return static_cast<char *>(base) + off; };
+
+    int slot = 0;
+    for (int b0 = 0; b0 < d.N; b0 += chunk, slot ^= 1) {
+        const int nb = (d.N - b0 < chunk) ? d.N - b0 : chunk;
+        cudaStream_t st = g_host.streams[slot];
+        char *w = static_cast<char *>(g_host.ws[slot]);
+        auto take = [&](size_t per_img) { char *r = w; w += static_cast<size_t>(chunk) * align256(per_img); return r; };
+        char *dv = take(v_img), *dl = take(l_img), *da = take(a_img), *dout = take(o_img);
+        char *dgo = nullptr, *dgv = nullptr, *dgl = nullptr, *dga = nullptr;
+        if (bwd) { dgo = take(o_img); dgv = take(v_img); dgl = take(l_img); dga = take(a_img); }
+
+#define BM2F_CP(dst, src, bytes, kind, what)                                                           \
+    if ((ce = cudaMemcpyAsync(dst, src, bytes, kind, st)) != cudaSuccess) return cuda_fail(ce, what);
+        BM2F_CP(dv, hp(value_host, b0 * v_img), nb * v_img, cudaMemcpyHostToDevice, "H2D value")
+        BM2F_CP(dl, hp(sampling_loc_host, b0 * l_img), nb * l_img, cudaMemcpyHostToDevice, "H2D sampling_loc")
+        BM2F_CP(da, hp(attn_weight_host, b0 * a_img), nb * a_img, cudaMemcpyHostToDevice, "H2D attn_weight")
+        rc = bm2f_msda_forward(dv, d_shapes, d_start, dl, da, dout, nb, d.S, d.M, d.D, d.L, d.Lq, d.P, dtype, tuning,
+                               st);
+        if (rc) return rc;
+        if (output_host) BM2F_CP(hpw(output_host, b0 * o_img), dout, nb * o_img, cudaMemcpyDeviceToHost, "D2H output")
+        if (bwd) {
+            BM2F_CP(dgo, hp(grad_output_host, b0 * o_img), nb * o_img, cudaMemcpyHostToDevice, "H2D grad_output")
+            rc = bm2f_msda_backward(dv, d_shapes, d_start, dl, da, dgo, dgv, dgl, dga, nb, d.S, d.M, d.D, d.L, d.Lq,
+                                    d.P, dtype, tuning, st);
+            if (rc) return rc;
+            if (grad_value_host)
+                BM2F_CP(hpw(grad_value_host, b0 * v_img), dgv, nb * v_img, cudaMemcpyDeviceToHost, "D2H grad_value")
+            if (grad_sampling_loc_host)
+                BM2F_CP(hpw(grad_sampling_loc_host, b0 * l_img), dgl, nb * l_img, cudaMemcpyDeviceToHost,
+                        "D2H grad_sampling_loc")
+            if (grad_attn_weight_host)
+                BM2F_CP(hpw(grad_attn_weight_host, b0 * a_img), dga, nb * a_img, cudaMemcpyDeviceToHost,
+                        "D2H grad_attn_weight")
+        }
+#undef BM2F_CP
+    }
+    for (int i = 0; i < 2; ++i)
+        if ((ce = cudaStreamSynchronize(g_host.streams[i])) != cudaSuccess) return cuda_fail(ce, "host-path sync");
+    return BM2F_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,412 @@
+// D = 32 fast path: persistent, strip-walking forward / backward sampling kernels for sm_100a.
+//
+// Work decomposition:
+//   job   = (image b, head m, query-level k, strip c, row chunk r): a column strip of SW
+//           consecutive queries walked down `rows` image rows.  One head per job keeps the L1
+//           working set to the bilinear footprints of ONE head around a slowly moving window,
+//           so corner lines fetched for one row are re-used by the next rows from L1.
+//   stage = one strip row: SW consecutive queries of head m.  Their sampling locations
+//           (LP x 2 floats) and attention weights (LP floats) are a strided 2-D box of the
+//           (N*Lq, M*LP*{2,1}) matrices: ONE TMA tensor-map copy each, landed in a shared-memory
+//           ring by a producer warp and consumed through full/empty mbarriers.
+//   warp  = one (query, head) at a time.  The 32 lanes are LG groups of LPC lanes; a group owns
+//           one sampling point, its LPC lanes span the 32 head channels with VEC-wide loads
+//           (VEC = 4: 8 lanes x 128 bit = one 128-byte line per corner, LG = 4 points in flight).
+//
+// When the queries are not the pixels of the levels (Lq != sum H*W) the same kernels walk the
+// queries in plain 1-D order.
+#pragma once
+
+#include "msda_common.cuh"
+
+namespace bm2f {
+
+constexpr int kHeads = 8;   // the fast path is compiled for M = 8 (d_model 256 = 8 x 32)
+
+struct FastParams {
+    const void *value;           // (N,S,M,32)
+    const int64_t *shapes;       // (L,2) device
+    const int64_t *start;        // (L)   device
+    const float *loc;            // (N,Lq,M,L,P,2)
+    const float *attn;           // (N,Lq,M,L,P)
+    const void *grad_out;        // (N,Lq,M,32)            bwd only
+    void *out;                   // (N,Lq,M,32)            fwd only
+    void *grad_value;            // (N,S,M,32)             bwd only
+    float *grad_loc;             // like loc               bwd only
+    float *grad_attn;            // like attn              bwd only
+    int N, S, M, Lq;
+    int rows;                    // strip rows per job
+    int order;                   // 1 = force 1-D query order
+};
+
+struct QLevel {
+    int qstart, Hq, Wq, nstrips, nchunks, job_base;
+};
+
+template <int L_>
+struct Tabs {
+    int H[L_], W[L_], start[L_];
+    QLevel ql[L_];
+    int nql;
+    int jobs_per_bm;
+};
+
+constexpr int kStages = 8;
+
+template <int L_, int SW>
+__device__ __forceinline__ void build_tabs(Tabs<L_> &t, const FastParams &p)
+{
+    // one thread; L_ <= 16 so this is a few dozen instructions
+    int total = 0;
+    for (int l = 0; l < L_; ++l) {
+        t.H[l] = static_cast<int>(p.shapes[2 * l]);
+        t.W[l] = static_cast<int>(p.shapes[2 * l + 1]);
+        t.start[l] = static_cast<int>(p.start[l]);
+        total += t.H[l] * t.W[l];
+    }
+    int jobs = 0;
+    if (p.order == 0 && total == p.Lq) {
+        // queries are the pixels of the levels (encoder self-attention): walk level geometry
+        int q0 = 0;
+        for (int l = 0; l < L_; ++l) {
+            QLevel &q = t.ql[l];
+            q.qstart = q0;
+            q.Hq = t.H[l];
+            q.Wq = t.W[l];
+            q.nstrips = (q.Wq + SW - 1) / SW;
+            q.nchunks = (q.Hq + p.rows - 1) / p.rows;
+            q.job_base = jobs;
+            jobs += q.nstrips * q.nchunks;
+            q0 += q.Hq * q.Wq;
+        }
+        t.nql = L_;
+    } else {
+        QLevel &q = t.ql[0];
+        q.qstart = 0;
+        q.Wq = SW;
+        q.Hq = (p.Lq + SW - 1) / SW;
+        q.nstrips = 1;
+        q.nchunks = (q.Hq + p.rows - 1) / p.rows;
+        q.job_base = 0;
+        jobs = q.nchunks;
+        t.nql = 1;
+    }
+    t.jobs_per_bm = jobs;
+}
+
+// Enumerates the stages of this CTA in a fixed order; producer and consumers call it with the
+// same arguments so they agree on the stage sequence without exchanging descriptors.
+template <int L_, int SW, typename F>
+__device__ __forceinline__ void for_each_stage(const Tabs<L_> &t, const FastParams &p, F &&f)
+{
+    const int per_b = kHeads * t.jobs_per_bm;
+    const int total_jobs = p.N * per_b;
+    int s = 0;
+    for (int j = blockIdx.x; j < total_jobs; j += gridDim.x) {
+        const int b = j / per_b;
+        const int r = j - b * per_b;
+        const int jj = r / kHeads;
+        const int m = r - jj * kHeads;
+        int k = 0;
+        while (k + 1 < t.nql && jj >= t.ql[k + 1].job_base) ++k;
+        const QLevel ql = t.ql[k];
+        const int tt = jj - ql.job_base;
+        const int chunk = tt / ql.nstrips;
+        const int strip = tt - chunk * ql.nstrips;
+        const int y_end = min(ql.Hq, (chunk + 1) * p.rows);
+        const int x0 = strip * SW;
+        const int nq_row = min(SW, ql.Wq - x0);
+        for (int y = chunk * p.rows; y < y_end; ++y, ++s) {
+            const int q_base = ql.qstart + y * ql.Wq + x0;
+            f(s, b, m, q_base, min(nq_row, p.Lq - q_base));
+        }
+    }
+}
+
+template <int SW, int LP>
+struct StageLayout {
+    static constexpr int kLocBytes = ((SW * LP * 8 + 127) / 128) * 128;
+    static constexpr int kWBytes = ((SW * LP * 4 + 127) / 128) * 128;
+    static constexpr int kBytes = kLocBytes + kWBytes;
+    static constexpr int kTxBytes = SW * LP * 12;  // what the two TMA boxes deliver
+};
+
+// Shared-memory state of the loc/weight ring + its producer.
+template <int L_, int P_, int SW, int WPG>
+struct Ring {
+    using Lay = StageLayout<SW, L_ * P_>;
+    alignas(128) unsigned char data[kStages * Lay::kBytes];
+    alignas(8) uint64_t full[kStages];
+    alignas(8) uint64_t empty[kStages];
+
+    __device__ __forceinline__ void init()
+    {
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], WPG);
+        }
+        fence_mbar_init();
+    }
+    __device__ __forceinline__ const float2 *loc(int slot, int qi) const
+    {
+        return reinterpret_cast<const float2 *>(data + slot * Lay::kBytes) + qi * (L_ * P_);
+    }
+    __device__ __forceinline__ const float *w(int slot, int qi) const
+    {
+        return reinterpret_cast<const float *>(data + slot * Lay::kBytes + Lay::kLocBytes) + qi * (L_ * P_);
+    }
+    // Producer (one lane): keep the ring full with the CTA's stage sequence.
+    __device__ __forceinline__ void produce(const Tabs<L_> &t, const FastParams &p, const CUtensorMap *tm_loc,
+                                            const CUtensorMap *tm_w)
+    {
+        constexpr int LP = L_ * P_;
+        for_each_stage<L_, SW>(t, p, [&](int s, int b, int m, int q_base, int) {
+            const int slot = s % kStages;
+            mbar_wait(&empty[slot], ((s / kStages) & 1) ^ 1);
+            mbar_arrive_expect_tx(&full[slot], Lay::kTxBytes);
+            unsigned char *dst = data + slot * Lay::kBytes;
+            const int row = b * p.Lq + q_base;
+            tma_load_2d(dst, tm_loc, m * LP * 2, row, &full[slot]);
+            tma_load_2d(dst + Lay::kLocBytes, tm_w, m * LP, row, &full[slot]);
+        });
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// Forward
+// ------------------------------------------------------------------------------------------
+template <typename T, int VEC, int L_, int P_, int SW, int NWARP, int G, bool TMA, int CPS>
+__global__ void __launch_bounds__((NWARP + (TMA ? 1 : 0)) * 32, CPS)
+msda_fwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_loc,
+                     const __grid_constant__ CUtensorMap tm_w)
+{
+    constexpr int D = 32, LP = L_ * P_, LPC = D / VEC, LG = 32 / LPC, NIT = LP / LG, WPG = NWARP / G;
+    static_assert(P_ % LG == 0, "a lane-group iteration must stay inside one level");
+    static_assert(NWARP % G == 0, "");
+
+    __shared__ Tabs<L_> tabs;
+    __shared__ Ring<L_, P_, TMA ? SW : 1, WPG> ring;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        build_tabs<L_, SW>(tabs, p);
+        if (TMA) {
+            ring.init();
+            tma_prefetch_desc(&tm_loc);
+            tma_prefetch_desc(&tm_w);
+        }
+    }
+    __syncthreads();
+
+    if (TMA && warp == NWARP) {
+        if (lane == 0) ring.produce(tabs, p, &tm_loc, &tm_w);
+        return;
+    }
+
+    int H[L_], W[L_], st[L_];
+    float Hf[L_], Wf[L_];
+#pragma unroll
+    for (int l = 0; l < L_; ++l) {
+        H[l] = tabs.H[l]; W[l] = tabs.W[l]; st[l] = tabs.start[l];
+        Hf[l] = static_cast<float>(H[l]); Wf[l] = static_cast<float>(W[l]);
+    }
+    const int g = warp / WPG, wi = warp % WPG;
+    const int lg = lane / LPC, sub = lane % LPC;
+    constexpr int MD = kHeads * D;  // elements between horizontally adjacent pixels (immediate offset)
+    const T *value = static_cast<const T *>(p.value);
+    T *out = static_cast<T *>(p.out);
+
+    for_each_stage<L_, SW>(tabs, p, [&](int s, int b, int m, int q_base, int nq) {
+        if (G > 1 && (s % G) != g) return;
+        const int slot = s % kStages;
+        if (TMA) mbar_wait(&ring.full[slot], (s / kStages) & 1);
+        const T *vlane = value + (static_cast<size_t>(b) * p.S * kHeads + m) * D + sub * VEC;
+        for (int qi = wi; qi < nq; qi += WPG) {
+            const int q = q_base + qi;
+            float xs[NIT], ys[NIT], ws[NIT];
+            if (TMA) {
+                const float2 *sl = ring.loc(slot, qi);
+                const float *sw = ring.w(slot, qi);
+#pragma unroll
+                for (int it = 0; it < NIT; ++it) {
+                    const float2 t = sl[it * LG + lg];
+                    xs[it] = t.x; ys[it] = t.y; ws[it] = sw[it * LG + lg];
+                }
+            } else {
+                const size_t k0 = ((static_cast<size_t>(b) * p.Lq + q) * kHeads + m) * LP;
+#pragma unroll
+                for (int it = 0; it < NIT; ++it) {
+                    const float2 t = __ldg(reinterpret_cast<const float2 *>(p.loc) + k0 + it * LG + lg);
+                    xs[it] = t.x; ys[it] = t.y; ws[it] = __ldg(p.attn + k0 + it * LG + lg);
+                }
+            }
+            float acc[VEC];
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int l = (it * LG) / P_;
+                const Footprint f = make_footprint(xs[it], ys[it], H[l], W[l], Hf[l], Wf[l]);
+                const T *row0 = vlane + static_cast<long long>(st[l] + f.y0 * W[l] + f.x0) * MD;
+                const T *row1 = row0 + W[l] * MD;
+                const T *corner[4] = {row0, row0 + MD, row1, row1 + MD};
+                const float wy[2] = {ws[it] * f.hh, ws[it] * f.lh};
+                const float wx[2] = {f.hw, f.lw};
+                float v[4][VEC];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                    for (int c = 0; c < VEC; ++c) v[k][c] = 0.f;
+                    if (f.ok[k]) VecIO<T, VEC>::load(corner[k], v[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float cw = wy[k >> 1] * wx[k & 1];   // v == 0 for dropped corners
+#pragma unroll
+                    for (int c = 0; c < VEC; ++c) acc[c] = fmaf(cw, v[k][c], acc[c]);
+                }
+            }
+            // fold the LG point groups
+#pragma unroll
+            for (int o = LPC; o < 32; o <<= 1)
+#pragma unroll
+                for (int c = 0; c < VEC; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+            if (lg == 0)
+                VecIO<T, VEC>::store(out + ((static_cast<size_t>(b) * p.Lq + q) * kHeads + m) * D + sub * VEC, acc);
+        }
+        if (TMA) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ring.empty[slot]);
+        }
+    });
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward
+// ------------------------------------------------------------------------------------------
+template <typename T, int VEC, int L_, int P_, int SW, int NWARP, int G, bool TMA, int CPS>
+__global__ void __launch_bounds__((NWARP + (TMA ? 1 : 0)) * 32, CPS)
+msda_bwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_loc,
+                     const __grid_constant__ CUtensorMap tm_w)
+{
+    constexpr int D = 32, LP = L_ * P_, LPC = D / VEC, LG = 32 / LPC, NIT = LP / LG, WPG = NWARP / G;
+    static_assert(P_ % LG == 0, "a lane-group iteration must stay inside one level");
+
+    __shared__ Tabs<L_> tabs;
+    __shared__ Ring<L_, P_, TMA ? SW : 1, WPG> ring;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        build_tabs<L_, SW>(tabs, p);
+        if (TMA) {
+            ring.init();
+            tma_prefetch_desc(&tm_loc);
+            tma_prefetch_desc(&tm_w);
+        }
+    }
+    __syncthreads();
+
+    if (TMA && warp == NWARP) {
+        if (lane == 0) ring.produce(tabs, p, &tm_loc, &tm_w);
+        return;
+    }
+
+    int H[L_], W[L_], st[L_];
+    float Hf[L_], Wf[L_];
+#pragma unroll
+    for (int l = 0; l < L_; ++l) {
+        H[l] = tabs.H[l]; W[l] = tabs.W[l]; st[l] = tabs.start[l];
+        Hf[l] = static_cast<float>(H[l]); Wf[l] = static_cast<float>(W[l]);
+    }
+    const int g = warp / WPG, wi = warp % WPG;
+    const int lg = lane / LPC, sub = lane % LPC;
+    constexpr int MD = kHeads * D;  // elements between horizontally adjacent pixels (immediate offset)
+    const T *value = static_cast<const T *>(p.value);
+    const T *grad_out = static_cast<const T *>(p.grad_out);
+    T *grad_value = static_cast<T *>(p.grad_value);
+
+    for_each_stage<L_, SW>(tabs, p, [&](int s, int b, int m, int q_base, int nq) {
+        if (G > 1 && (s % G) != g) return;
+        const int slot = s % kStages;
+        if (TMA) mbar_wait(&ring.full[slot], (s / kStages) & 1);
+        const size_t img = (static_cast<size_t>(b) * p.S * kHeads + m) * D + sub * VEC;
+        const T *vlane = value + img;
+        T *gvlane = grad_value + img;
+        for (int qi = wi; qi < nq; qi += WPG) {
+            const int q = q_base + qi;
+            const size_t qm = (static_cast<size_t>(b) * p.Lq + q) * kHeads + m;
+            float go[VEC];
+            VecIO<T, VEC>::load(grad_out + qm * D + sub * VEC, go);
+            float xs[NIT], ys[NIT], ws[NIT];
+            if (TMA) {
+                const float2 *sl = ring.loc(slot, qi);
+                const float *sw = ring.w(slot, qi);
+#pragma unroll
+                for (int it = 0; it < NIT; ++it) {
+                    const float2 t = sl[it * LG + lg];
+                    xs[it] = t.x; ys[it] = t.y; ws[it] = sw[it * LG + lg];
+                }
+            } else {
+#pragma unroll
+                for (int it = 0; it < NIT; ++it) {
+                    const float2 t = __ldg(reinterpret_cast<const float2 *>(p.loc) + qm * LP + it * LG + lg);
+                    xs[it] = t.x; ys[it] = t.y; ws[it] = __ldg(p.attn + qm * LP + it * LG + lg);
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int l = (it * LG) / P_;
+                const Footprint f = make_footprint(xs[it], ys[it], H[l], W[l], Hf[l], Wf[l]);
+                const long long e00 = static_cast<long long>(st[l] + f.y0 * W[l] + f.x0) * MD;
+                const long long eoff[4] = {e00, e00 + MD, e00 + W[l] * MD, e00 + W[l] * MD + MD};
+                const float wy[2] = {f.hh, f.lh};
+                const float wx[2] = {f.hw, f.lw};
+                float v[4][VEC];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                    for (int c = 0; c < VEC; ++c) v[k][c] = 0.f;
+                    if (f.ok[k]) VecIO<T, VEC>::load(vlane + eoff[k], v[k]);
+                }
+                // scatter grad_value; dot products of grad_out with the four corners
+                float t[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (f.ok[k]) {
+                        const float cwk = ws[it] * wy[k >> 1] * wx[k & 1];
+                        float r[VEC];
+#pragma unroll
+                        for (int c = 0; c < VEC; ++c) r[c] = cwk * go[c];
+                        VecIO<T, VEC>::red_add(gvlane + eoff[k], r);
+                    }
+                    t[k] = 0.f;
+#pragma unroll
+                    for (int c = 0; c < VEC; ++c) t[k] = fmaf(go[c], v[k][c], t[k]);
+                }
+                // <grad_out, sample>, d/dw_im, d/dh_im restricted to this lane's channels
+                float pa = f.hh * (f.hw * t[0] + f.lw * t[1]) + f.lh * (f.hw * t[2] + f.lw * t[3]);
+                float px = f.hh * (t[1] - t[0]) + f.lh * (t[3] - t[2]);
+                float py = f.hw * (t[2] - t[0]) + f.lw * (t[3] - t[1]);
+#pragma unroll
+                for (int o = LPC / 2; o > 0; o >>= 1) {
+                    pa += __shfl_xor_sync(0xffffffffu, pa, o);
+                    px += __shfl_xor_sync(0xffffffffu, px, o);
+                    py += __shfl_xor_sync(0xffffffffu, py, o);
+                }
+                if (sub == 0) {
+                    // skipped points leave zeros (reference outputs are zero-initialised)
+                    const size_t k = qm * LP + it * LG + lg;
+                    p.grad_attn[k] = f.in_range ? pa : 0.f;
+                    reinterpret_cast<float2 *>(p.grad_loc)[k] =
+                        f.in_range ? make_float2(Wf[l] * ws[it] * px, Hf[l] * ws[it] * py) : make_float2(0.f, 0.f);
+                }
+            }
+        }
+        if (TMA) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ring.empty[slot]);
+        }
+    });
+}
+
+}  // namespace bm2f

@@ -1,0 +1,149 @@
+// Python extension module "MultiScaleDeformableAttention": the reference's binding surface
+// (ops/src/vision.cpp:18-21) on top of the C ABI in include/bm2f_msda.h.
+//
+//   ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+//                          im2col_step) -> Tensor[N, Lq, M*D]
+//   ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+//                           grad_output, im2col_step) -> [grad_value, grad_sampling_loc, grad_attn_weight]
+//
+// Same positional signatures, same preconditions and error type (RuntimeError) as
+// ms_deform_attn_cuda_forward/backward (ops/src/cuda/ms_deform_attn_cuda.cu:25-158) and the
+// CPU/CUDA dispatch in ops/src/ms_deform_attn.h:25-66.  This file is plumbing only: it checks
+// tensors, allocates the results with the caller's options (so torch's caching allocator and
+// stream semantics hold), picks the current stream and device, and forwards raw pointers.
+// PyTorch appears nowhere below this file.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include <vector>
+
+#include "../../include/bm2f_msda.h"
+
+namespace {
+
+int dtype_code(const at::Tensor &value)
+{
+    switch (value.scalar_type()) {
+    case at::kFloat: return BM2F_DTYPE_F32;
+    case at::kDouble: return BM2F_DTYPE_F64;
+    case at::kBFloat16: return BM2F_DTYPE_BF16;
+    default:
+        TORCH_CHECK(false, "ms_deform_attn: unsupported dtype ", value.scalar_type(),
+                    " (float32, float64 and bfloat16 are implemented)");
+    }
+    return -1;
+}
+
+struct Checked {
+    at::Tensor loc, attn;  // possibly converted (bf16 value path keeps float32 locations/weights)
+    int N, S, M, D, L, Lq, P, dtype;
+};
+
+Checked check_inputs(const at::Tensor &value, const at::Tensor &spatial_shapes, const at::Tensor &level_start_index,
+                     const at::Tensor &sampling_loc, const at::Tensor &attn_weight, int im2col_step)
+{
+    // reference: ms_deform_attn.h:40-43 / 62-65
+    TORCH_CHECK(value.is_cuda(), "Not implemented on the CPU");
+    // reference: ms_deform_attn_cuda.cu:33-43
+    TORCH_CHECK(value.is_contiguous(), "value tensor has to be contiguous");
+    TORCH_CHECK(spatial_shapes.is_contiguous(), "spatial_shapes tensor has to be contiguous");
+    TORCH_CHECK(level_start_index.is_contiguous(), "level_start_index tensor has to be contiguous");
+    TORCH_CHECK(sampling_loc.is_contiguous(), "sampling_loc tensor has to be contiguous");
+    TORCH_CHECK(attn_weight.is_contiguous(), "attn_weight tensor has to be contiguous");
+    TORCH_CHECK(spatial_shapes.is_cuda(), "spatial_shapes must be a CUDA tensor");
+    TORCH_CHECK(level_start_index.is_cuda(), "level_start_index must be a CUDA tensor");
+    TORCH_CHECK(sampling_loc.is_cuda(), "sampling_loc must be a CUDA tensor");
+    TORCH_CHECK(attn_weight.is_cuda(), "attn_weight must be a CUDA tensor");
+    // the reference reinterprets both tables as int64 (.cu:72-73); make that explicit
+    TORCH_CHECK(spatial_shapes.scalar_type() == at::kLong, "spatial_shapes must be int64");
+    TORCH_CHECK(level_start_index.scalar_type() == at::kLong, "level_start_index must be int64");
+    TORCH_CHECK(value.dim() == 4, "value must be (N, S, M, D)");
+    TORCH_CHECK(sampling_loc.dim() == 6 && sampling_loc.size(5) == 2, "sampling_loc must be (N, Lq, M, L, P, 2)");
+    TORCH_CHECK(attn_weight.dim() == 5, "attn_weight must be (N, Lq, M, L, P)");
+    TORCH_CHECK(spatial_shapes.dim() == 2 && spatial_shapes.size(1) == 2, "spatial_shapes must be (L, 2)");
+
+    Checked c;
+    c.N = static_cast<int>(value.size(0));
+    c.S = static_cast<int>(value.size(1));
+    c.M = static_cast<int>(value.size(2));
+    c.D = static_cast<int>(value.size(3));
+    c.L = static_cast<int>(spatial_shapes.size(0));
+    c.Lq = static_cast<int>(sampling_loc.size(1));
+    c.P = static_cast<int>(sampling_loc.size(4));
+    TORCH_CHECK(level_start_index.numel() == c.L, "level_start_index must have one entry per level");
+    TORCH_CHECK(sampling_loc.size(0) == c.N && sampling_loc.size(2) == c.M && sampling_loc.size(3) == c.L,
+                "sampling_loc shape does not match value / spatial_shapes");
+    TORCH_CHECK(attn_weight.size(0) == c.N && attn_weight.size(1) == c.Lq && attn_weight.size(2) == c.M &&
+                    attn_weight.size(3) == c.L && attn_weight.size(4) == c.P,
+                "attn_weight shape does not match sampling_loc");
+    // reference: .cu:53-57
+    TORCH_CHECK(bm2f_msda_check_im2col_step(c.N, im2col_step) == BM2F_OK, bm2f_msda_last_error());
+
+    c.dtype = dtype_code(value);
+    if (c.dtype == BM2F_DTYPE_BF16) {
+        // bf16 values, fp32 sampling locations / weights (see include/bm2f_msda.h)
+        c.loc = sampling_loc.scalar_type() == at::kFloat ? sampling_loc : sampling_loc.to(at::kFloat);
+        c.attn = attn_weight.scalar_type() == at::kFloat ? attn_weight : attn_weight.to(at::kFloat);
+    } else {
+        TORCH_CHECK(sampling_loc.scalar_type() == value.scalar_type() &&
+                        attn_weight.scalar_type() == value.scalar_type(),
+                    "sampling_loc / attn_weight must have the dtype of value");
+        c.loc = sampling_loc;
+        c.attn = attn_weight;
+    }
+    return c;
+}
+
+at::Tensor ms_deform_attn_forward(const at::Tensor &value, const at::Tensor &spatial_shapes,
+                                  const at::Tensor &level_start_index, const at::Tensor &sampling_loc,
+                                  const at::Tensor &attn_weight, const int im2col_step)
+{
+    const Checked c = check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step);
+    const c10::cuda::CUDAGuard guard(value.device());
+    auto output = at::empty({c.N, c.Lq, c.M * c.D}, value.options());  // every element is written
+    const int rc = bm2f_msda_forward(value.data_ptr(), spatial_shapes.data_ptr<int64_t>(),
+                                     level_start_index.data_ptr<int64_t>(), c.loc.data_ptr(), c.attn.data_ptr(),
+                                     output.data_ptr(), c.N, c.S, c.M, c.D, c.L, c.Lq, c.P, c.dtype, nullptr,
+                                     at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == BM2F_OK, "ms_deform_attn_forward: ", bm2f_msda_last_error());
+    return output;
+}
+
+std::vector<at::Tensor> ms_deform_attn_backward(const at::Tensor &value, const at::Tensor &spatial_shapes,
+                                                const at::Tensor &level_start_index, const at::Tensor &sampling_loc,
+                                                const at::Tensor &attn_weight, const at::Tensor &grad_output,
+                                                const int im2col_step)
+{
+    const Checked c = check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step);
+    TORCH_CHECK(grad_output.is_contiguous(), "grad_output tensor has to be contiguous");
+    TORCH_CHECK(grad_output.is_cuda(), "grad_output must be a CUDA tensor");
+    TORCH_CHECK(grad_output.scalar_type() == value.scalar_type(), "grad_output must have the dtype of value");
+    TORCH_CHECK(grad_output.numel() == static_cast<int64_t>(c.N) * c.Lq * c.M * c.D,
+                "grad_output must be (N, Lq, M*D)");
+    const c10::cuda::CUDAGuard guard(value.device());
+    auto grad_value = at::empty_like(value);  // zero-filled by the library
+    auto grad_loc = at::empty_like(c.loc);
+    auto grad_attn = at::empty_like(c.attn);
+    const int rc = bm2f_msda_backward(value.data_ptr(), spatial_shapes.data_ptr<int64_t>(),
+                                      level_start_index.data_ptr<int64_t>(), c.loc.data_ptr(), c.attn.data_ptr(),
+                                      grad_output.data_ptr(), grad_value.data_ptr(), grad_loc.data_ptr(),
+                                      grad_attn.data_ptr(), c.N, c.S, c.M, c.D, c.L, c.Lq, c.P, c.dtype, nullptr,
+                                      at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == BM2F_OK, "ms_deform_attn_backward: ", bm2f_msda_last_error());
+    if (grad_loc.scalar_type() != sampling_loc.scalar_type()) grad_loc = grad_loc.to(sampling_loc.scalar_type());
+    if (grad_attn.scalar_type() != attn_weight.scalar_type()) grad_attn = grad_attn.to(attn_weight.scalar_type());
+    return {grad_value, grad_loc, grad_attn};
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
+{
+    m.doc() = "B200-native multi-scale deformable attention (drop-in for the Deformable-DETR op)";
+    m.def("ms_deform_attn_forward", &ms_deform_attn_forward, "ms_deform_attn_forward");
+    m.def("ms_deform_attn_backward", &ms_deform_attn_backward, "ms_deform_attn_backward");
+    m.def("abi_version", []() { return bm2f_msda_abi_version(); });
+    m.def("build_info", []() { return std::string(bm2f_msda_build_info()); });
+    m.def("launch_count", []() { return bm2f_msda_launch_count(); });
+}

@@ -1,0 +1,41 @@
+"""Autograd bridge with the reference's surface (ops/functions/ms_deform_attn_func.py:32-49).
+
+`MSDeformAttnFunction.apply(value, value_spatial_shapes, value_level_start_index,
+sampling_locations, attention_weights, im2col_step)` — same argument order and meaning, same
+saved tensors, backward returns `(grad_value, None, None, grad_sampling_loc, grad_attn_weight,
+None)` and is once-differentiable.
+
+Differences from the reference file, both deliberate:
+  * the native module is the sm_100a build loaded from this tree (bm2f_b200.load_extension);
+  * the pure-torch `ms_deform_attn_core_pytorch` is NOT here: it is a test oracle and lives in
+    oracle/ (the product path has no CPU route).  When this tree is dropped into the reference,
+    the reference keeps its own functions/ file and only the native module is replaced.
+"""
+from __future__ import annotations
+
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from ... import load_extension
+
+MSDA = load_extension()
+
+
+class MSDeformAttnFunction(Function):
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                attention_weights, im2col_step):
+        ctx.im2col_step = im2col_step
+        output = MSDA.ms_deform_attn_forward(value, value_spatial_shapes, value_level_start_index,
+                                             sampling_locations, attention_weights, ctx.im2col_step)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                              attention_weights)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, start, loc, attn = ctx.saved_tensors
+        grad_value, grad_loc, grad_attn = MSDA.ms_deform_attn_backward(
+            value, shapes, start, loc, attn, grad_output.contiguous(), ctx.im2col_step)
+        return grad_value, None, None, grad_loc, grad_attn, None

@@ -1,0 +1,116 @@
+"""`MSDeformAttn` with the reference's module surface (ops/modules/ms_deform_attn.py:34-125).
+
+Same constructor signature and defaults (d_model=256, n_levels=4, n_heads=8, n_points=4), same
+sub-module names and therefore the same state-dict keys
+(`sampling_offsets.{weight,bias}`, `attention_weights.{weight,bias}`, `value_proj.{weight,bias}`,
+`output_proj.{weight,bias}`), same parameter initialisation (ms_deform_attn.py:64-80: zero offset
+weights, compass-direction offset bias scaled by point index, zero attention weights, xavier
+projections), same `forward(query, reference_points, input_flatten, input_spatial_shapes,
+input_level_start_index, input_padding_mask=None)` and `im2col_step = 128`.
+
+Deliberate difference: the reference wraps the native call in a bare `try/except` and silently
+falls back to a pure-torch CPU path on ANY error (ms_deform_attn.py:116-121).  Here errors
+propagate and non-CUDA inputs raise: there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+from torch.nn.init import constant_, xavier_uniform_
+
+from ..functions import MSDeformAttnFunction
+
+
+def _is_power_of_2(n):
+    if (not isinstance(n, int)) or (n < 0):
+        raise ValueError("invalid input for _is_power_of_2: {} (type: {})".format(n, type(n)))
+    return (n & (n - 1) == 0) and n != 0
+
+
+class MSDeformAttn(nn.Module):
+    def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4):
+        super().__init__()
+        if d_model % n_heads != 0:
+            raise ValueError("d_model must be divisible by n_heads, but got {} and {}".format(d_model, n_heads))
+        head_dim = d_model // n_heads
+        if not _is_power_of_2(head_dim):
+            warnings.warn("MSDeformAttn: head dimension %d is not a power of 2; only head_dim == 32 runs on the "
+                          "sm_100a fast path, other sizes use the generic kernel." % head_dim)
+
+        self.im2col_step = 128
+
+        self.d_model = d_model
+        self.n_levels = n_levels
+        self.n_heads = n_heads
+        self.n_points = n_points
+
+        self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 2)
+        self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
+        self.value_proj = nn.Linear(d_model, d_model)
+        self.output_proj = nn.Linear(d_model, d_model)
+
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        constant_(self.sampling_offsets.weight.data, 0.)
+        # head m looks along angle 2*pi*m/M (normalised to the unit square); point p sits p+1 pixels out
+        angle = torch.arange(self.n_heads, dtype=torch.float32) * (2.0 * math.pi / self.n_heads)
+        direction = torch.stack([angle.cos(), angle.sin()], -1)
+        direction = direction / direction.abs().max(-1, keepdim=True)[0]
+        reach = torch.arange(1, self.n_points + 1, dtype=torch.float32)
+        bias = direction[:, None, None, :] * reach[None, None, :, None]
+        bias = bias.expand(self.n_heads, self.n_levels, self.n_points, 2)
+        with torch.no_grad():
+            self.sampling_offsets.bias = nn.Parameter(bias.reshape(-1).clone())
+        constant_(self.attention_weights.weight.data, 0.)
+        constant_(self.attention_weights.bias.data, 0.)
+        xavier_uniform_(self.value_proj.weight.data)
+        constant_(self.value_proj.bias.data, 0.)
+        xavier_uniform_(self.output_proj.weight.data)
+        constant_(self.output_proj.bias.data, 0.)
+
+    def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
+                input_padding_mask=None):
+        """
+        query                    (N, Lq, C)
+        reference_points         (N, Lq, n_levels, 2) in [0,1] (x, y), or (N, Lq, n_levels, 4) boxes (x, y, w, h)
+        input_flatten            (N, sum_l H_l*W_l, C)
+        input_spatial_shapes     (n_levels, 2) int64 [(H_0, W_0), ...]
+        input_level_start_index  (n_levels,) int64
+        input_padding_mask       (N, sum_l H_l*W_l) bool, True = padding
+        returns                  (N, Lq, C)
+        """
+        N, Len_q, _ = query.shape
+        N, Len_in, _ = input_flatten.shape
+        if not query.is_cuda:
+            raise RuntimeError("MSDeformAttn: Not implemented on the CPU (this build has no CPU fallback)")
+        # no device->host sync here: the level table is validated on the device side of the op
+
+        value = self.value_proj(input_flatten)
+        if input_padding_mask is not None:
+            value = value.masked_fill(input_padding_mask[..., None], float(0))
+        value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
+        sampling_offsets = self.sampling_offsets(query).view(
+            N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
+        attention_weights = self.attention_weights(query).view(
+            N, Len_q, self.n_heads, self.n_levels * self.n_points)
+        attention_weights = F.softmax(attention_weights, -1).view(
+            N, Len_q, self.n_heads, self.n_levels, self.n_points)
+        if reference_points.shape[-1] == 2:
+            offset_normalizer = torch.stack([input_spatial_shapes[..., 1], input_spatial_shapes[..., 0]], -1)
+            sampling_locations = reference_points[:, :, None, :, None, :] \
+                + sampling_offsets / offset_normalizer[None, None, None, :, None, :]
+        elif reference_points.shape[-1] == 4:
+            sampling_locations = reference_points[:, :, None, :, None, :2] \
+                + sampling_offsets / self.n_points * reference_points[:, :, None, :, None, 2:] * 0.5
+        else:
+            raise ValueError(
+                "Last dim of reference_points must be 2 or 4, but get {} instead.".format(reference_points.shape[-1]))
+        output = MSDeformAttnFunction.apply(
+            value, input_spatial_shapes, input_level_start_index, sampling_locations.contiguous(),
+            attention_weights, self.im2col_step)
+        return self.output_proj(output)

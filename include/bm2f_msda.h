@@ -1,0 +1,147 @@
+/*
+ * bm2f_msda.h — C ABI of the B200-native multi-scale deformable attention library
+ * (libbm2f_msda.so, built from bm2f_b200/csrc/ for sm_100a only).
+ *
+ * This is the drop-in boundary for the one path this repository replaces.  Each entry
+ * point names the reference interface it stands in for.  Paths are relative to
+ * /root/reference/mask2former/modeling/pixel_decoder/ops/.
+ *
+ *   reference (pybind module "MultiScaleDeformableAttention", src/vision.cpp:18-21)
+ *     ms_deform_attn_forward  (src/ms_deform_attn.h:25-44  -> src/cuda/ms_deform_attn_cuda.cu:25-85)
+ *     ms_deform_attn_backward (src/ms_deform_attn.h:46-66  -> src/cuda/ms_deform_attn_cuda.cu:88-158)
+ *   and, below them, the launchers ms_deformable_im2col_cuda / ms_deformable_col2im_cuda
+ *   (src/cuda/ms_deform_im2col_cuda.cuh:928-959, 961-1332).
+ *
+ * Conventions
+ *   - Plain pointers and sizes; no torch / ATen types.  All pointers are DEVICE pointers
+ *     on the current CUDA device unless the name ends in _host.
+ *   - Tensors are dense and contiguous (the reference asserts the same, .cu:33-43):
+ *       value        (N, S, M, D)         element type = dtype
+ *       spatial_shapes (L, 2) int64 = (H_l, W_l);  level_start_index (L) int64 — both read
+ *                      ON THE DEVICE (the reference dereferences them in-kernel, .cuh:279-282);
+ *                      the library never copies them to the host.
+ *       sampling_loc (N, Lq, M, L, P, 2)  last dim = (x, y) normalised to [0,1]
+ *       attn_weight  (N, Lq, M, L, P)
+ *       output / grad_output (N, Lq, M*D)
+ *     For BM2F_DTYPE_F32 / F64 every floating tensor has that type.  For BM2F_DTYPE_BF16 the
+ *     value / output / grad_output / grad_value tensors are bf16 while sampling_loc,
+ *     attn_weight and their gradients stay float32 (a bf16 location has +-0.5 px error at
+ *     W=256); the reference has no 16-bit path at all (.cu:69,139).
+ *   - Callee never allocates result buffers: the caller (the torch shim) owns them, so the
+ *     framework's caching allocator and stream semantics hold.  `output` need not be
+ *     zeroed; `grad_value` is zero-filled by the library (reference: at::zeros, .cu:59,126);
+ *     grad_sampling_loc and grad_attn_weight are fully overwritten.
+ *   - Every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the
+ *     legacy default stream).  No internal synchronisation, no static mutable state other
+ *     than a launch counter and a thread-local error string: re-entrant across streams.
+ *   - Return value: 0 on success; a negative BM2F_ERR_* code otherwise, in which case
+ *     bm2f_msda_last_error() returns a message for the calling thread.  Unlike the
+ *     reference (which only printf's launch failures, .cuh:953-957,1326-1330) kernel-launch
+ *     errors are returned.
+ *   - There is no CPU implementation and no fallback: with no usable sm_100 device the
+ *     calls fail with BM2F_ERR_CUDA.
+ */
+#ifndef BM2F_MSDA_H_
+#define BM2F_MSDA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BM2F_MSDA_ABI_VERSION 1
+
+typedef enum {
+    BM2F_DTYPE_F32 = 0,
+    BM2F_DTYPE_F64 = 1,
+    BM2F_DTYPE_BF16 = 2
+} bm2f_dtype_t;
+
+typedef enum {
+    BM2F_OK = 0,
+    BM2F_ERR_INVALID = -1,     /* bad argument (null pointer, non-positive size, bad dtype)     */
+    BM2F_ERR_UNSUPPORTED = -2, /* shape outside what the kernels cover (e.g. L > 16)            */
+    BM2F_ERR_CUDA = -3,        /* CUDA runtime / driver error, message has cudaGetErrorString   */
+    BM2F_ERR_IM2COL_STEP = -4  /* batch % min(batch, im2col_step) != 0  (.cu:55-57)             */
+} bm2f_status_t;
+
+/* Tunables of the D=32 fast path; zero-initialise for defaults.  Exposed so that bench.py and
+ * the tests can sweep / pin every variant through the same ABI. */
+typedef struct {
+    int vec;        /* floats per lane per corner: 4 (8 lanes x 128-bit, default), 2 or 1        */
+    int staging;    /* 0 = default, 1 = TMA tensor-map staging of loc/weights, 2 = direct loads */
+    int strip_w;    /* queries per strip row (stage), 0 = default (16)                           */
+    int rows;       /* strip rows per job, 0 = auto from problem size                            */
+    int ctas_per_sm;/* persistent CTAs per SM, 0 = default                                        */
+    int force_generic; /* 1 = always use the any-D kernel                                        */
+    int order;      /* 0 = default; 1 = 1-D query order (ignore level geometry)                  */
+    int reserved[9];
+} bm2f_msda_tuning_t;
+
+/* Library / ABI identification. */
+int bm2f_msda_abi_version(void);
+const char *bm2f_msda_build_info(void);
+
+/* Message of the last failing call made by this thread ("" if none). */
+const char *bm2f_msda_last_error(void);
+
+/* Number of kernels this library has launched since load (all threads).  bench.py reports
+ * the difference over its timed region as `gpu_launches`. */
+uint64_t bm2f_msda_launch_count(void);
+
+/* Process-wide default tuning used when a call passes tuning == NULL. */
+void bm2f_msda_set_default_tuning(const bm2f_msda_tuning_t *tuning);
+
+/* Precondition shared with the reference host wrapper (.cu:53-57):
+ * step = min(batch, im2col_step); batch % step must be 0.  Returns BM2F_OK or
+ * BM2F_ERR_IM2COL_STEP. */
+int bm2f_msda_check_im2col_step(int batch, int im2col_step);
+
+/*
+ * Forward.  Replaces ms_deform_attn_cuda_forward + ms_deformable_im2col_cuda
+ * (.cu:25-85, .cuh:928-959):
+ *   output[b,q,m,:] = sum_{l,p} attn[b,q,m,l,p] *
+ *                     bilinear_zero_pad(value[b, level l, m, :], x*W_l - 0.5, y*H_l - 0.5)
+ */
+int bm2f_msda_forward(const void *value, const int64_t *spatial_shapes,
+                      const int64_t *level_start_index, const void *sampling_loc,
+                      const void *attn_weight, void *output,
+                      int batch, int spatial_size, int num_heads, int channels,
+                      int num_levels, int num_query, int num_point,
+                      int dtype, const bm2f_msda_tuning_t *tuning, void *stream);
+
+/*
+ * Backward.  Replaces ms_deform_attn_cuda_backward + ms_deformable_col2im_cuda and its six
+ * kernel variants (.cu:88-158, .cuh:961-1332).
+ */
+int bm2f_msda_backward(const void *value, const int64_t *spatial_shapes,
+                       const int64_t *level_start_index, const void *sampling_loc,
+                       const void *attn_weight, const void *grad_output,
+                       void *grad_value, void *grad_sampling_loc, void *grad_attn_weight,
+                       int batch, int spatial_size, int num_heads, int channels,
+                       int num_levels, int num_query, int num_point,
+                       int dtype, const bm2f_msda_tuning_t *tuning, void *stream);
+
+/*
+ * Host-buffer convenience used for end-to-end measurement and by non-torch callers:
+ * every pointer is a HOST pointer (pinned memory gives full PCIe rate).  The library copies
+ * the inputs to a device workspace it owns for the duration of the call, runs forward and,
+ * when grad_output_host != NULL, backward, copies the results back and synchronises.
+ * The batch is pipelined image by image over two streams so copies overlap the kernels.
+ * Any of the result pointers may be NULL to skip that copy-back.
+ */
+int bm2f_msda_forward_backward_host(const void *value_host, const int64_t *spatial_shapes_host,
+                                    const int64_t *level_start_index_host,
+                                    const void *sampling_loc_host, const void *attn_weight_host,
+                                    const void *grad_output_host, void *output_host,
+                                    void *grad_value_host, void *grad_sampling_loc_host,
+                                    void *grad_attn_weight_host,
+                                    int batch, int spatial_size, int num_heads, int channels,
+                                    int num_levels, int num_query, int num_point,
+                                    int dtype, const bm2f_msda_tuning_t *tuning);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BM2F_MSDA_H_ */
