@@ -1,0 +1,200 @@
+// Stand-alone microbenchmarks that establish the machine limits the sampling kernels are judged
+// against (SURVEY.md §8d asks for a measured L2-gather peak; MEASURED_PEAKS.json only has HBM copy):
+//
+//   gather  — every warp instruction fetches whole 128-byte lines at pseudo-random line indices
+//             inside a buffer of a given size (22/44/88/352 MB = value of 1/2/4/16 COCO images; 96 KB
+//             = L1-resident window).  Shapes: 32 lanes x 4 B (one line / instruction, the
+//             reference's access shape), 8 lanes x 16 B (four lines / instruction, the fast path's
+//             shape), 4 lanes x 32 B (eight lines / instruction, 256-bit loads).
+//   red     — vector / scalar fp32 reductions (red.global.add) to pseudo-random lines: 32 x scalar
+//             (one line / instruction, the reference's atomicAdd shape) and 8 x v4 (four lines).
+//
+// Prints one line per measurement:  name  buffer_MB  GB/s  (useful bytes = lines x 128 B).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o msda_microbench msda_microbench.cu
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#define CK(x)                                                                               \
+    do {                                                                                    \
+        cudaError_t e_ = (x);                                                               \
+        if (e_ != cudaSuccess) {                                                            \
+            fprintf(stderr, "%s:%d %s: %s\n", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
+            exit(1);                                                                        \
+        }                                                                                   \
+    } while (0)
+
+__device__ __forceinline__ uint32_t mix(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+
+// MODE 0: 32 lanes x 4 B -> 1 line / instr.   MODE 1: 8 lanes x 16 B -> 4 lines / instr.
+// MODE 2: 4 lanes x 32 B -> 8 lines / instr (ld.global.nc.v8.f32).
+// `window` > 0 confines each CTA's lines to a private window of that many lines (L1-resident test).
+template <int MODE>
+__global__ void __launch_bounds__(512) gather_kernel(const float *__restrict__ buf, uint32_t nlines, int iters,
+                                                     uint32_t window, float *sink)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    constexpr int LPL = MODE == 0 ? 32 : (MODE == 1 ? 8 : 4);   // lanes per line
+    const int grp = lane / LPL, sub = lane % LPL;
+    const uint32_t wbase = window ? (uint32_t)(((uint64_t)blockIdx.x * window) % (nlines - window)) : 0u;
+    const uint32_t range = window ? window : nlines;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        const uint32_t h = mix((gwarp * 977u + i) * 64u + grp);
+        const uint32_t line = wbase + (uint32_t)(((uint64_t)h * range) >> 32);
+        const float *p = buf + (size_t)line * 32;
+        if (MODE == 0) {
+            acc += __ldg(p + sub);
+        } else if (MODE == 1) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(p) + sub);
+            acc += v.x + v.y + v.z + v.w;
+        } else {
+            float a, b, c, d, e, f, g, hh;
+            asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=f"(a), "=f"(b), "=f"(c), "=f"(d), "=f"(e), "=f"(f), "=f"(g), "=f"(hh)
+                         : "l"(p + sub * 8));
+            acc += a + b + c + d + e + f + g + hh;
+        }
+    }
+    if (acc == 123.456f) *sink = acc;
+}
+
+// MODE 0: 32 lanes x scalar red (1 line / instr).  MODE 1: 8 lanes x red.v4 (4 lines / instr).
+template <int MODE>
+__global__ void __launch_bounds__(512) red_kernel(float *buf, uint32_t nlines, int iters, uint32_t window)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    constexpr int LPL = MODE == 0 ? 32 : 8;
+    const int grp = lane / LPL, sub = lane % LPL;
+    const uint32_t wbase = window ? (uint32_t)(((uint64_t)blockIdx.x * window) % (nlines - window)) : 0u;
+    const uint32_t range = window ? window : nlines;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        const uint32_t h = mix((gwarp * 977u + i) * 64u + grp);
+        const uint32_t line = wbase + (uint32_t)(((uint64_t)h * range) >> 32);
+        float *p = buf + (size_t)line * 32;
+        if (MODE == 0) {
+            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p + sub), "f"(1.0f));
+        } else {
+            asm volatile("red.global.add.v4.f32 [%0], {%1,%1,%1,%1};" ::"l"(p + sub * 4), "f"(1.0f));
+        }
+    }
+}
+
+template <typename F>
+float time_ms(F launch, int reps)
+{
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    launch();
+    launch();
+    CK(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int r = 0; r < reps; ++r) {
+        CK(cudaEventRecord(a));
+        launch();
+        CK(cudaEventRecord(b));
+        CK(cudaEventSynchronize(b));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        if (ms < best) best = ms;
+    }
+    CK(cudaGetLastError());
+    return best;
+}
+
+int main()
+{
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    printf("# device %s  SMs %d  L2 %.1f MB  smem/SM %zu KB\n", prop.name, prop.multiProcessorCount,
+           prop.l2CacheSize / 1048576.0, prop.sharedMemPerMultiprocessor / 1024);
+    const size_t max_bytes = 704ull << 20;
+    float *buf, *sink;
+    CK(cudaMalloc(&buf, max_bytes));
+    CK(cudaMalloc(&sink, 4));
+    CK(cudaMemset(buf, 0, max_bytes));
+    const int sms = prop.multiProcessorCount;
+    const int threads = 512;
+    const int grid = sms * 4;                      // 64 warps / SM
+    const int warps = grid * threads / 32;
+    const int iters = 512;
+
+    const double mbs[] = {22, 44, 88, 352, 704};
+    const char *gname[] = {"gather_32x4B_1line", "gather_8x16B_4lines", "gather_4x32B_8lines"};
+    const int lines_per_instr[] = {1, 4, 8};
+    for (int mode = 0; mode < 3; ++mode) {
+        for (double mb : mbs) {
+            const uint32_t nlines = (uint32_t)(mb * 1048576.0 / 128);
+            auto launch = [&] {
+                if (mode == 0) gather_kernel<0><<<grid, threads>>>(buf, nlines, iters, 0, sink);
+                if (mode == 1) gather_kernel<1><<<grid, threads>>>(buf, nlines, iters, 0, sink);
+                if (mode == 2) gather_kernel<2><<<grid, threads>>>(buf, nlines, iters, 0, sink);
+            };
+            const float ms = time_ms(launch, 5);
+            const double bytes = (double)warps * iters * lines_per_instr[mode] * 128.0;
+            printf("%-24s %7.1f MB  %9.1f GB/s\n", gname[mode], mb, bytes / ms * 1e-6);
+        }
+        // L1-resident: each CTA re-reads a private 96 KB window (768 lines); 1 CTA per SM
+        {
+            const uint32_t nlines = (uint32_t)(352.0 * 1048576.0 / 128);
+            const int g1 = sms, it1 = 4096;
+            auto launch = [&] {
+                if (mode == 0) gather_kernel<0><<<g1, threads>>>(buf, nlines, it1, 768, sink);
+                if (mode == 1) gather_kernel<1><<<g1, threads>>>(buf, nlines, it1, 768, sink);
+                if (mode == 2) gather_kernel<2><<<g1, threads>>>(buf, nlines, it1, 768, sink);
+            };
+            const float ms = time_ms(launch, 5);
+            const double bytes = (double)(g1 * threads / 32) * it1 * lines_per_instr[mode] * 128.0;
+            printf("%-24s %7s     %9.1f GB/s  (L1-resident 96 KB window per SM)\n", gname[mode], "L1", bytes / ms * 1e-6);
+        }
+    }
+    const char *rname[] = {"red_32xf32_1line", "red_8xv4f32_4lines"};
+    const int rl[] = {1, 4};
+    for (int mode = 0; mode < 2; ++mode) {
+        for (double mb : mbs) {
+            const uint32_t nlines = (uint32_t)(mb * 1048576.0 / 128);
+            const int it = 128;
+            auto launch = [&] {
+                if (mode == 0) red_kernel<0><<<grid, threads>>>(buf, nlines, it, 0);
+                if (mode == 1) red_kernel<1><<<grid, threads>>>(buf, nlines, it, 0);
+            };
+            const float ms = time_ms(launch, 5);
+            const double bytes = (double)warps * it * rl[mode] * 128.0;
+            printf("%-24s %7.1f MB  %9.1f GB/s\n", rname[mode], mb, bytes / ms * 1e-6);
+        }
+        {   // localised: each CTA reduces into a private 96 KB window (what a strip-walking job does)
+            const uint32_t nlines = (uint32_t)(352.0 * 1048576.0 / 128);
+            const int it = 256;
+            auto launch = [&] {
+                if (mode == 0) red_kernel<0><<<grid, threads>>>(buf, nlines, it, 768);
+                if (mode == 1) red_kernel<1><<<grid, threads>>>(buf, nlines, it, 768);
+            };
+            const float ms = time_ms(launch, 5);
+            const double bytes = (double)warps * it * rl[mode] * 128.0;
+            printf("%-24s %7s     %9.1f GB/s  (96 KB window per CTA)\n", rname[mode], "win", bytes / ms * 1e-6);
+        }
+    }
+    // plain streaming copy for reference (same denominator as MEASURED_PEAKS.json hbm_gbs)
+    {
+        const size_t n = 512ull << 20;
+        float *dst;
+        CK(cudaMalloc(&dst, n));
+        auto launch = [&] { CK(cudaMemcpyAsync(dst, buf, n, cudaMemcpyDeviceToDevice)); };
+        const float ms = time_ms(launch, 5);
+        printf("%-24s %7.1f MB  %9.1f GB/s  (read+write)\n", "d2d_copy", n / 1048576.0, 2.0 * n / ms * 1e-6);
+        CK(cudaFree(dst));
+    }
+    CK(cudaFree(buf));
+    CK(cudaFree(sink));
+    return 0;
+}

@@ -1,0 +1,288 @@
+"""GPU parity tests: the sm_100a kernels, called through the C ABI (bm2f_b200.cabi -> libbm2f_msda.so),
+against the CPU oracle and the golden vectors recorded from the reference.
+
+Tolerances (BASELINE.json north_star): forward max-abs <= 1e-5 in fp32 (<= 1e-2 relative in bf16),
+gradients <= 1e-4 relative in fp32 (relative to the largest reference entry), atomic order is free.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from bm2f_b200 import cabi
+from bm2f_b200 import workloads as W
+from oracle import msda_oracle as O
+from tests.helpers import rel_err, smooth_mask
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+FWD_ABS_F32 = 1e-5
+GRAD_REL_F32 = 1e-4
+
+TORCH_DT = {cabi.DTYPE_F32: torch.float32, cabi.DTYPE_F64: torch.float64, cabi.DTYPE_BF16: torch.bfloat16}
+
+
+def _dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def run_cabi(value, shapes, start, loc, attn, grad_out=None, dtype=cabi.DTYPE_F32, tuning=None):
+    """CPU tensors/arrays in -> device -> C ABI -> CPU float64 numpy out.  bf16: value-side tensors
+    are bf16, loc/attn stay fp32 (include/bm2f_msda.h)."""
+    dev = _dev()
+    vt = TORCH_DT[dtype]
+    lt = torch.float64 if dtype == cabi.DTYPE_F64 else torch.float32
+    t = lambda a, d: torch.as_tensor(np.asarray(a)).to(device=dev, dtype=d).contiguous()
+    v, lo, at = t(value, vt), t(loc, lt), t(attn, lt)
+    sh = torch.as_tensor(np.asarray(shapes)).to(dev, torch.long).contiguous()
+    st = torch.as_tensor(np.asarray(start)).to(dev, torch.long).contiguous()
+    N, S, M, D = v.shape
+    Lq, L, P = lo.shape[1], lo.shape[3], lo.shape[4]
+    dims = (N, S, M, D, L, Lq, P)
+    out = torch.full((N, Lq, M * D), float("nan"), device=dev, dtype=vt)   # must be fully overwritten
+    stream = torch.cuda.current_stream().cuda_stream
+    cabi.forward(v.data_ptr(), sh.data_ptr(), st.data_ptr(), lo.data_ptr(), at.data_ptr(), out.data_ptr(), dims,
+                 dtype, tuning, stream)
+    res = {"out": out.double().cpu().numpy()}
+    if grad_out is not None:
+        go = t(grad_out, vt).reshape(N, Lq, M * D)
+        gv = torch.full_like(v, float("nan"))      # library must zero-fill
+        gl = torch.full_like(lo, float("nan"))     # library must fully overwrite
+        ga = torch.full_like(at, float("nan"))
+        cabi.backward(v.data_ptr(), sh.data_ptr(), st.data_ptr(), lo.data_ptr(), at.data_ptr(), go.data_ptr(),
+                      gv.data_ptr(), gl.data_ptr(), ga.data_ptr(), dims, dtype, tuning, stream)
+        res.update(grad_value=gv.double().cpu().numpy(), grad_loc=gl.double().cpu().numpy(),
+                   grad_attn=ga.double().cpu().numpy())
+    torch.cuda.synchronize()
+    return res
+
+
+def check_f32(res, ref, loc, shapes, tag=""):
+    assert np.isfinite(res["out"]).all(), tag
+    assert np.abs(res["out"] - ref["out"]).max() <= FWD_ABS_F32 * max(1.0, np.abs(ref["out"]).max()), tag
+    if "grad_value" in res:
+        ok = smooth_mask(loc, shapes)
+        assert rel_err(res["grad_value"], ref["grad_value"]) <= GRAD_REL_F32, tag
+        assert rel_err(res["grad_attn"], ref["grad_attn"]) <= GRAD_REL_F32, tag
+        assert rel_err(res["grad_loc"] * ok, ref["grad_loc"] * ok) <= GRAD_REL_F32, tag
+        assert np.isfinite(res["grad_loc"]).all() and np.isfinite(res["grad_value"]).all(), tag
+
+
+def oracle_ref(inp):
+    a = {k: v.numpy() if isinstance(v, torch.Tensor) else v for k, v in inp.items()}
+    out = O.forward(a["value"], a["shapes"], a["start"], a["loc"], a["attn"])
+    gv, gl, ga = O.backward(a["value"], a["shapes"], a["start"], a["loc"], a["attn"], a["grad_out"])
+    return dict(out=out, grad_value=gv, grad_loc=gl, grad_attn=ga)
+
+
+# ----------------------------------------------------------------------------------------------
+# 1. golden vectors recorded from the reference (tests/golden, oracle/gen_golden.py)
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_golden_f32(path, built):
+    z = np.load(path)
+    res = run_cabi(z["value"], z["shapes"], z["start"], z["loc"], z["attn"], z["grad_out"])
+    check_f32(res, z, z["loc"], z["shapes"], path)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_golden_f64(path, built):
+    # float64 goes through the any-shape kernels, like the reference's own double test (test.py:34-47)
+    z = np.load(path)
+    res = run_cabi(z["value"], z["shapes"], z["start"], z["loc"], z["attn"], z["grad_out"], dtype=cabi.DTYPE_F64)
+    assert np.abs(res["out"] - z["out"]).max() < 1e-12
+    assert np.abs(res["grad_value"] - z["grad_value"]).max() < 1e-12
+    assert np.abs(res["grad_attn"] - z["grad_attn"]).max() < 1e-12
+    assert np.abs(res["grad_loc"] - z["grad_loc"]).max() < 1e-11
+
+
+@pytest.mark.parametrize("path", [p for p in GOLDEN if "m2f_tiny" in p],
+                         ids=[os.path.basename(p)[:-4] for p in GOLDEN if "m2f_tiny" in p])
+def test_golden_f32_generic_kernel(path, built):
+    z = np.load(path)
+    res = run_cabi(z["value"], z["shapes"], z["start"], z["loc"], z["attn"], z["grad_out"],
+                   tuning=cabi.make_tuning(force_generic=1))
+    check_f32(res, z, z["loc"], z["shapes"], path)
+
+
+# ----------------------------------------------------------------------------------------------
+# 2. every fast-path variant against the oracle on a Mask2Former-shaped problem
+# ----------------------------------------------------------------------------------------------
+SMALL_LEVELS = ((6, 10), (12, 20), (24, 40))     # cfg-5 aspect ratio, widths not multiples of 16/32
+
+
+@pytest.fixture(scope="module")
+def small_problem():
+    inp = W.make_inputs(SMALL_LEVELS, 3, seed=77)
+    return inp, oracle_ref(inp)
+
+
+VARIANTS = [dict(vec=v, staging=s, strip_w=sw, ctas_per_sm=c)
+            for v in (4, 2, 1) for s in (1, 2) for sw in (8, 16, 32) for c in (1, 2)]
+
+
+@pytest.mark.parametrize("var", VARIANTS, ids=lambda d: "v{vec}_st{staging}_sw{strip_w}_c{ctas_per_sm}".format(**d))
+def test_fast_variants_vs_oracle(var, small_problem, built):
+    inp, ref = small_problem
+    res = run_cabi(inp["value"], inp["shapes"], inp["start"], inp["loc"], inp["attn"], inp["grad_out"],
+                   tuning=cabi.make_tuning(**var))
+    check_f32(res, ref, inp["loc"].numpy(), inp["shapes"].numpy(), str(var))
+
+
+@pytest.mark.parametrize("rows", [1, 4, 7, 64])
+@pytest.mark.parametrize("order", [0, 1])
+def test_job_shapes_do_not_change_results(rows, order, small_problem, built):
+    inp, ref = small_problem
+    res = run_cabi(inp["value"], inp["shapes"], inp["start"], inp["loc"], inp["attn"], inp["grad_out"],
+                   tuning=cabi.make_tuning(rows=rows, order=order))
+    check_f32(res, ref, inp["loc"].numpy(), inp["shapes"].numpy(), f"rows={rows} order={order}")
+
+
+@pytest.mark.parametrize("L", [1, 2, 4])
+@pytest.mark.parametrize("staging", [1, 2])
+def test_other_level_counts(L, staging, built):
+    levels = ((3, 5), (7, 9), (16, 16), (5, 33))[:L]
+    inp = W.make_inputs(levels, 2, seed=100 + L, dist="uniform", n_query=123)       # Lq != S: 1-D order
+    ref = oracle_ref(inp)
+    res = run_cabi(inp["value"], inp["shapes"], inp["start"], inp["loc"], inp["attn"], inp["grad_out"],
+                   tuning=cabi.make_tuning(staging=staging))
+    check_f32(res, ref, inp["loc"].numpy(), inp["shapes"].numpy(), f"L={L}")
+
+
+# ----------------------------------------------------------------------------------------------
+# 3. BASELINE.json config shapes at sizes the oracle finishes in seconds
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg,batch,dist", [(1, 1, "model"), (5, 2, "model"), (2, 1, "model"), (1, 1, "uniform"),
+                                            (3, 1, "model")])
+def test_config_shapes_vs_oracle(cfg, batch, dist, built):
+    inp = W.workload_inputs(cfg, batch=batch, dist=dist)
+    ref = oracle_ref(inp)
+    res = run_cabi(inp["value"], inp["shapes"], inp["start"], inp["loc"], inp["attn"], inp["grad_out"])
+    check_f32(res, ref, inp["loc"].numpy(), inp["shapes"].numpy(), f"cfg{cfg}")
+
+
+def test_bf16_forward_and_backward_vs_oracle(built):
+    # config 3 is bf16 inference; oracle runs in float64 on the bf16-rounded value
+    inp = W.workload_inputs(3, batch=2)
+    inp["value"] = inp["value"].bfloat16().float()
+    inp["grad_out"] = inp["grad_out"].bfloat16().float()
+    ref = oracle_ref(inp)
+    res = run_cabi(inp["value"], inp["shapes"], inp["start"], inp["loc"], inp["attn"], inp["grad_out"],
+                   dtype=cabi.DTYPE_BF16)
+    assert rel_err(res["out"], ref["out"]) <= 1e-2
+    ok = smooth_mask(inp["loc"].numpy(), inp["shapes"].numpy())
+    assert rel_err(res["grad_attn"], ref["grad_attn"]) <= 1e-4      # fp32 outputs
+    assert rel_err(res["grad_loc"] * ok, ref["grad_loc"] * ok) <= 1e-4
+    assert rel_err(res["grad_value"], ref["grad_value"]) <= 3e-2    # bf16 atomics accumulate rounding
+
+
+# ----------------------------------------------------------------------------------------------
+# 4. full BASELINE size (cfg 2, N = 16): size-independent properties, no oracle
+# ----------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def full_problem():
+    inp = W.workload_inputs(2)
+    dev = _dev()
+    return {k: v.to(dev) for k, v in inp.items()}
+
+
+def _fwd(d, value=None, tuning=None):
+    v = d["value"] if value is None else value
+    N, S, M, D = v.shape
+    Lq = d["loc"].shape[1]
+    out = torch.empty(N, Lq, M * D, device=v.device)
+    cabi.forward(v.data_ptr(), d["shapes"].data_ptr(), d["start"].data_ptr(), d["loc"].data_ptr(),
+                 d["attn"].data_ptr(), out.data_ptr(), (N, S, M, D, 3, Lq, 4), cabi.DTYPE_F32, tuning,
+                 torch.cuda.current_stream().cuda_stream)
+    return out
+
+
+def _bwd(d, grad_out, tuning=None):
+    v = d["value"]
+    N, S, M, D = v.shape
+    Lq = d["loc"].shape[1]
+    gv, gl, ga = torch.empty_like(v), torch.empty_like(d["loc"]), torch.empty_like(d["attn"])
+    cabi.backward(v.data_ptr(), d["shapes"].data_ptr(), d["start"].data_ptr(), d["loc"].data_ptr(),
+                  d["attn"].data_ptr(), grad_out.data_ptr(), gv.data_ptr(), gl.data_ptr(), ga.data_ptr(),
+                  (N, S, M, D, 3, Lq, 4), cabi.DTYPE_F32, tuning, torch.cuda.current_stream().cuda_stream)
+    return gv, gl, ga
+
+
+def test_full_size_linearity_in_value(full_problem, built):
+    d = full_problem
+    v2 = torch.randn_like(d["value"])
+    lhs = _fwd(d, 0.5 * d["value"] + 2.0 * v2)
+    rhs = 0.5 * _fwd(d) + 2.0 * _fwd(d, v2)
+    assert (lhs - rhs).abs().max().item() <= 1e-4
+
+
+def test_full_size_constant_value_gives_coverage(full_problem, built):
+    # value == 1 everywhere: out = sum of attention weights x bilinear coverage, in [0, 1]; equal
+    # to 1 wherever every sampling point lies at least one pixel inside its level
+    d = full_problem
+    out = _fwd(d, torch.ones_like(d["value"]))
+    assert out.min().item() >= -1e-6 and out.max().item() <= 1 + 1e-5
+    shapes = d["shapes"].float()
+    wh = torch.stack((shapes[:, 1], shapes[:, 0]), -1)[None, None, None, :, None, :]
+    px = d["loc"] * wh - 0.5
+    inside = ((px >= 0) & (px <= wh - 1)).all(-1).all(-1).all(-1)            # (N, Lq, M)
+    full = out.view(*inside.shape, 32)[inside]
+    assert full.numel() > 0 and (full - 1).abs().max().item() <= 1e-5
+
+
+def test_full_size_adjoint_identity(full_problem, built):
+    # forward is linear in value, so <A v, g> == <v, A^T g>: ties the scatter (backward) to the gather
+    d = full_problem
+    g = d["grad_out"]
+    out = _fwd(d)
+    gv, gl, ga = _bwd(d, g)
+    lhs = (out.double() * g.double()).sum().item()
+    rhs = (d["value"].double() * gv.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), 1.0) + 1e-2
+    # grad_attn is the directional derivative in the attention weights: <grad_attn, attn> == <out, g>
+    mid = (ga.double() * d["attn"].double()).sum().item()
+    assert abs(lhs - mid) <= 1e-6 * max(abs(lhs), 1.0) + 1e-2
+
+
+def test_full_size_fast_equals_generic(full_problem, built):
+    # two independent kernel families on the full problem
+    d = full_problem
+    gen = cabi.make_tuning(force_generic=1)
+    out_f, out_g = _fwd(d), _fwd(d, tuning=gen)
+    assert (out_f - out_g).abs().max().item() <= 1e-5 * max(1.0, out_g.abs().max().item())
+    gf, gg = _bwd(d, d["grad_out"]), _bwd(d, d["grad_out"], tuning=gen)
+    for a, b in zip(gf[:1] + gf[2:], gg[:1] + gg[2:]):
+        assert (a - b).abs().max().item() <= 1e-4 * b.abs().max().item()
+
+
+def test_full_size_staging_variants_agree_bitwise_forward(full_problem, built):
+    # TMA-staged and directly loaded sampling metadata feed the same arithmetic: forward is bit-equal
+    d = full_problem
+    a = _fwd(d, tuning=cabi.make_tuning(staging=1))
+    b = _fwd(d, tuning=cabi.make_tuning(staging=2))
+    assert torch.equal(a, b)
+
+
+# ----------------------------------------------------------------------------------------------
+# 5. host-buffer entry
+# ----------------------------------------------------------------------------------------------
+def test_host_entry_matches_device_entry(built):
+    inp = W.workload_inputs(5, batch=5)                    # odd batch: ragged last chunk
+    pin = {k: v.contiguous().pin_memory() for k, v in inp.items()}
+    N, S, M, D = inp["value"].shape
+    Lq = inp["loc"].shape[1]
+    out = torch.empty(N, Lq, M * D).pin_memory()
+    gv, gl, ga = (torch.empty_like(inp[k]).pin_memory() for k in ("value", "loc", "attn"))
+    cabi.forward_backward_host(pin["value"].data_ptr(), pin["shapes"].data_ptr(), pin["start"].data_ptr(),
+                               pin["loc"].data_ptr(), pin["attn"].data_ptr(), pin["grad_out"].data_ptr(),
+                               out.data_ptr(), gv.data_ptr(), gl.data_ptr(), ga.data_ptr(),
+                               (N, S, M, D, 3, Lq, 4))
+    ref = run_cabi(inp["value"], inp["shapes"], inp["start"], inp["loc"], inp["attn"], inp["grad_out"])
+    assert np.abs(out.double().numpy() - ref["out"]).max() <= 1e-6
+    assert rel_err(gv.numpy(), ref["grad_value"]) <= 1e-5
+    assert rel_err(gl.numpy(), ref["grad_loc"]) <= 1e-5
+    assert rel_err(ga.numpy(), ref["grad_attn"]) <= 1e-5
