@@ -371,7 +371,8 @@ int bm2f_msda_backward(const void *value, const int64_t *spatial_shapes, const i
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
     // grad_value accumulates through atomics: zero it first (reference: at::zeros_like, .cu:126)
-    const size_t gv_bytes = static_cast<size_t>(d.N) * d.S * d.M * d.D * elem_size(dtype);
+    // bf16 values still accumulate grad_value in float32 (see include/bm2f_msda.h)
+    const size_t gv_bytes = static_cast<size_t>(d.N) * d.S * d.M * d.D * (dtype == BM2F_DTYPE_F64 ? 8 : 4);
     cudaError_t e = cudaMemsetAsync(grad_value, 0, gv_bytes, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(grad_value)");
 
@@ -424,6 +425,7 @@ int bm2f_msda_forward_backward_host(const void *value_host, const int64_t *spati
     const bool bwd = grad_output_host != nullptr;
     const size_t e = elem_size(dtype), el = loc_elem_size(dtype);
     const size_t v_img = static_cast<size_t>(d.S) * d.M * d.D * e;
+    const size_t gv_img = static_cast<size_t>(d.S) * d.M * d.D * (dtype == BM2F_DTYPE_F64 ? 8 : 4);
     const size_t o_img = static_cast<size_t>(d.Lq) * d.M * d.D * e;
     const size_t l_img = static_cast<size_t>(d.Lq) * d.M * d.L * d.P * 2 * el;
     const size_t a_img = static_cast<size_t>(d.Lq) * d.M * d.L * d.P * el;
@@ -432,7 +434,7 @@ int bm2f_msda_forward_backward_host(const void *value_host, const int64_t *spati
     int chunk = d.N >= 8 ? d.N / 8 : 1;
     const size_t slot_bytes = static_cast<size_t>(chunk) *
                               (align256(v_img) + align256(l_img) + align256(a_img) + align256(o_img) +
-                               (bwd ? align256(o_img) + align256(v_img) + align256(l_img) + align256(a_img) : 0)) +
+                               (bwd ? align256(o_img) + align256(gv_img) + align256(l_img) + align256(a_img) : 0)) +
                               4096;
 
     std::lock_guard<std::mutex> lk(g_host.mu);
@@ -481,7 +483,7 @@ int bm2f_msda_forward_backward_host(const void *value_host, const int64_t *spati
         auto take = [&](size_t per_img) { char *r = w; w += static_cast<size_t>(chunk) * align256(per_img); return r; };
         char *dv = take(v_img), *dl = take(l_img), *da = take(a_img), *dout = take(o_img);
         char *dgo = nullptr, *dgv = nullptr, *dgl = nullptr, *dga = nullptr;
-        if (bwd) { dgo = take(o_img); dgv = take(v_img); dgl = take(l_img); dga = take(a_img); }
+        if (bwd) { dgo = take(o_img); dgv = take(gv_img); dgl = take(l_img); dga = take(a_img); }
 
 #define BM2F_CP(dst, src, bytes, kind, what)                                                           \
     if ((ce = cudaMemcpyAsync(dst, src, bytes, kind, st)) != cudaSuccess) return cuda_fail(ce, what);
@@ -498,7 +500,7 @@ int bm2f_msda_forward_backward_host(const void *value_host, const int64_t *spati
                                     d.P, dtype, tuning, st);
             if (rc) return rc;
             if (grad_value_host)
-                BM2F_CP(hpw(grad_value_host, b0 * v_img), dgv, nb * v_img, cudaMemcpyDeviceToHost, "D2H grad_value")
+                BM2F_CP(hpw(grad_value_host, b0 * gv_img), dgv, nb * gv_img, cudaMemcpyDeviceToHost, "D2H grad_value")
             if (grad_sampling_loc_host)
                 BM2F_CP(hpw(grad_sampling_loc_host, b0 * l_img), dgl, nb * l_img, cudaMemcpyDeviceToHost,
                         "D2H grad_sampling_loc")

@@ -31,7 +31,7 @@ struct FastParams {
     const float *attn;           // (N,Lq,M,L,P)
     const void *grad_out;        // (N,Lq,M,32)            bwd only
     void *out;                   // (N,Lq,M,32)            fwd only
-    void *grad_value;            // (N,S,M,32)             bwd only
+    void *grad_value;            // (N,S,M,32) float32      bwd only
     float *grad_loc;             // like loc               bwd only
     float *grad_attn;            // like attn              bwd only
     int N, S, M, Lq;
@@ -323,7 +323,7 @@ msda_bwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_
     constexpr int MD = kHeads * D;  // elements between horizontally adjacent pixels (immediate offset)
     const T *value = static_cast<const T *>(p.value);
     const T *grad_out = static_cast<const T *>(p.grad_out);
-    T *grad_value = static_cast<T *>(p.grad_value);
+    float *grad_value = static_cast<float *>(p.grad_value);   // fp32 accumulation for every value dtype
 
     for_each_stage<L_, SW>(tabs, p, [&](int s, int b, int m, int q_base, int nq) {
         if (G > 1 && (s % G) != g) return;
@@ -331,7 +331,7 @@ msda_bwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_
         if (TMA) mbar_wait(&ring.full[slot], (s / kStages) & 1);
         const size_t img = (static_cast<size_t>(b) * p.S * kHeads + m) * D + sub * VEC;
         const T *vlane = value + img;
-        T *gvlane = grad_value + img;
+        float *gvlane = grad_value + img;
         for (int qi = wi; qi < nq; qi += WPG) {
             const int q = q_base + qi;
             const size_t qm = (static_cast<size_t>(b) * p.Lq + q) * kHeads + m;
@@ -377,7 +377,7 @@ msda_bwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_
                         float r[VEC];
 #pragma unroll
                         for (int c = 0; c < VEC; ++c) r[c] = cwk * go[c];
-                        VecIO<T, VEC>::red_add(gvlane + eoff[k], r);
+                        VecIO<float, VEC>::red_add(gvlane + eoff[k], r);
                     }
                     t[k] = 0.f;
 #pragma unroll

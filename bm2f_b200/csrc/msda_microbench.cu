@@ -89,6 +89,40 @@ __global__ void __launch_bounds__(512) red_kernel(float *buf, uint32_t nlines, i
     }
 }
 
+
+// TMA bulk reduction: every warp stages CHUNK bytes of addends in shared memory and lets the
+// TMA engine add them into global memory (cp.reduce.async.bulk ... .add.f32), bypassing the
+// LSU RED path.  CHUNK = 128 (one line) or 512 (four consecutive lines).
+template <int CHUNK>
+__global__ void __launch_bounds__(512) tma_red_kernel(float *buf, uint32_t nlines, int iters, uint32_t window)
+{
+    __shared__ __align__(128) float stage[16][2][CHUNK / 4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t wbase = window ? (uint32_t)(((uint64_t)blockIdx.x * window) % (nlines - window)) : 0u;
+    const uint32_t range = (window ? window : nlines) - CHUNK / 128;
+    for (int i = 0; i < iters; ++i) {
+        float *s = stage[warp][i & 1];
+        if (i >= 2) {   // the buffer written two iterations ago must have been read by the TMA engine
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+        }
+        for (int k = lane; k < CHUNK / 4; k += 32) s[k] = 1.0f;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t h = mix((gwarp * 977u + i) * 64u);
+            const uint32_t line = wbase + (uint32_t)(((uint64_t)h * range) >> 32);
+            float *g = buf + (size_t)line * 32;
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(g),
+                         "r"((uint32_t)__cvta_generic_to_shared(s)), "n"(CHUNK)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 template <typename F>
 float time_ms(F launch, int reps)
 {
@@ -183,6 +217,61 @@ int main()
             const double bytes = (double)warps * it * rl[mode] * 128.0;
             printf("%-24s %7s     %9.1f GB/s  (96 KB window per CTA)\n", rname[mode], "win", bytes / ms * 1e-6);
         }
+    }
+
+    // ---- is the vector-RED rate an SM-side or an L2-side limit?  scale SMs and warps per SM ----
+    {
+        const uint32_t nlines = (uint32_t)(44.0 * 1048576.0 / 128);
+        const int it = 256;
+        const int grids[] = {sms / 4, sms / 2, sms, sms * 2, sms * 4};
+        for (int g : grids) {
+            for (int th : {128, 512}) {
+                auto launch = [&] { red_kernel<1><<<g, th>>>(buf, nlines, it, 0); };
+                const float ms = time_ms(launch, 3);
+                const double bytes = (double)(g * th / 32) * it * 4 * 128.0;
+                printf("red_v4_scaling  ctas %4d x %3d thr  %9.1f GB/s\n", g, th, bytes / ms * 1e-6);
+            }
+        }
+        for (int g : grids) {
+            auto launch = [&] { gather_kernel<1><<<g, 512>>>(buf, nlines, 512, 0, sink); };
+            const float ms = time_ms(launch, 3);
+            const double bytes = (double)(g * 512 / 32) * 512 * 4 * 128.0;
+            printf("gather_v4_scaling ctas %4d x 512 thr  %9.1f GB/s\n", g, bytes / ms * 1e-6);
+        }
+    }
+    // ---- TMA bulk reduce (cp.reduce.async.bulk .add.f32) ----
+    for (double mb : {44.0, 352.0}) {
+        const uint32_t nlines = (uint32_t)(mb * 1048576.0 / 128);
+        const int it = 256;
+        {
+            auto launch = [&] { tma_red_kernel<128><<<grid, threads>>>(buf, nlines, it, 0); };
+            const float ms = time_ms(launch, 3);
+            printf("%-24s %7.1f MB  %9.1f GB/s\n", "tma_reduce_128B", mb, (double)warps * it * 128.0 / ms * 1e-6);
+        }
+        {
+            auto launch = [&] { tma_red_kernel<512><<<grid, threads>>>(buf, nlines, it, 0); };
+            const float ms = time_ms(launch, 3);
+            printf("%-24s %7.1f MB  %9.1f GB/s\n", "tma_reduce_512B", mb, (double)warps * it * 512.0 / ms * 1e-6);
+        }
+    }
+    {   // TMA reduce and LSU vector REDs at the same time (two streams): do the two paths add up?
+        const uint32_t nlines = (uint32_t)(44.0 * 1048576.0 / 128);
+        cudaStream_t s1, s2;
+        CK(cudaStreamCreate(&s1)); CK(cudaStreamCreate(&s2));
+        const int it = 256;
+        auto launch = [&] {
+            tma_red_kernel<512><<<grid / 2, threads, 0, s1>>>(buf, nlines, it, 0);
+            red_kernel<1><<<grid / 2, threads, 0, s2>>>(buf, nlines, it, 0);
+            CK(cudaStreamSynchronize(s1)); CK(cudaStreamSynchronize(s2));
+        };
+        cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+        launch();
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(a)); launch(); CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+        float ms; CK(cudaEventElapsedTime(&ms, a, b));
+        const double bytes = (double)(warps / 2) * it * 512.0 * 2;
+        printf("%-24s %7.1f MB  %9.1f GB/s  (half grid TMA-reduce + half grid red.v4 concurrently)\n", "tma+lsu_red", 44.0,
+               bytes / ms * 1e-6);
     }
     // plain streaming copy for reference (same denominator as MEASURED_PEAKS.json hbm_gbs)
     {

@@ -122,7 +122,9 @@ std::vector<at::Tensor> ms_deform_attn_backward(const at::Tensor &value, const a
     TORCH_CHECK(grad_output.numel() == static_cast<int64_t>(c.N) * c.Lq * c.M * c.D,
                 "grad_output must be (N, Lq, M*D)");
     const c10::cuda::CUDAGuard guard(value.device());
-    auto grad_value = at::empty_like(value);  // zero-filled by the library
+    // zero-filled by the library; bf16 values accumulate their gradient in fp32 (include/bm2f_msda.h)
+    auto grad_value = c.dtype == BM2F_DTYPE_BF16 ? at::empty(value.sizes(), value.options().dtype(at::kFloat))
+                                                 : at::empty_like(value);
     auto grad_loc = at::empty_like(c.loc);
     auto grad_attn = at::empty_like(c.attn);
     const int rc = bm2f_msda_backward(value.data_ptr(), spatial_shapes.data_ptr<int64_t>(),
@@ -131,6 +133,7 @@ std::vector<at::Tensor> ms_deform_attn_backward(const at::Tensor &value, const a
                                       grad_attn.data_ptr(), c.N, c.S, c.M, c.D, c.L, c.Lq, c.P, c.dtype, nullptr,
                                       at::cuda::getCurrentCUDAStream().stream());
     TORCH_CHECK(rc == BM2F_OK, "ms_deform_attn_backward: ", bm2f_msda_last_error());
+    if (grad_value.scalar_type() != value.scalar_type()) grad_value = grad_value.to(value.scalar_type());
     if (grad_loc.scalar_type() != sampling_loc.scalar_type()) grad_loc = grad_loc.to(sampling_loc.scalar_type());
     if (grad_attn.scalar_type() != attn_weight.scalar_type()) grad_attn = grad_attn.to(attn_weight.scalar_type());
     return {grad_value, grad_loc, grad_attn};

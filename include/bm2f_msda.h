@@ -24,9 +24,11 @@
  *       attn_weight  (N, Lq, M, L, P)
  *       output / grad_output (N, Lq, M*D)
  *     For BM2F_DTYPE_F32 / F64 every floating tensor has that type.  For BM2F_DTYPE_BF16 the
- *     value / output / grad_output / grad_value tensors are bf16 while sampling_loc,
- *     attn_weight and their gradients stay float32 (a bf16 location has +-0.5 px error at
- *     W=256); the reference has no 16-bit path at all (.cu:69,139).
+ *     value / output / grad_output tensors are bf16 while sampling_loc, attn_weight, their
+ *     gradients AND grad_value are float32: a bf16 location has +-0.5 px error at W=256, and
+ *     ~44 bf16 atomic adds per grad_value element lose 3e-2 relative (measured), so grad_value
+ *     accumulates in fp32 and the caller casts.  The reference has no 16-bit path at all
+ *     (.cu:69,139).
  *   - Callee never allocates result buffers: the caller (the torch shim) owns them, so the
  *     framework's caching allocator and stream semantics hold.  `output` need not be
  *     zeroed; `grad_value` is zero-filled by the library (reference: at::zeros, .cu:59,126);

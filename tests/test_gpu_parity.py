@@ -50,7 +50,8 @@ def run_cabi(value, shapes, start, loc, attn, grad_out=None, dtype=cabi.DTYPE_F3
     res = {"out": out.double().cpu().numpy()}
     if grad_out is not None:
         go = t(grad_out, vt).reshape(N, Lq, M * D)
-        gv = torch.full_like(v, float("nan"))      # library must zero-fill
+        # library must zero-fill; bf16 values accumulate grad_value in fp32 (include/bm2f_msda.h)
+        gv = torch.full(v.shape, float("nan"), device=dev, dtype=torch.float64 if dtype == cabi.DTYPE_F64 else torch.float32)
         gl = torch.full_like(lo, float("nan"))     # library must fully overwrite
         ga = torch.full_like(at, float("nan"))
         cabi.backward(v.data_ptr(), sh.data_ptr(), st.data_ptr(), lo.data_ptr(), at.data_ptr(), go.data_ptr(),
@@ -177,7 +178,7 @@ def test_bf16_forward_and_backward_vs_oracle(built):
     ok = smooth_mask(inp["loc"].numpy(), inp["shapes"].numpy())
     assert rel_err(res["grad_attn"], ref["grad_attn"]) <= 1e-4      # fp32 outputs
     assert rel_err(res["grad_loc"] * ok, ref["grad_loc"] * ok) <= 1e-4
-    assert rel_err(res["grad_value"], ref["grad_value"]) <= 3e-2    # bf16 atomics accumulate rounding
+    assert rel_err(res["grad_value"], ref["grad_value"]) <= 1e-4    # fp32 accumulation of bf16 products
 
 
 # ----------------------------------------------------------------------------------------------
