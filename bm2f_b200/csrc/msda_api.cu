@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 
 #include "msda_fast.cuh"
 #include "msda_generic.cuh"
@@ -110,26 +111,30 @@ int make_map(CUtensorMap *map, const float *base, uint64_t rows, uint64_t cols, 
 constexpr int kNWarp = 16;
 
 template <typename T, int VEC, int L_, int SW, bool TMA, int CPS>
-cudaError_t launch_fast(bool bwd, const FastParams &p, const CUtensorMap &ml, const CUtensorMap &mw, int grid,
-                        cudaStream_t st)
+cudaError_t launch_fast(bool bwd, bool merge, bool wide, const FastParams &p, const CUtensorMap &ml, const CUtensorMap &mw,
+                        int grid, cudaStream_t st)
 {
     constexpr int G = (SW < kNWarp) ? kNWarp / SW : 1;
     constexpr int threads = (kNWarp + (TMA ? 1 : 0)) * 32;
-    if (bwd)
-        msda_bwd_fast_kernel<T, VEC, L_, 4, SW, kNWarp, G, TMA, CPS><<<grid, threads, 0, st>>>(p, ml, mw);
+    if (bwd && merge && VEC == 4)
+        msda_bwd_fast_kernel<T, VEC, L_, 4, SW, kNWarp, G, TMA, CPS, true><<<grid, threads, 0, st>>>(p, ml, mw);
+    else if (bwd)
+        msda_bwd_fast_kernel<T, VEC, L_, 4, SW, kNWarp, G, TMA, CPS, false><<<grid, threads, 0, st>>>(p, ml, mw);
+    else if (wide && std::is_same<T, float>::value && VEC == 4)
+        msda_fwd_fast256_kernel<L_, 4, SW, kNWarp, G, TMA, CPS><<<grid, threads, 0, st>>>(p, ml, mw);
     else
         msda_fwd_fast_kernel<T, VEC, L_, 4, SW, kNWarp, G, TMA, CPS><<<grid, threads, 0, st>>>(p, ml, mw);
     return cudaGetLastError();
 }
 
 struct FastChoice {
-    int vec, sw, tma, cps;
+    int vec, sw, tma, cps, merge, wide;
 };
 
 #define BM2F_CASE(T, VEC, L_, SW, TMA, CPS)                                              \
     if (c.vec == VEC && c.sw == SW && c.tma == TMA && c.cps == CPS) {                    \
         *found = true;                                                                   \
-        return launch_fast<T, VEC, L_, SW, (TMA != 0), CPS>(bwd, p, ml, mw, grid, st);   \
+        return launch_fast<T, VEC, L_, SW, (TMA != 0), CPS>(bwd, c.merge != 0, c.wide != 0, p, ml, mw, grid, st);   \
     }
 
 // Full sweep grid for the Mask2Former shape (L = 3, P = 4, fp32).
@@ -153,8 +158,8 @@ template <typename T, int L_>
 cudaError_t dispatch_default(const FastChoice &c, bool bwd, const FastParams &p, const CUtensorMap &ml,
                              const CUtensorMap &mw, int grid, cudaStream_t st, bool *found)
 {
-    BM2F_CASE(T, 4, L_, 16, 0, 2)
-    BM2F_CASE(T, 4, L_, 16, 1, 2)
+    BM2F_CASE(T, 4, L_, 32, 0, 1)
+    BM2F_CASE(T, 4, L_, 32, 1, 1)
     return cudaSuccess;
 }
 #undef BM2F_CASE
@@ -218,11 +223,16 @@ int run_fast(bool bwd, FastParams p, const Dims &d, int dtype, const bm2f_msda_t
 
     FastChoice c;
     c.vec = t.vec ? t.vec : 4;
-    c.sw = t.strip_w ? t.strip_w : 16;
+    // vec = 8: 256-bit forward gathers (fp32); the backward scatter has no 256-bit RED and stays at vec = 4
+    c.wide = (c.vec == 8 && dtype == BM2F_DTYPE_F32);
+    if (c.vec == 8) c.vec = 4;
+    // defaults = winner of the round-1 sweep on B200 (profiles/r01_sweep_cfg2.txt)
+    c.sw = t.strip_w ? t.strip_w : 32;
     c.tma = t.staging ? (t.staging == 1) : 1;
-    c.cps = t.ctas_per_sm ? t.ctas_per_sm : 2;
+    c.cps = t.ctas_per_sm ? t.ctas_per_sm : 1;
+    c.merge = t.merge ? (t.merge == 1) : 1;
     const bool sweepable = (dtype == BM2F_DTYPE_F32 && d.L == 3);
-    if (!sweepable) { c.vec = 4; c.sw = 16; c.cps = 2; }
+    if (!sweepable) { c.vec = 4; c.sw = 32; c.cps = 1; }
 
     const int grid_max = sms * c.cps;
     int rows = t.rows;

@@ -125,6 +125,21 @@ struct VecIO<float, 1> {
     }
 };
 
+
+// 256-bit predicated read-only load (LDG.E.ENL2.256.CONSTANT on sm_100a): 8 consecutive floats.
+// v must be zero-initialised by the caller; nothing is fetched when pred is false.
+__device__ __forceinline__ void ldg256_pred(const float *p, bool pred, float (&v)[8])
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "setp.ne.b32 P1, %9, 0;\n"
+        "@P1 ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+        "}\n"
+        : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7])
+        : "l"(p), "r"(static_cast<int>(pred)));
+}
+
 __device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)

@@ -51,7 +51,8 @@ struct Tabs {
     int jobs_per_bm;
 };
 
-constexpr int kStages = 8;
+// ring depth: 8 stages unless that would exceed the 48 KB static shared-memory budget
+constexpr int ring_stages(int sw, int lp) { return sw * lp * 12 * 8 <= 40 * 1024 ? 8 : 4; }
 
 template <int L_, int SW>
 __device__ __forceinline__ void build_tabs(Tabs<L_> &t, const FastParams &p)
@@ -135,6 +136,7 @@ struct StageLayout {
 template <int L_, int P_, int SW, int WPG>
 struct Ring {
     using Lay = StageLayout<SW, L_ * P_>;
+    static constexpr int kStages = ring_stages(SW, L_ * P_);
     alignas(128) unsigned char data[kStages * Lay::kBytes];
     alignas(8) uint64_t full[kStages];
     alignas(8) uint64_t empty[kStages];
@@ -185,7 +187,9 @@ msda_fwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_
     static_assert(NWARP % G == 0, "");
 
     __shared__ Tabs<L_> tabs;
-    __shared__ Ring<L_, P_, TMA ? SW : 1, WPG> ring;
+    using RingT = Ring<L_, P_, TMA ? SW : 1, WPG>;
+    constexpr int kStages = RingT::kStages;
+    __shared__ RingT ring;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -281,10 +285,116 @@ msda_fwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_
     });
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Forward, 256-bit variant (fp32 only): 4 lanes x 32 B per corner.  The 32 lanes are 8 groups =
+// 4 points x 2 footprint rows; a lane loads the two horizontally adjacent corners of its row with
+// two LDG.256, so a warp instruction moves 8 lines.  Measured L1 line rate of this access shape is
+// 1.6x the 8 x 16 B shape (profiles/r01_microbench.txt).
+// ------------------------------------------------------------------------------------------
+template <int L_, int P_, int SW, int NWARP, int G, bool TMA, int CPS>
+__global__ void __launch_bounds__((NWARP + (TMA ? 1 : 0)) * 32, CPS)
+msda_fwd_fast256_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_loc,
+                        const __grid_constant__ CUtensorMap tm_w)
+{
+    constexpr int D = 32, LP = L_ * P_, WPG = NWARP / G;
+    static_assert(P_ == 4, "one lane-group quartet per level");
+    using RingT = Ring<L_, P_, TMA ? SW : 1, WPG>;
+    constexpr int kStages = RingT::kStages;
+    __shared__ Tabs<L_> tabs;
+    __shared__ RingT ring;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        build_tabs<L_, SW>(tabs, p);
+        if (TMA) {
+            ring.init();
+            tma_prefetch_desc(&tm_loc);
+            tma_prefetch_desc(&tm_w);
+        }
+    }
+    __syncthreads();
+    if (TMA && warp == NWARP) {
+        if (lane == 0) ring.produce(tabs, p, &tm_loc, &tm_w);
+        return;
+    }
+    int H[L_], W[L_], st[L_];
+    float Hf[L_], Wf[L_];
+#pragma unroll
+    for (int l = 0; l < L_; ++l) {
+        H[l] = tabs.H[l]; W[l] = tabs.W[l]; st[l] = tabs.start[l];
+        Hf[l] = static_cast<float>(H[l]); Wf[l] = static_cast<float>(W[l]);
+    }
+    const int g = warp / WPG, wi = warp % WPG;
+    const int grp = lane >> 2, sub = lane & 3;
+    const int pt = grp & 3, dy = grp >> 2;
+    constexpr int MD = kHeads * D;
+    const float *value = static_cast<const float *>(p.value);
+    float *out = static_cast<float *>(p.out);
+
+    for_each_stage<L_, SW>(tabs, p, [&](int s, int b, int m, int q_base, int nq) {
+        if (G > 1 && (s % G) != g) return;
+        const int slot = s % kStages;
+        if (TMA) mbar_wait(&ring.full[slot], (s / kStages) & 1);
+        const float *vlane = value + (static_cast<size_t>(b) * p.S * kHeads + m) * D + sub * 8;
+        for (int qi = wi; qi < nq; qi += WPG) {
+            const int q = q_base + qi;
+            float xs[L_], ys[L_], ws[L_];
+            if (TMA) {
+                const float2 *sl = ring.loc(slot, qi);
+                const float *sw = ring.w(slot, qi);
+#pragma unroll
+                for (int l = 0; l < L_; ++l) {
+                    const float2 t = sl[l * 4 + pt];
+                    xs[l] = t.x; ys[l] = t.y; ws[l] = sw[l * 4 + pt];
+                }
+            } else {
+                const size_t k0 = ((static_cast<size_t>(b) * p.Lq + q) * kHeads + m) * LP;
+#pragma unroll
+                for (int l = 0; l < L_; ++l) {
+                    const float2 t = __ldg(reinterpret_cast<const float2 *>(p.loc) + k0 + l * 4 + pt);
+                    xs[l] = t.x; ys[l] = t.y; ws[l] = __ldg(p.attn + k0 + l * 4 + pt);
+                }
+            }
+            float acc[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+#pragma unroll
+            for (int l = 0; l < L_; ++l) {
+                const Footprint f = make_footprint(xs[l], ys[l], H[l], W[l], Hf[l], Wf[l]);
+                const bool ok0 = dy ? f.ok[2] : f.ok[0], ok1 = dy ? f.ok[3] : f.ok[1];
+                const float wrow = ws[l] * (dy ? f.lh : f.hh);
+                const float *c0 = vlane + static_cast<long long>(st[l] + (f.y0 + dy) * W[l] + f.x0) * MD;
+                float v0[8], v1[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) { v0[c] = 0.f; v1[c] = 0.f; }
+                ldg256_pred(c0, ok0, v0);
+                ldg256_pred(c0 + MD, ok1, v1);
+                const float w0 = wrow * f.hw, w1 = wrow * f.lw;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[c] = fmaf(w1, v1[c], fmaf(w0, v0[c], acc[c]));
+            }
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+            if (grp == 0) {
+                float4 *o4 = reinterpret_cast<float4 *>(out + ((static_cast<size_t>(b) * p.Lq + q) * kHeads + m) * D + sub * 8);
+                o4[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                o4[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            }
+        }
+        if (TMA) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ring.empty[slot]);
+        }
+    });
+}
+
 // ------------------------------------------------------------------------------------------
 // Backward
 // ------------------------------------------------------------------------------------------
-template <typename T, int VEC, int L_, int P_, int SW, int NWARP, int G, bool TMA, int CPS>
+template <typename T, int VEC, int L_, int P_, int SW, int NWARP, int G, bool TMA, int CPS, bool MERGE>
 __global__ void __launch_bounds__((NWARP + (TMA ? 1 : 0)) * 32, CPS)
 msda_bwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_loc,
                      const __grid_constant__ CUtensorMap tm_w)
@@ -293,7 +403,9 @@ msda_bwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_
     static_assert(P_ % LG == 0, "a lane-group iteration must stay inside one level");
 
     __shared__ Tabs<L_> tabs;
-    __shared__ Ring<L_, P_, TMA ? SW : 1, WPG> ring;
+    using RingT = Ring<L_, P_, TMA ? SW : 1, WPG>;
+    constexpr int kStages = RingT::kStages;
+    __shared__ RingT ring;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -370,18 +482,59 @@ msda_bwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_
                 }
                 // scatter grad_value; dot products of grad_out with the four corners
                 float t[4];
+                if constexpr (MERGE && VEC == 4) {
+                    // Warp-aggregated scatter: the 16 corners of this iteration (4 points x 4 corners) all
+                    // carry the same grad_out vector, so corners that land on the same pixel are merged by
+                    // adding their scalar weights; one RED per distinct pixel.  Lanes sub<4 of every group
+                    // stand for corner k=sub; match.any finds equal pixels, two pointer-jumping rounds sum
+                    // up to 4 chained duplicates, every 4th chain member issues.
+                    const int kk = sub & 3;
+                    const bool okk = kk == 0 ? f.ok[0] : (kk == 1 ? f.ok[1] : (kk == 2 ? f.ok[2] : f.ok[3]));
+                    const bool part = (sub < 4) && okk;
+                    const float wyk = (kk >> 1) ? f.lh : f.hh, wxk = (kk & 1) ? f.lw : f.hw;
+                    const int pix = (f.y0 + (kk >> 1)) * W[l] + f.x0 + (kk & 1);
+                    const int key = part ? pix : -1 - lane;
+                    float sum = part ? ws[it] * wyk * wxk : 0.f;
+                    const unsigned mask = __match_any_sync(0xffffffffu, key);
+                    const unsigned above = mask & ~((2u << lane) - 1u);
+                    int nxt = above ? __ffs(above) - 1 : -1;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (f.ok[k]) {
-                        const float cwk = ws[it] * wy[k >> 1] * wx[k & 1];
-                        float r[VEC];
-#pragma unroll
-                        for (int c = 0; c < VEC; ++c) r[c] = cwk * go[c];
-                        VecIO<float, VEC>::red_add(gvlane + eoff[k], r);
+                    for (int round = 0; round < 2; ++round) {
+                        const int src = nxt < 0 ? lane : nxt;
+                        const float sv = __shfl_sync(0xffffffffu, sum, src);
+                        const int nv = __shfl_sync(0xffffffffu, nxt, src);
+                        sum += nxt < 0 ? 0.f : sv;
+                        nxt = nxt < 0 ? -1 : nv;
                     }
-                    t[k] = 0.f;
+                    const int pos = __popc(mask & ((1u << lane) - 1u));
+                    const float merged = (part && (pos & 3) == 0) ? sum : 0.f;
 #pragma unroll
-                    for (int c = 0; c < VEC; ++c) t[k] = fmaf(go[c], v[k][c], t[k]);
+                    for (int k = 0; k < 4; ++k) {
+                        const float wk = __shfl_sync(0xffffffffu, merged, (lane & 24) | k);
+                        if (wk != 0.f) {
+                            float r[VEC];
+#pragma unroll
+                            for (int c = 0; c < VEC; ++c) r[c] = wk * go[c];
+                            VecIO<float, VEC>::red_add(gvlane + eoff[k], r);
+                        }
+                        t[k] = 0.f;
+#pragma unroll
+                        for (int c = 0; c < VEC; ++c) t[k] = fmaf(go[c], v[k][c], t[k]);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (f.ok[k]) {
+                            const float cwk = ws[it] * wy[k >> 1] * wx[k & 1];
+                            float r[VEC];
+#pragma unroll
+                            for (int c = 0; c < VEC; ++c) r[c] = cwk * go[c];
+                            VecIO<float, VEC>::red_add(gvlane + eoff[k], r);
+                        }
+                        t[k] = 0.f;
+#pragma unroll
+                        for (int c = 0; c < VEC; ++c) t[k] = fmaf(go[c], v[k][c], t[k]);
+                    }
                 }
                 // <grad_out, sample>, d/dw_im, d/dh_im restricted to this lane's channels
                 float pa = f.hh * (f.hw * t[0] + f.lw * t[1]) + f.lh * (f.hw * t[2] + f.lw * t[3]);

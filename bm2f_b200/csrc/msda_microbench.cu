@@ -123,6 +123,40 @@ __global__ void __launch_bounds__(512) tma_red_kernel(float *buf, uint32_t nline
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// Hybrid: every warp iteration issues one red.v4 (4 random lines through the LSU/L1TEX path) AND one
+// 512-byte TMA bulk reduce (4 consecutive lines through the TMA engine).  If the two paths have separate
+// per-SM limits and L2 has headroom, lines/s exceeds either path alone.
+__global__ void __launch_bounds__(512) hybrid_red_kernel(float *buf, uint32_t nlines, int iters)
+{
+    __shared__ __align__(128) float stage[16][2][128];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int grp = lane >> 3, sub = lane & 7;
+    for (int i = 0; i < iters; ++i) {
+        float *s = stage[warp][i & 1];
+        if (i >= 2) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+        }
+        reinterpret_cast<float4 *>(s)[lane] = make_float4(1.f, 1.f, 1.f, 1.f);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        const uint32_t h = mix((gwarp * 977u + i) * 64u + grp);
+        const uint32_t line = (uint32_t)(((uint64_t)h * (nlines - 4)) >> 32);
+        asm volatile("red.global.add.v4.f32 [%0], {%1,%1,%1,%1};" ::"l"(buf + (size_t)line * 32 + sub * 4), "f"(1.0f));
+        if (lane == 0) {
+            const uint32_t h2 = mix((gwarp * 977u + i) * 64u + 17u);
+            const uint32_t l2 = (uint32_t)(((uint64_t)h2 * (nlines - 4)) >> 32);
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], 512;" ::"l"(
+                             buf + (size_t)l2 * 32),
+                         "r"((uint32_t)__cvta_generic_to_shared(s))
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 template <typename F>
 float time_ms(F launch, int reps)
 {
@@ -272,6 +306,16 @@ int main()
         const double bytes = (double)(warps / 2) * it * 512.0 * 2;
         printf("%-24s %7.1f MB  %9.1f GB/s  (half grid TMA-reduce + half grid red.v4 concurrently)\n", "tma+lsu_red", 44.0,
                bytes / ms * 1e-6);
+    }
+
+    {   // hybrid LSU red.v4 + TMA bulk reduce from the same warps
+        const uint32_t nlines = (uint32_t)(44.0 * 1048576.0 / 128);
+        const int it = 256;
+        for (int g : {sms, sms * 2, sms * 4}) {
+            auto launch = [&] { hybrid_red_kernel<<<g, threads>>>(buf, nlines, it); };
+            const float ms = time_ms(launch, 3);
+            printf("hybrid_red_v4+tma512  ctas %4d  %9.1f GB/s\n", g, (double)(g * threads / 32) * it * 8 * 128.0 / ms * 1e-6);
+        }
     }
     // plain streaming copy for reference (same denominator as MEASURED_PEAKS.json hbm_gbs)
     {

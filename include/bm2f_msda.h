@@ -71,14 +71,16 @@ typedef enum {
 /* Tunables of the D=32 fast path; zero-initialise for defaults.  Exposed so that bench.py and
  * the tests can sweep / pin every variant through the same ABI. */
 typedef struct {
-    int vec;        /* floats per lane per corner: 4 (8 lanes x 128-bit, default), 2 or 1        */
+    int vec;        /* floats per lane per corner: 4 (8 lanes x 128-bit, default), 2, 1, or 8 =
+                       256-bit forward gathers (fp32 forward only; backward then uses 4)          */
     int staging;    /* 0 = default, 1 = TMA tensor-map staging of loc/weights, 2 = direct loads */
-    int strip_w;    /* queries per strip row (stage), 0 = default (16)                           */
+    int strip_w;    /* queries per strip row (stage): 8, 16 or 32; 0 = default (32)              */
     int rows;       /* strip rows per job, 0 = auto from problem size                            */
-    int ctas_per_sm;/* persistent CTAs per SM, 0 = default                                        */
+    int ctas_per_sm;/* persistent CTAs per SM: 1 or 2; 0 = default (1)                            */
     int force_generic; /* 1 = always use the any-D kernel                                        */
     int order;      /* 0 = default; 1 = 1-D query order (ignore level geometry)                  */
-    int reserved[9];
+    int merge;      /* backward: 0 = default (on), 1 = merge equal-pixel corners in-warp, 2 = off */
+    int reserved[8];
 } bm2f_msda_tuning_t;
 
 /* Library / ABI identification. */

@@ -122,11 +122,13 @@ def small_problem():
     return inp, oracle_ref(inp)
 
 
-VARIANTS = [dict(vec=v, staging=s, strip_w=sw, ctas_per_sm=c)
-            for v in (4, 2, 1) for s in (1, 2) for sw in (8, 16, 32) for c in (1, 2)]
+VARIANTS = [dict(vec=v, staging=s, strip_w=sw, ctas_per_sm=c, merge=1)
+            for v in (8, 4, 2, 1) for s in (1, 2) for sw in (8, 16, 32) for c in (1, 2)]
+VARIANTS += [dict(vec=4, staging=s, strip_w=sw, ctas_per_sm=1, merge=2) for s in (1, 2) for sw in (16, 32)]
 
 
-@pytest.mark.parametrize("var", VARIANTS, ids=lambda d: "v{vec}_st{staging}_sw{strip_w}_c{ctas_per_sm}".format(**d))
+@pytest.mark.parametrize("var", VARIANTS,
+                         ids=lambda d: "v{vec}_st{staging}_sw{strip_w}_c{ctas_per_sm}_m{merge}".format(**d))
 def test_fast_variants_vs_oracle(var, small_problem, built):
     inp, ref = small_problem
     res = run_cabi(inp["value"], inp["shapes"], inp["start"], inp["loc"], inp["attn"], inp["grad_out"],
@@ -266,6 +268,18 @@ def test_full_size_staging_variants_agree_bitwise_forward(full_problem, built):
     a = _fwd(d, tuning=cabi.make_tuning(staging=1))
     b = _fwd(d, tuning=cabi.make_tuning(staging=2))
     assert torch.equal(a, b)
+    # 256-bit gathers change the summation order only
+    c = _fwd(d, tuning=cabi.make_tuning(vec=8))
+    assert (a - c).abs().max().item() <= 1e-5 * max(1.0, a.abs().max().item())
+
+
+def test_full_size_merged_scatter_matches_unmerged(full_problem, built):
+    # warp-aggregated REDs (equal-pixel corners merged) vs one RED per corner
+    d = full_problem
+    a = _bwd(d, d["grad_out"], tuning=cabi.make_tuning(merge=1))
+    b = _bwd(d, d["grad_out"], tuning=cabi.make_tuning(merge=2))
+    assert (a[0] - b[0]).abs().max().item() <= 1e-4 * b[0].abs().max().item()
+    assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])       # grad_loc / grad_attn untouched by merging
 
 
 # ----------------------------------------------------------------------------------------------

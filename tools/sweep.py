@@ -50,20 +50,16 @@ def main():
             best = min(best, a.elapsed_time(b))
         return best
 
-    grid = dict(vec=(4, 2, 1), staging=(1, 2), strip_w=(8, 16, 32), ctas_per_sm=(1, 2), rows=(0, 8, 64), order=(0, 1))
+    grid = dict(vec=(8, 4), staging=(1, 2), strip_w=(16, 32), ctas_per_sm=(1, 2), rows=(0,), order=(0,), merge=(1, 2))
     if args.quick:
-        grid = dict(vec=(4,), staging=(1, 2), strip_w=(16,), ctas_per_sm=(1, 2), rows=(0,), order=(0, 1))
+        grid = dict(vec=(8, 4), staging=(1,), strip_w=(32,), ctas_per_sm=(1,), rows=(0,), order=(0,), merge=(1, 2))
     res = []
     gb_f = W.gather_bytes(S, "fwd") * N / 1e9
     print(f"# cfg{args.cfg} batch {N} S={S}; gather bytes fwd {gb_f:.2f} GB; hbm fwd {W.hbm_bytes(S,'fwd')*N/1e9:.3f} GB "
           f"bwd {W.hbm_bytes(S,'bwd')*N/1e9:.3f} GB")
-    print(f"{'vec':>3} {'stg':>3} {'sw':>3} {'cps':>3} {'rows':>4} {'ord':>3} | {'fwd ms':>8} {'bwd ms':>8} {'fwd lineTB/s':>12} {'img/s(6L)':>10}")
+    print(f"{'vec':>3} {'stg':>3} {'sw':>3} {'cps':>3} {'rows':>4} {'ord':>3} {'mrg':>3} | {'fwd ms':>8} {'bwd ms':>8} {'fwd lineTB/s':>12} {'img/s(6L)':>10}")
     for vals in itertools.product(*grid.values()):
         kw = dict(zip(grid.keys(), vals))
-        if kw["order"] == 1 and (kw["rows"] != 0 or kw["vec"] != 4):
-            continue
-        if kw["rows"] != 0 and (kw["vec"] != 4):
-            continue
         t = cabi.make_tuning(**kw)
         try:
             f, b = timeit(fwd, t), timeit(bwd, t)
@@ -71,7 +67,7 @@ def main():
             print(kw, "ERR", e); continue
         r = dict(kw, fwd_ms=f, bwd_ms=b, img_s=N / (6 * (f + b) * 1e-3))
         res.append(r)
-        print(f"{kw['vec']:>3} {kw['staging']:>3} {kw['strip_w']:>3} {kw['ctas_per_sm']:>3} {kw['rows']:>4} {kw['order']:>3} | "
+        print(f"{kw['vec']:>3} {kw['staging']:>3} {kw['strip_w']:>3} {kw['ctas_per_sm']:>3} {kw['rows']:>4} {kw['order']:>3} {kw['merge']:>3} | "
               f"{f:8.3f} {b:8.3f} {gb_f / f:12.2f} {r['img_s']:10.1f}", flush=True)
     gen = cabi.make_tuning(force_generic=1)
     f, b = timeit(fwd, gen), timeit(bwd, gen)
