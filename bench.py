@@ -354,7 +354,17 @@ def run_ours(args, wl):
         gb = W.gather_bytes(wl.S, k, wl.dtype) * nb
         gather[k] = {"ms_per_launch": kms[k], "line_traffic_GBs": gb / (kms[k] * 1e-3) / 1e9,
                      "hbm_GBs": W.hbm_bytes(wl.S, k, wl.dtype) * nb / (kms[k] * 1e-3) / 1e9}
-    gather["measured_peaks"] = facts.get("gather_peaks")
+    peaks_g = facts.get("gather_peaks") or {}
+    gather["measured_peaks"] = peaks_g or None
+    if peaks_g:
+        # forward: gathered 128-B lines vs the measured L1 line rate of the same access shape (8 lanes x 16 B);
+        # backward: RED lines vs the measured red.global.add.v4.f32 rate (L2-side limit)
+        if "fwd" in gather:
+            gather["fwd"]["frac_of_measured_l1_gather_peak"] = gather["fwd"]["line_traffic_GBs"] / peaks_g["l1_resident_8x16B"]
+        if "bwd" in gather:
+            red_gbs = W.gather_bytes(wl.S, "fwd", wl.dtype) * nb / (kms["bwd"] * 1e-3) / 1e9
+            gather["bwd"]["red_line_traffic_GBs"] = red_gbs
+            gather["bwd"]["frac_of_measured_red_peak"] = red_gbs / peaks_g["red_v4_l2_resident"]
 
     # ---- reference CUDA op, same inputs, same timing (only when oracle/_ref was built) ----------------
     ref_cuda = None

@@ -230,7 +230,9 @@ int run_fast(bool bwd, FastParams p, const Dims &d, int dtype, const bm2f_msda_t
     c.sw = t.strip_w ? t.strip_w : 32;
     c.tma = t.staging ? (t.staging == 1) : 1;
     c.cps = t.ctas_per_sm ? t.ctas_per_sm : 1;
-    c.merge = t.merge ? (t.merge == 1) : 1;
+    // in-warp merging of equal-pixel corners removes 17 % of the REDs but its match/shuffle chain costs
+    // more than it saves on B200 (2.76 ms -> 3.53 ms, profiles/r01_sweep_cfg2_b.txt): off unless asked for
+    c.merge = (t.merge == 1);
     const bool sweepable = (dtype == BM2F_DTYPE_F32 && d.L == 3);
     if (!sweepable) { c.vec = 4; c.sw = 32; c.cps = 1; }
 

@@ -79,7 +79,8 @@ typedef struct {
     int ctas_per_sm;/* persistent CTAs per SM: 1 or 2; 0 = default (1)                            */
     int force_generic; /* 1 = always use the any-D kernel                                        */
     int order;      /* 0 = default; 1 = 1-D query order (ignore level geometry)                  */
-    int merge;      /* backward: 0 = default (on), 1 = merge equal-pixel corners in-warp, 2 = off */
+    int merge;      /* backward: 1 = merge equal-pixel corners in-warp before the REDs; 0/2 = off
+                       (default: measured slower on B200)                          */
     int reserved[8];
 } bm2f_msda_tuning_t;
 
