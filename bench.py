@@ -253,7 +253,7 @@ def run_ours(args, wl):
     ev = lambda: torch.cuda.Event(enable_timing=True)
     kernel_events = {"fwd": [], "bwd": []}
 
-    def step(record=False):
+    def step(record=False, collective=True):
         outs = None
         for L in layers:
             if record:
@@ -270,7 +270,7 @@ def run_ours(args, wl):
                     b.record(); kernel_events["bwd"].append((a, b))
             else:
                 outs = out
-        if grad_bucket is not None:
+        if grad_bucket is not None and collective:
             # DDP-style: projection-weight gradients of the 6 layers, one flat bucket, side stream
             comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(comm_stream):
@@ -310,7 +310,7 @@ def run_ours(args, wl):
     if sampler:
         t_end = time.perf_counter() + 0.5
         while time.perf_counter() < t_end:
-            step()
+            step(collective=False)          # rank-local only: the other ranks are not in this loop
         torch.cuda.synchronize()
         clocks = sampler.stop()
     if dist:

@@ -18,7 +18,8 @@ DTYPE_F32, DTYPE_F64, DTYPE_BF16 = 0, 1, 2
 SYMBOLS = (
     "bm2f_msda_abi_version", "bm2f_msda_build_info", "bm2f_msda_last_error", "bm2f_msda_launch_count",
     "bm2f_msda_set_default_tuning", "bm2f_msda_check_im2col_step", "bm2f_msda_forward",
-    "bm2f_msda_backward", "bm2f_msda_forward_backward_host",
+    "bm2f_msda_backward", "bm2f_msda_forward_backward_host", "bm2f_msda_fused_supported",
+    "bm2f_msda_fused_forward", "bm2f_msda_fused_backward", "bm2f_linear_workspace_bytes", "bm2f_linear_forward",
 )
 
 
@@ -55,6 +56,16 @@ def lib():
         L.bm2f_msda_forward.restype = ci
         L.bm2f_msda_backward.argtypes = [vp, i64p, i64p, vp, vp, vp, vp, vp, vp] + [ci] * 8 + [tp, vp]
         L.bm2f_msda_backward.restype = ci
+        L.bm2f_msda_fused_supported.argtypes = [ci] * 5
+        L.bm2f_msda_fused_supported.restype = ci
+        L.bm2f_msda_fused_forward.argtypes = [vp, i64p, i64p, vp, vp, vp, vp] + [ci] * 8 + [tp, vp]
+        L.bm2f_msda_fused_forward.restype = ci
+        L.bm2f_msda_fused_backward.argtypes = [vp, i64p, i64p, vp, vp, vp, vp, vp, vp, vp] + [ci] * 8 + [tp, vp]
+        L.bm2f_msda_fused_backward.restype = ci
+        L.bm2f_linear_workspace_bytes.argtypes = [ci, ci]
+        L.bm2f_linear_workspace_bytes.restype = ctypes.c_size_t
+        L.bm2f_linear_forward.argtypes = [vp] * 5 + [ci] * 4 + [vp]
+        L.bm2f_linear_forward.restype = ci
         L.bm2f_msda_forward_backward_host.argtypes = [vp] * 10 + [ci] * 8 + [tp]
         L.bm2f_msda_forward_backward_host.restype = ci
         _lib = L
@@ -99,6 +110,25 @@ def forward_backward_host(value, shapes, start, loc, attn, grad_out, out, grad_v
     _check(lib().bm2f_msda_forward_backward_host(value, shapes, start, loc, attn, grad_out, out, grad_value,
                                                  grad_loc, grad_attn, *dims, dtype, _tp(tuning)),
            "bm2f_msda_forward_backward_host")
+
+
+def fused_forward(value, shapes, start, ref, offsets, logits, out, dims, dtype=DTYPE_F32, tuning=None, stream=0):
+    """softmax(logits) and ref + offsets/(W,H) are computed inside the kernel."""
+    _check(lib().bm2f_msda_fused_forward(value, shapes, start, ref, offsets, logits, out, *dims, dtype, _tp(tuning),
+                                         stream), "bm2f_msda_fused_forward")
+
+
+def fused_backward(value, shapes, start, ref, offsets, logits, grad_out, grad_value, grad_offsets, grad_logits, dims,
+                   dtype=DTYPE_F32, tuning=None, stream=0):
+    _check(lib().bm2f_msda_fused_backward(value, shapes, start, ref, offsets, logits, grad_out, grad_value,
+                                          grad_offsets, grad_logits, *dims, dtype, _tp(tuning), stream),
+           "bm2f_msda_fused_backward")
+
+
+def linear_forward(x, weight, bias, y, workspace, rows, out_features, in_features, split=3, stream=0):
+    """tcgen05 projection GEMM: y = x @ weight^T + bias (device addresses; bias may be 0)."""
+    _check(lib().bm2f_linear_forward(x, weight, bias, y, workspace, rows, out_features, in_features, split, stream),
+           "bm2f_linear_forward")
 
 
 def launch_count() -> int:

@@ -1,0 +1,312 @@
+// tcgen05 GEMM for the MSDeformAttn projections (value_proj, sampling_offsets||attention_weights,
+// output_proj — reference: nn.Linear x4 in ops/modules/ms_deform_attn.py:59-62,98-102,124):
+//
+//     Y[M, N] = X[M, K] * W[N, K]^T + bias[N]          K = 256 (d_model), N in {96..288}, fp32 in / out
+//
+// fp32 parity matters (the reference runs these layers in fp32, msdeformattn.py:314-320), so the product
+// is computed as a 3-term TF32 split on the 5th-generation tensor cores:
+//     x = x_hi + x_lo,  w = w_hi + w_lo    (hi = top 19 bits, exactly representable in TF32)
+//     Y ~= x_hi*w_hi + x_lo*w_hi + x_hi*w_lo                (the dropped x_lo*w_lo term is ~2^-22 relative)
+// with fp32 accumulation in tensor memory (TMEM).
+//
+// One CTA per 128-row tile of X, 6 warps:
+//   warp 0      TMEM allocation; lane 0 = TMA producer of the W_hi / W_lo k-blocks (tensor maps, 128B swizzle)
+//   warp 1      lane 0 = MMA issuer: tcgen05.mma.cta_group::1.kind::tf32, M=128, N=tile width, K=8 per instruction
+//   warps 2..5  X producers: coalesced 128-bit global loads, split into hi / lo, written to shared memory in
+//               the UMMA K-major SWIZZLE_128B layout; after the main loop the same warps are the epilogue:
+//               tcgen05.ld (TMEM -> registers), + bias, 128-bit stores.
+// Two shared-memory stages of one k-block (32 floats = one 128-byte swizzle row) each, full/empty mbarriers;
+// tcgen05.commit releases a stage when the MMAs that read it have retired.
+#pragma once
+
+#include "msda_common.cuh"
+
+namespace bm2f {
+
+constexpr int kGemmK = 256;         // d_model
+constexpr int kGemmBlockM = 128;
+constexpr int kGemmBlockK = 32;     // floats per k-block = 128 bytes = one SWIZZLE_128B row
+constexpr int kGemmStages = 2;
+constexpr int kGemmThreads = 192;
+
+struct LinearParams {
+    const float *x;      // (M, K)
+    const float *bias;   // (N) or nullptr
+    float *y;            // (M, N)
+    int M, N;
+    int split;           // 3 = tf32x3 (fp32-grade), 1 = single TF32 pass
+};
+
+// ---- tcgen05 / TMEM wrappers -------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_slot, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], TF32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrives when every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread (thread i <-> TMEM lane base+i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
+{
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor, K-major, SWIZZLE_128B, one 128-byte row per matrix row, 8-row atoms of
+// 1024 bytes (stride byte offset).  Field layout = cute::UMMA::SmemDescriptor (sm_100).
+__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3ffff) >> 4);          // [0,14)  start address >> 4
+    d |= static_cast<uint64_t>(0) << 16;                             // [16,30) leading byte offset (unused, 1 atom in K)
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;                     // [32,46) stride byte offset >> 4
+    d |= static_cast<uint64_t>(1) << 46;                             // [46,48) descriptor version (sm_100)
+    d |= static_cast<uint64_t>(2) << 61;                             // [61,64) layout: SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulator, TF32 A/B, both K-major.
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n)
+{
+    return (1u << 4)                                   // c_format = F32
+           | (2u << 7)                                 // a_format = TF32
+           | (2u << 10)                                // b_format = TF32
+           | (0u << 15) | (0u << 16)                   // A, B K-major
+           | (static_cast<uint32_t>(n >> 3) << 17)     // N / 8
+           | (static_cast<uint32_t>(m >> 4) << 24);    // M / 16
+}
+
+// mbarrier wait with a poll budget: a descriptor / barrier bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (uint32_t i = 0; i < (1u << 24); ++i) {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+
+// NT = tile width in columns: the whole N of the layer (N <= 256) or half of it (N = 288 -> 2 x 144).
+// NH = number of such tiles per CTA (1 or 2); TMEM columns used = NH * NT.
+template <int NT, int NH>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+linear_tf32x3_kernel(const LinearParams p, const __grid_constant__ CUtensorMap tm_whi,
+                     const __grid_constant__ CUtensorMap tm_wlo)
+{
+    constexpr int N = NT * NH;
+    constexpr int kXBytes = kGemmBlockM * kGemmBlockK * 4;              // 16 KB
+    constexpr int kWBytes = N * kGemmBlockK * 4;                        // N x 128 B
+    constexpr int kStageBytes = 2 * kXBytes + 2 * kWBytes;
+    constexpr int kKBlocks = kGemmK / kGemmBlockK;                      // 8
+    constexpr uint32_t kTmemCols = (N <= 32) ? 32 : (N <= 64) ? 64 : (N <= 128) ? 128 : (N <= 256) ? 256 : 512;
+    static_assert(NT % 16 == 0 && NT <= 256, "UMMA N for M = 128");
+    static_assert((NT * 128) % 1024 == 0, "second tile must start on a swizzle atom");
+
+    extern __shared__ unsigned char smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment; the launch allocates 1 KB of slack for this round-up
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t full_bar[kGemmStages], empty_bar[kGemmStages], acc_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = blockIdx.x * kGemmBlockM;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGemmStages; ++s) {
+            mbar_init(&full_bar[s], 128 + 1);   // 128 X-producer threads + the TMA producer's expect_tx arrive
+            mbar_init(&empty_bar[s], 1);        // tcgen05.commit
+        }
+        mbar_init(&acc_bar, 1);
+        fence_mbar_init();
+        tma_prefetch_desc(&tm_whi);
+        tma_prefetch_desc(&tm_wlo);
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    auto stage_ptr = [&](int s) { return smem + s * kStageBytes; };
+
+    if (warp == 0) {
+        // ---------------- TMA producer: W_hi and W_lo k-blocks ----------------
+        if (lane == 0) {
+            for (int kb = 0; kb < kKBlocks; ++kb) {
+                const int s = kb % kGemmStages;
+                mbar_wait_bounded(&empty_bar[s], ((kb / kGemmStages) & 1) ^ 1);
+                mbar_arrive_expect_tx(&full_bar[s], p.split == 3 ? 2 * kWBytes : kWBytes);
+                unsigned char *w_hi = stage_ptr(s) + 2 * kXBytes;
+                unsigned char *w_lo = w_hi + kWBytes;
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                    tma_load_2d(w_hi + h * NT * 128, &tm_whi, kb * kGemmBlockK, h * NT, &full_bar[s]);
+                    if (p.split == 3) tma_load_2d(w_lo + h * NT * 128, &tm_wlo, kb * kGemmBlockK, h * NT, &full_bar[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(kGemmBlockM, NT);
+            for (int kb = 0; kb < kKBlocks; ++kb) {
+                const int s = kb % kGemmStages;
+                mbar_wait_bounded(&full_bar[s], (kb / kGemmStages) & 1);
+                tc_fence_after();
+                const uint32_t x_hi = smem_u32(stage_ptr(s));
+                const uint32_t x_lo = x_hi + kXBytes;
+                const uint32_t w_hi = x_hi + 2 * kXBytes;
+                const uint32_t w_lo = w_hi + kWBytes;
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                    const uint32_t d = tmem_base + h * NT;
+#pragma unroll
+                    for (int k = 0; k < kGemmBlockK / 8; ++k) {
+                        const uint32_t koff = k * 32;     // 8 floats along K inside the 128-byte swizzle row
+                        const uint64_t a_hi = umma_desc_k128(x_hi + koff);
+                        const uint64_t b_hi = umma_desc_k128(w_hi + h * NT * 128 + koff);
+                        umma_tf32(d, a_hi, b_hi, idesc, (kb | k) ? 1u : 0u);
+                        if (p.split == 3) {
+                            const uint64_t a_lo = umma_desc_k128(x_lo + koff);
+                            const uint64_t b_lo = umma_desc_k128(w_lo + h * NT * 128 + koff);
+                            umma_tf32(d, a_lo, b_hi, idesc, 1u);
+                            umma_tf32(d, a_hi, b_lo, idesc, 1u);
+                        }
+                    }
+                }
+                umma_commit(&empty_bar[s]);            // stage reusable once these MMAs retire
+            }
+            umma_commit(&acc_bar);                     // accumulator complete
+        }
+    } else {
+        // ---------------- X producers (warps 2..5), then epilogue ----------------
+        const int t = threadIdx.x - 64;                // 0..127
+        const int c16 = t & 7;                         // 16-byte chunk inside the 128-byte row
+        const int rsub = t >> 3;                       // 0..15
+        for (int kb = 0; kb < kKBlocks; ++kb) {
+            const int s = kb % kGemmStages;
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int r = rsub + 16 * j;
+                const int gr = row0 + r;
+                v[j] = gr < p.M ? __ldg(reinterpret_cast<const float4 *>(p.x + static_cast<size_t>(gr) * kGemmK +
+                                                                           kb * kGemmBlockK) + c16)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            mbar_wait_bounded(&empty_bar[s], ((kb / kGemmStages) & 1) ^ 1);
+            unsigned char *x_hi = stage_ptr(s);
+            unsigned char *x_lo = x_hi + kXBytes;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int r = rsub + 16 * j;
+                const uint32_t off = r * 128 + ((c16 ^ (r & 7)) << 4);      // SWIZZLE_128B
+                float4 hi, lo;
+                hi.x = __uint_as_float(__float_as_uint(v[j].x) & 0xffffe000u); lo.x = v[j].x - hi.x;
+                hi.y = __uint_as_float(__float_as_uint(v[j].y) & 0xffffe000u); lo.y = v[j].y - hi.y;
+                hi.z = __uint_as_float(__float_as_uint(v[j].z) & 0xffffe000u); lo.z = v[j].z - hi.z;
+                hi.w = __uint_as_float(__float_as_uint(v[j].w) & 0xffffe000u); lo.w = v[j].w - hi.w;
+                *reinterpret_cast<float4 *>(x_hi + off) = hi;
+                *reinterpret_cast<float4 *>(x_lo + off) = lo;
+            }
+            fence_async_smem();                        // generic-proxy writes -> visible to the tensor core (async proxy)
+            mbar_arrive(&full_bar[s]);
+        }
+        // epilogue: thread <-> one output row; warp w may touch TMEM lanes 32*(w%4) .. +31
+        mbar_wait_bounded(&acc_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int gr = row0 + r;
+        float *yrow = p.y + static_cast<size_t>(gr) * p.N;
+#pragma unroll 1
+        for (int c0 = 0; c0 < N; c0 += 32) {
+            float acc[32];
+            tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, acc);
+            if (gr < p.M) {
+#pragma unroll
+                for (int c = 0; c < 32; c += 4) {
+                    float4 o = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+                    if (p.bias) {
+                        const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + c0 + c));
+                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                    }
+                    *reinterpret_cast<float4 *>(yrow + c0 + c) = o;
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+template <int NT, int NH>
+constexpr int linear_smem_bytes()
+{
+    return kGemmStages * (2 * kGemmBlockM * kGemmBlockK * 4 + 2 * NT * NH * kGemmBlockK * 4) + 1024;
+}
+
+// W (N, K) -> W_hi, W_lo (exact TF32 split); tiny, run once per weight version
+__global__ void split_tf32_kernel(const float *__restrict__ w, float *__restrict__ hi, float *__restrict__ lo, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float x = w[i];
+        const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+        hi[i] = h;
+        lo[i] = x - h;
+    }
+}
+
+}  // namespace bm2f

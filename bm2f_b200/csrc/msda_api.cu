@@ -17,6 +17,7 @@
 
 #include "msda_fast.cuh"
 #include "msda_generic.cuh"
+#include "linear_tf32x3.cuh"
 
 namespace {
 
@@ -92,7 +93,7 @@ EncodeTiledFn encode_fn()
 
 // 2-D fp32 matrix (rows x cols, row-major) -> boxes of (box_rows x box_cols).
 int make_map(CUtensorMap *map, const float *base, uint64_t rows, uint64_t cols, uint32_t box_rows,
-             uint32_t box_cols)
+             uint32_t box_cols, bool swizzle128 = false)
 {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(BM2F_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
@@ -101,7 +102,8 @@ int make_map(CUtensorMap *map, const float *base, uint64_t rows, uint64_t cols, 
     const cuuint32_t box[2] = {box_cols, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstride, box,
-                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(BM2F_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return BM2F_OK;
@@ -124,6 +126,20 @@ cudaError_t launch_fast(bool bwd, bool merge, bool wide, const FastParams &p, co
         msda_fwd_fast256_kernel<L_, 4, SW, kNWarp, G, TMA, CPS><<<grid, threads, 0, st>>>(p, ml, mw);
     else
         msda_fwd_fast_kernel<T, VEC, L_, 4, SW, kNWarp, G, TMA, CPS><<<grid, threads, 0, st>>>(p, ml, mw);
+    return cudaGetLastError();
+}
+
+// Fused-prologue variants (softmax + location arithmetic in the kernel): default tile shape only.
+template <typename T, int L_, bool TMA>
+cudaError_t launch_fused(bool bwd, const FastParams &p, const CUtensorMap &ml, const CUtensorMap &mw, int grid,
+                         cudaStream_t st)
+{
+    constexpr int SW = 32, CPS = 1, G = 1;
+    constexpr int threads = (kNWarp + (TMA ? 1 : 0)) * 32;
+    if (bwd)
+        msda_bwd_fast_kernel<T, 4, L_, 4, SW, kNWarp, G, TMA, CPS, false, true><<<grid, threads, 0, st>>>(p, ml, mw);
+    else
+        msda_fwd_fast_kernel<T, 4, L_, 4, SW, kNWarp, G, TMA, CPS, true><<<grid, threads, 0, st>>>(p, ml, mw);
     return cudaGetLastError();
 }
 
@@ -214,7 +230,8 @@ bool fast_eligible(const Dims &d, int dtype, const bm2f_msda_tuning_t &t, const 
     return true;
 }
 
-int run_fast(bool bwd, FastParams p, const Dims &d, int dtype, const bm2f_msda_tuning_t &t, cudaStream_t st)
+int run_fast(bool bwd, FastParams p, const Dims &d, int dtype, const bm2f_msda_tuning_t &t, cudaStream_t st,
+             bool fused = false)
 {
     int sms = 0, cc = 0;
     int rc = device_info(&sms, &cc);
@@ -234,7 +251,7 @@ int run_fast(bool bwd, FastParams p, const Dims &d, int dtype, const bm2f_msda_t
     // more than it saves on B200 (2.76 ms -> 3.53 ms, profiles/r01_sweep_cfg2_b.txt): off unless asked for
     c.merge = (t.merge == 1);
     const bool sweepable = (dtype == BM2F_DTYPE_F32 && d.L == 3);
-    if (!sweepable) { c.vec = 4; c.sw = 32; c.cps = 1; }
+    if (!sweepable || fused) { c.vec = 4; c.sw = 32; c.cps = 1; c.merge = 0; c.wide = 0; }
 
     const int grid_max = sms * c.cps;
     int rows = t.rows;
@@ -264,7 +281,21 @@ int run_fast(bool bwd, FastParams p, const Dims &d, int dtype, const bm2f_msda_t
 
     bool found = false;
     cudaError_t e = cudaSuccess;
-    if (dtype == BM2F_DTYPE_F32) {
+    if (fused) {
+        found = true;
+#define BM2F_FUSED(T, L_) (c.tma ? launch_fused<T, L_, true>(bwd, p, ml, mw, grid, st) : launch_fused<T, L_, false>(bwd, p, ml, mw, grid, st))
+        if (dtype == BM2F_DTYPE_F32) {
+            switch (d.L) {
+            case 1: e = BM2F_FUSED(float, 1); break;
+            case 2: e = BM2F_FUSED(float, 2); break;
+            case 3: e = BM2F_FUSED(float, 3); break;
+            case 4: e = BM2F_FUSED(float, 4); break;
+            }
+        } else {
+            e = BM2F_FUSED(__nv_bfloat16, 3);
+        }
+#undef BM2F_FUSED
+    } else if (dtype == BM2F_DTYPE_F32) {
         switch (d.L) {
         case 1: e = dispatch_default<float, 1>(c, bwd, p, ml, mw, grid, st, &found); break;
         case 2: e = dispatch_default<float, 2>(c, bwd, p, ml, mw, grid, st, &found); break;
@@ -404,6 +435,143 @@ int bm2f_msda_backward(const void *value, const int64_t *spatial_shapes, const i
     g.grad_attn = grad_attn_weight;
     g.N = d.N; g.S = d.S; g.M = d.M; g.D = d.D; g.L = d.L; g.Lq = d.Lq; g.P = d.P;
     return run_generic(true, g, dtype, st);
+}
+
+
+int bm2f_msda_fused_supported(int num_heads, int channels, int num_levels, int num_point, int dtype)
+{
+    if (channels != 32 || num_point != 4 || num_heads != kHeads) return 0;
+    if (dtype == BM2F_DTYPE_F32) return num_levels >= 1 && num_levels <= 4;
+    if (dtype == BM2F_DTYPE_BF16) return num_levels == 3;
+    return 0;
+}
+
+int bm2f_msda_fused_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                            const void *reference_points, const void *sampling_offsets, const void *attn_logits,
+                            void *output, int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                            int num_query, int num_point, int dtype, const bm2f_msda_tuning_t *tuning, void *stream)
+{
+    const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+    int rc = check_common(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, d, dtype);
+    if (rc) return rc;
+    if (!output || !reference_points) return fail(BM2F_ERR_INVALID, "null output / reference_points pointer");
+    const bm2f_msda_tuning_t t = resolve_tuning(tuning);
+    if (!bm2f_msda_fused_supported(num_heads, channels, num_levels, num_point, dtype) ||
+        !fast_eligible(d, dtype, t, value, output, sampling_offsets, attn_logits) || !aligned16(reference_points) ||
+        (reinterpret_cast<uintptr_t>(reference_points) & 7u))
+        return fail(BM2F_ERR_UNSUPPORTED,
+                    "fused path covers D=32, M=8, P=4, L<=4 (f32) / L=3 (bf16), 16-byte aligned tensors "
+                    "(got M=%d D=%d L=%d P=%d dtype=%d); use bm2f_msda_forward",
+                    num_heads, channels, num_levels, num_point, dtype);
+    FastParams p{};
+    p.value = value; p.shapes = spatial_shapes; p.start = level_start_index;
+    p.loc = static_cast<const float *>(sampling_offsets); p.attn = static_cast<const float *>(attn_logits);
+    p.ref = static_cast<const float *>(reference_points);
+    p.out = output;
+    p.N = d.N; p.S = d.S; p.M = d.M; p.Lq = d.Lq;
+    return run_fast(false, p, d, dtype, t, static_cast<cudaStream_t>(stream), true);
+}
+
+int bm2f_msda_fused_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                             const void *reference_points, const void *sampling_offsets, const void *attn_logits,
+                             const void *grad_output, void *grad_value, void *grad_sampling_offsets,
+                             void *grad_attn_logits, int batch, int spatial_size, int num_heads, int channels,
+                             int num_levels, int num_query, int num_point, int dtype,
+                             const bm2f_msda_tuning_t *tuning, void *stream)
+{
+    const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+    int rc = check_common(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, d, dtype);
+    if (rc) return rc;
+    if (!grad_output || !grad_value || !grad_sampling_offsets || !grad_attn_logits || !reference_points)
+        return fail(BM2F_ERR_INVALID, "null gradient / reference_points pointer");
+    const bm2f_msda_tuning_t t = resolve_tuning(tuning);
+    if (!bm2f_msda_fused_supported(num_heads, channels, num_levels, num_point, dtype) ||
+        !fast_eligible(d, dtype, t, value, grad_value, sampling_offsets, attn_logits) || !aligned16(grad_output) ||
+        !aligned16(grad_sampling_offsets) || !aligned16(grad_attn_logits) ||
+        (reinterpret_cast<uintptr_t>(reference_points) & 7u))
+        return fail(BM2F_ERR_UNSUPPORTED, "fused path: unsupported shape or alignment; use bm2f_msda_backward");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t gv_bytes = static_cast<size_t>(d.N) * d.S * d.M * d.D * 4;
+    cudaError_t e = cudaMemsetAsync(grad_value, 0, gv_bytes, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(grad_value)");
+    FastParams p{};
+    p.value = value; p.shapes = spatial_shapes; p.start = level_start_index;
+    p.loc = static_cast<const float *>(sampling_offsets); p.attn = static_cast<const float *>(attn_logits);
+    p.ref = static_cast<const float *>(reference_points);
+    p.grad_out = grad_output; p.grad_value = grad_value;
+    p.grad_loc = static_cast<float *>(grad_sampling_offsets); p.grad_attn = static_cast<float *>(grad_attn_logits);
+    p.N = d.N; p.S = d.S; p.M = d.M; p.Lq = d.Lq;
+    return run_fast(true, p, d, dtype, t, st, true);
+}
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 projection GEMM (linear_tf32x3.cuh)
+// ---------------------------------------------------------------------------------------------
+}  // extern "C"
+namespace {
+template <int NT, int NH>
+int launch_linear(const LinearParams &p, const float *w_hi, const float *w_lo, cudaStream_t st)
+{
+    constexpr int N = NT * NH;
+    CUtensorMap mh, ml;
+    int rc;
+    if ((rc = make_map(&mh, w_hi, N, kGemmK, NT, kGemmBlockK, true))) return rc;
+    if ((rc = make_map(&ml, w_lo, N, kGemmK, NT, kGemmBlockK, true))) return rc;
+    constexpr int smem = linear_smem_bytes<NT, NH>();
+    static bool attr_set = false;   // idempotent; a race only repeats the same call
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(linear_tf32x3_kernel<NT, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(linear smem)");
+        attr_set = true;
+    }
+    const int grid = (p.M + kGemmBlockM - 1) / kGemmBlockM;
+    linear_tf32x3_kernel<NT, NH><<<grid, kGemmThreads, smem, st>>>(p, mh, ml);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "launch linear_tf32x3_kernel");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return BM2F_OK;
+}
+}  // namespace
+extern "C" {
+
+size_t bm2f_linear_workspace_bytes(int out_features, int in_features)
+{
+    return static_cast<size_t>(2) * out_features * in_features * sizeof(float);
+}
+
+int bm2f_linear_forward(const void *x, const void *weight, const void *bias, void *y, void *workspace, int rows,
+                        int out_features, int in_features, int split, void *stream)
+{
+    if (!x || !weight || !y || !workspace) return fail(BM2F_ERR_INVALID, "null pointer");
+    if (rows <= 0) return fail(BM2F_ERR_INVALID, "rows must be positive");
+    if (in_features != kGemmK)
+        return fail(BM2F_ERR_UNSUPPORTED, "tcgen05 projection GEMM is built for in_features = %d (got %d)", kGemmK,
+                    in_features);
+    if (split != 1 && split != 3) return fail(BM2F_ERR_INVALID, "split must be 3 (tf32x3) or 1 (single TF32 pass)");
+    if (!aligned16(x) || !aligned16(y) || !aligned16(weight) || !aligned16(workspace) || (bias && !aligned16(bias)))
+        return fail(BM2F_ERR_UNSUPPORTED, "linear: tensors must be 16-byte aligned");
+    int sms = 0, cc = 0;
+    int rc = device_info(&sms, &cc);
+    if (rc) return rc;
+    if (cc < 10) return fail(BM2F_ERR_CUDA, "this library contains sm_100a code only; device has cc %d.x", cc);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float *w_hi = static_cast<float *>(workspace);
+    float *w_lo = w_hi + static_cast<size_t>(out_features) * in_features;
+    const int n = out_features * in_features;
+    split_tf32_kernel<<<(n + 255) / 256, 256, 0, st>>>(static_cast<const float *>(weight), w_hi, w_lo, n);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "launch split_tf32_kernel");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    LinearParams p{static_cast<const float *>(x), static_cast<const float *>(bias), static_cast<float *>(y), rows,
+                   out_features, split};
+    switch (out_features) {
+    case 256: return launch_linear<256, 1>(p, w_hi, w_lo, st);
+    case 288: return launch_linear<144, 2>(p, w_hi, w_lo, st);
+    case 192: return launch_linear<192, 1>(p, w_hi, w_lo, st);
+    case 96: return launch_linear<96, 1>(p, w_hi, w_lo, st);
+    default:
+        return fail(BM2F_ERR_UNSUPPORTED, "linear: out_features %d not instantiated (256, 288, 192, 96)", out_features);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -27,8 +27,9 @@ struct FastParams {
     const void *value;           // (N,S,M,32)
     const int64_t *shapes;       // (L,2) device
     const int64_t *start;        // (L)   device
-    const float *loc;            // (N,Lq,M,L,P,2)
-    const float *attn;           // (N,Lq,M,L,P)
+    const float *loc;            // (N,Lq,M,L,P,2)        fused mode: raw sampling offsets in pixels
+    const float *attn;           // (N,Lq,M,L,P)          fused mode: raw logits
+    const float *ref;            // (N,Lq,L,2) reference points, fused mode only (loc = ref + offset / (W,H))
     const void *grad_out;        // (N,Lq,M,32)            bwd only
     void *out;                   // (N,Lq,M,32)            fwd only
     void *grad_value;            // (N,S,M,32) float32      bwd only
@@ -174,10 +175,43 @@ struct Ring {
     }
 };
 
+
+// Fused prologue of MSDeformAttn.forward (reference: ops/modules/ms_deform_attn.py:101-109), done in
+// registers per (query, head): attention weights = softmax over the L*P logits, sampling locations =
+// reference point + offset / (W_l, H_l).  Each lane holds NIT points (one per level iteration); the LG
+// lane groups hold the other points, so max / sum are folded across groups with xor-shuffles.
+template <int NIT, int LPC, int LG, int L_, int P_>
+__device__ __forceinline__ void fused_prologue(float (&xs)[NIT], float (&ys)[NIT], float (&ws)[NIT],
+                                               const float2 *ref_q, const float (&rW)[L_], const float (&rH)[L_])
+{
+    float mx = ws[0];
+#pragma unroll
+    for (int it = 1; it < NIT; ++it) mx = fmaxf(mx, ws[it]);
+#pragma unroll
+    for (int o = LPC; o < 32; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        ws[it] = __expf(ws[it] - mx);
+        sum += ws[it];
+    }
+#pragma unroll
+    for (int o = LPC; o < 32; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int l = (it * LG) / P_;
+        const float2 r = __ldg(ref_q + l);
+        ws[it] *= inv;
+        xs[it] = fmaf(xs[it], rW[l], r.x);
+        ys[it] = fmaf(ys[it], rH[l], r.y);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Forward
 // ------------------------------------------------------------------------------------------
-template <typename T, int VEC, int L_, int P_, int SW, int NWARP, int G, bool TMA, int CPS>
+template <typename T, int VEC, int L_, int P_, int SW, int NWARP, int G, bool TMA, int CPS, bool FUSED = false>
 __global__ void __launch_bounds__((NWARP + (TMA ? 1 : 0)) * 32, CPS)
 msda_fwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_loc,
                      const __grid_constant__ CUtensorMap tm_w)
@@ -214,6 +248,10 @@ msda_fwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_
         H[l] = tabs.H[l]; W[l] = tabs.W[l]; st[l] = tabs.start[l];
         Hf[l] = static_cast<float>(H[l]); Wf[l] = static_cast<float>(W[l]);
     }
+    float rW[L_], rH[L_];
+#pragma unroll
+    for (int l = 0; l < L_; ++l) { rW[l] = 1.f / Wf[l]; rH[l] = 1.f / Hf[l]; }
+    (void)rW; (void)rH;
     const int g = warp / WPG, wi = warp % WPG;
     const int lg = lane / LPC, sub = lane % LPC;
     constexpr int MD = kHeads * D;  // elements between horizontally adjacent pixels (immediate offset)
@@ -244,6 +282,9 @@ msda_fwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_
                     xs[it] = t.x; ys[it] = t.y; ws[it] = __ldg(p.attn + k0 + it * LG + lg);
                 }
             }
+            if constexpr (FUSED)
+                fused_prologue<NIT, LPC, LG, L_, P_>(
+                    xs, ys, ws, reinterpret_cast<const float2 *>(p.ref) + (static_cast<size_t>(b) * p.Lq + q) * L_, rW, rH);
             float acc[VEC];
 #pragma unroll
             for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
@@ -394,7 +435,8 @@ msda_fwd_fast256_kernel(const FastParams p, const __grid_constant__ CUtensorMap 
 // ------------------------------------------------------------------------------------------
 // Backward
 // ------------------------------------------------------------------------------------------
-template <typename T, int VEC, int L_, int P_, int SW, int NWARP, int G, bool TMA, int CPS, bool MERGE>
+template <typename T, int VEC, int L_, int P_, int SW, int NWARP, int G, bool TMA, int CPS, bool MERGE,
+          bool FUSED = false>
 __global__ void __launch_bounds__((NWARP + (TMA ? 1 : 0)) * 32, CPS)
 msda_bwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_loc,
                      const __grid_constant__ CUtensorMap tm_w)
@@ -430,6 +472,10 @@ msda_bwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_
         H[l] = tabs.H[l]; W[l] = tabs.W[l]; st[l] = tabs.start[l];
         Hf[l] = static_cast<float>(H[l]); Wf[l] = static_cast<float>(W[l]);
     }
+    float rW[L_], rH[L_];
+#pragma unroll
+    for (int l = 0; l < L_; ++l) { rW[l] = 1.f / Wf[l]; rH[l] = 1.f / Hf[l]; }
+    (void)rW; (void)rH;
     const int g = warp / WPG, wi = warp % WPG;
     const int lg = lane / LPC, sub = lane % LPC;
     constexpr int MD = kHeads * D;  // elements between horizontally adjacent pixels (immediate offset)
@@ -465,6 +511,11 @@ msda_bwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_
                     xs[it] = t.x; ys[it] = t.y; ws[it] = __ldg(p.attn + qm * LP + it * LG + lg);
                 }
             }
+            if constexpr (FUSED)
+                fused_prologue<NIT, LPC, LG, L_, P_>(
+                    xs, ys, ws, reinterpret_cast<const float2 *>(p.ref) + (static_cast<size_t>(b) * p.Lq + q) * L_, rW, rH);
+            float ga_keep[NIT], gx_keep[NIT], gy_keep[NIT];   // fused mode: written after the softmax backward
+            (void)ga_keep; (void)gx_keep; (void)gy_keep;
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
                 const int l = (it * LG) / P_;
@@ -546,12 +597,33 @@ msda_bwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_
                     px += __shfl_xor_sync(0xffffffffu, px, o);
                     py += __shfl_xor_sync(0xffffffffu, py, o);
                 }
-                if (sub == 0) {
+                if constexpr (FUSED) {
+                    // d loc / d offset = 1 / (W, H): the W, H factors of grad_loc cancel
+                    ga_keep[it] = f.in_range ? pa : 0.f;
+                    gx_keep[it] = f.in_range ? ws[it] * px : 0.f;
+                    gy_keep[it] = f.in_range ? ws[it] * py : 0.f;
+                } else if (sub == 0) {
                     // skipped points leave zeros (reference outputs are zero-initialised)
                     const size_t k = qm * LP + it * LG + lg;
                     p.grad_attn[k] = f.in_range ? pa : 0.f;
                     reinterpret_cast<float2 *>(p.grad_loc)[k] =
                         f.in_range ? make_float2(Wf[l] * ws[it] * px, Hf[l] * ws[it] * py) : make_float2(0.f, 0.f);
+                }
+            }
+            if constexpr (FUSED) {
+                // softmax backward: grad_logit_i = a_i * (ga_i - sum_j a_j ga_j)
+                float dot = 0.f;
+#pragma unroll
+                for (int it = 0; it < NIT; ++it) dot = fmaf(ws[it], ga_keep[it], dot);
+#pragma unroll
+                for (int o = LPC; o < 32; o <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+                if (sub == 0) {
+#pragma unroll
+                    for (int it = 0; it < NIT; ++it) {
+                        const size_t k = qm * LP + it * LG + lg;
+                        p.grad_attn[k] = ws[it] * (ga_keep[it] - dot);
+                        reinterpret_cast<float2 *>(p.grad_loc)[k] = make_float2(gx_keep[it], gy_keep[it]);
+                    }
                 }
             }
         }

@@ -139,6 +139,134 @@ std::vector<at::Tensor> ms_deform_attn_backward(const at::Tensor &value, const a
     return {grad_value, grad_loc, grad_attn};
 }
 
+
+// ---- fused prologue variants (not part of the reference surface; used by bm2f_b200.ops.modules) ----
+struct FusedChecked {
+    int N, S, M, D, L, Lq, P, dtype;
+};
+
+FusedChecked check_fused(const at::Tensor &value, const at::Tensor &spatial_shapes, const at::Tensor &level_start_index,
+                         const at::Tensor &reference_points, const at::Tensor &sampling_offsets,
+                         const at::Tensor &attn_logits)
+{
+    TORCH_CHECK(value.is_cuda(), "Not implemented on the CPU");
+    for (const at::Tensor *t : {&value, &spatial_shapes, &level_start_index, &reference_points, &sampling_offsets,
+                                &attn_logits}) {
+        TORCH_CHECK(t->is_cuda(), "all tensors must be CUDA tensors");
+        TORCH_CHECK(t->is_contiguous(), "all tensors have to be contiguous");
+    }
+    TORCH_CHECK(spatial_shapes.scalar_type() == at::kLong && level_start_index.scalar_type() == at::kLong,
+                "spatial_shapes / level_start_index must be int64");
+    TORCH_CHECK(value.dim() == 4 && sampling_offsets.dim() == 6 && sampling_offsets.size(5) == 2,
+                "value must be (N,S,M,D), sampling_offsets (N,Lq,M,L,P,2)");
+    TORCH_CHECK(reference_points.dim() == 4 && reference_points.size(3) == 2,
+                "fused path takes 2-d reference points (N,Lq,L,2)");
+    TORCH_CHECK(reference_points.scalar_type() == at::kFloat && sampling_offsets.scalar_type() == at::kFloat &&
+                    attn_logits.scalar_type() == at::kFloat,
+                "reference_points / sampling_offsets / attn_logits must be float32");
+    FusedChecked c;
+    c.N = static_cast<int>(value.size(0)); c.S = static_cast<int>(value.size(1));
+    c.M = static_cast<int>(value.size(2)); c.D = static_cast<int>(value.size(3));
+    c.L = static_cast<int>(spatial_shapes.size(0)); c.Lq = static_cast<int>(sampling_offsets.size(1));
+    c.P = static_cast<int>(sampling_offsets.size(4));
+    TORCH_CHECK(sampling_offsets.size(0) == c.N && sampling_offsets.size(2) == c.M && sampling_offsets.size(3) == c.L,
+                "sampling_offsets shape does not match value / spatial_shapes");
+    TORCH_CHECK(attn_logits.numel() == static_cast<int64_t>(c.N) * c.Lq * c.M * c.L * c.P,
+                "attn_logits must be (N,Lq,M,L*P)");
+    TORCH_CHECK(reference_points.size(0) == c.N && reference_points.size(1) == c.Lq && reference_points.size(2) == c.L,
+                "reference_points must be (N,Lq,L,2)");
+    c.dtype = dtype_code(value);
+    return c;
+}
+
+bool ms_deform_attn_fused_supported(int64_t num_heads, int64_t channels, int64_t num_levels, int64_t num_point,
+                                    bool bf16)
+{
+    return bm2f_msda_fused_supported(static_cast<int>(num_heads), static_cast<int>(channels),
+                                     static_cast<int>(num_levels), static_cast<int>(num_point),
+                                     bf16 ? BM2F_DTYPE_BF16 : BM2F_DTYPE_F32) != 0;
+}
+
+at::Tensor ms_deform_attn_fused_forward(const at::Tensor &value, const at::Tensor &spatial_shapes,
+                                        const at::Tensor &level_start_index, const at::Tensor &reference_points,
+                                        const at::Tensor &sampling_offsets, const at::Tensor &attn_logits)
+{
+    const FusedChecked c = check_fused(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
+                                       attn_logits);
+    const c10::cuda::CUDAGuard guard(value.device());
+    auto output = at::empty({c.N, c.Lq, c.M * c.D}, value.options());
+    const int rc = bm2f_msda_fused_forward(value.data_ptr(), spatial_shapes.data_ptr<int64_t>(),
+                                           level_start_index.data_ptr<int64_t>(), reference_points.data_ptr(),
+                                           sampling_offsets.data_ptr(), attn_logits.data_ptr(), output.data_ptr(),
+                                           c.N, c.S, c.M, c.D, c.L, c.Lq, c.P, c.dtype, nullptr,
+                                           at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == BM2F_OK, "ms_deform_attn_fused_forward: ", bm2f_msda_last_error());
+    return output;
+}
+
+std::vector<at::Tensor> ms_deform_attn_fused_backward(const at::Tensor &value, const at::Tensor &spatial_shapes,
+                                                      const at::Tensor &level_start_index,
+                                                      const at::Tensor &reference_points,
+                                                      const at::Tensor &sampling_offsets,
+                                                      const at::Tensor &attn_logits, const at::Tensor &grad_output)
+{
+    const FusedChecked c = check_fused(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
+                                       attn_logits);
+    TORCH_CHECK(grad_output.is_cuda() && grad_output.is_contiguous(), "grad_output must be a contiguous CUDA tensor");
+    TORCH_CHECK(grad_output.scalar_type() == value.scalar_type(), "grad_output must have the dtype of value");
+    const c10::cuda::CUDAGuard guard(value.device());
+    auto grad_value = at::empty(value.sizes(), value.options().dtype(at::kFloat));
+    auto grad_off = at::empty_like(sampling_offsets);
+    auto grad_logits = at::empty_like(attn_logits);
+    const int rc = bm2f_msda_fused_backward(value.data_ptr(), spatial_shapes.data_ptr<int64_t>(),
+                                            level_start_index.data_ptr<int64_t>(), reference_points.data_ptr(),
+                                            sampling_offsets.data_ptr(), attn_logits.data_ptr(), grad_output.data_ptr(),
+                                            grad_value.data_ptr(), grad_off.data_ptr(), grad_logits.data_ptr(), c.N,
+                                            c.S, c.M, c.D, c.L, c.Lq, c.P, c.dtype, nullptr,
+                                            at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == BM2F_OK, "ms_deform_attn_fused_backward: ", bm2f_msda_last_error());
+    if (grad_value.scalar_type() != value.scalar_type()) grad_value = grad_value.to(value.scalar_type());
+    return {grad_value, grad_off, grad_logits};
+}
+
+
+// ---- tcgen05 projection GEMM (forward of nn.Linear, fp32) -------------------------------------------------
+bool linear_tf32x3_supported(int64_t in_features, int64_t out_features)
+{
+    return in_features == 256 && (out_features == 256 || out_features == 288 || out_features == 192 || out_features == 96);
+}
+
+at::Tensor linear_tf32x3(const at::Tensor &x, const at::Tensor &weight, const c10::optional<at::Tensor> &bias,
+                         int64_t split)
+{
+    TORCH_CHECK(x.is_cuda() && weight.is_cuda(), "linear_tf32x3: CUDA tensors only (no CPU path)");
+    TORCH_CHECK(x.scalar_type() == at::kFloat && weight.scalar_type() == at::kFloat, "linear_tf32x3: float32 only");
+    TORCH_CHECK(weight.dim() == 2 && x.size(-1) == weight.size(1), "linear_tf32x3: shape mismatch");
+    TORCH_CHECK(linear_tf32x3_supported(weight.size(1), weight.size(0)), "linear_tf32x3: unsupported layer shape ",
+                weight.size(1), " -> ", weight.size(0));
+    const c10::cuda::CUDAGuard guard(x.device());
+    auto xc = x.contiguous();
+    auto wc = weight.contiguous();
+    const int64_t rows = xc.numel() / xc.size(-1);
+    auto sizes = xc.sizes().vec();
+    sizes.back() = wc.size(0);
+    auto y = at::empty(sizes, xc.options());
+    auto ws = at::empty({static_cast<int64_t>(bm2f_linear_workspace_bytes(wc.size(0), wc.size(1)) / 4)}, xc.options());
+    const void *b = nullptr;
+    at::Tensor bc;
+    if (bias.has_value() && bias->defined()) {
+        bc = bias->contiguous();
+        TORCH_CHECK(bc.is_cuda() && bc.scalar_type() == at::kFloat && bc.numel() == wc.size(0), "linear_tf32x3: bad bias");
+        b = bc.data_ptr();
+    }
+    const int rc = bm2f_linear_forward(xc.data_ptr(), wc.data_ptr(), b, y.data_ptr(), ws.data_ptr(),
+                                       static_cast<int>(rows), static_cast<int>(wc.size(0)),
+                                       static_cast<int>(wc.size(1)), static_cast<int>(split),
+                                       at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == BM2F_OK, "linear_tf32x3: ", bm2f_msda_last_error());
+    return y;
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
@@ -146,6 +274,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.doc() = "B200-native multi-scale deformable attention (drop-in for the Deformable-DETR op)";
     m.def("ms_deform_attn_forward", &ms_deform_attn_forward, "ms_deform_attn_forward");
     m.def("ms_deform_attn_backward", &ms_deform_attn_backward, "ms_deform_attn_backward");
+    m.def("ms_deform_attn_fused_supported", &ms_deform_attn_fused_supported);
+    m.def("ms_deform_attn_fused_forward", &ms_deform_attn_fused_forward, "fused softmax + location prologue + sampling");
+    m.def("ms_deform_attn_fused_backward", &ms_deform_attn_fused_backward, "backward of the fused op");
+    m.def("linear_tf32x3", &linear_tf32x3, "tcgen05 projection GEMM (y = x W^T + b), split=3: tf32x3, 1: tf32");
+    m.def("linear_tf32x3_supported", &linear_tf32x3_supported);
     m.def("abi_version", []() { return bm2f_msda_abi_version(); });
     m.def("build_info", []() { return std::string(bm2f_msda_build_info()); });
     m.def("launch_count", []() { return bm2f_msda_launch_count(); });

@@ -39,3 +39,29 @@ class MSDeformAttnFunction(Function):
         grad_value, grad_loc, grad_attn = MSDA.ms_deform_attn_backward(
             value, shapes, start, loc, attn, grad_output.contiguous(), ctx.im2col_step)
         return grad_value, None, None, grad_loc, grad_attn, None
+
+
+class MSDeformAttnFusedFunction(Function):
+    """Fused variant used by bm2f_b200.ops.modules.MSDeformAttn (not part of the reference surface):
+    `apply(value, value_spatial_shapes, value_level_start_index, reference_points, sampling_offsets,
+    attention_logits)` where sampling_offsets / attention_logits are the raw outputs of the two Linear
+    layers.  The softmax over the L*P points and `ref + offset / (W_l, H_l)`
+    (ops/modules/ms_deform_attn.py:101-109) run inside the sampling kernels; backward returns the
+    gradients of the raw Linear outputs.  reference_points (2-d form) receive no gradient."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, reference_points, sampling_offsets,
+                attention_logits):
+        output = MSDA.ms_deform_attn_fused_forward(value, value_spatial_shapes, value_level_start_index,
+                                                   reference_points, sampling_offsets, attention_logits)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, reference_points,
+                              sampling_offsets, attention_logits)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, start, ref, off, logits = ctx.saved_tensors
+        grad_value, grad_off, grad_logits = MSDA.ms_deform_attn_fused_backward(
+            value, shapes, start, ref, off, logits, grad_output.contiguous())
+        return grad_value, None, None, None, grad_off, grad_logits

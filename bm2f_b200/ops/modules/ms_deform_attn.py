@@ -22,7 +22,9 @@ import torch.nn.functional as F
 from torch import nn
 from torch.nn.init import constant_, xavier_uniform_
 
-from ..functions import MSDeformAttnFunction
+from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction
+from ..functions.ms_deform_attn_func import MSDA
+from ..functions import linear_func
 
 
 def _is_power_of_2(n):
@@ -42,6 +44,11 @@ class MSDeformAttn(nn.Module):
                           "sm_100a fast path, other sizes use the generic kernel." % head_dim)
 
         self.im2col_step = 128
+        # softmax + sampling-location arithmetic inside the sampling kernels (fp32 / bf16 values, 2-d
+        # reference points, head_dim 32, 8 heads, 4 points, <= 4 levels); set False for the unfused op
+        self.fuse_prologue = True
+        # forward GEMMs of the four projections on tcgen05 (tf32x3, fp32-grade); False = torch / cuBLAS
+        self.tcgen05_linear = True
 
         self.d_model = d_model
         self.n_levels = n_levels
@@ -73,6 +80,11 @@ class MSDeformAttn(nn.Module):
         xavier_uniform_(self.output_proj.weight.data)
         constant_(self.output_proj.bias.data, 0.)
 
+    def _proj(self, layer, x):
+        if self.tcgen05_linear and linear_func.supported(layer, x):
+            return linear_func.linear_tf32x3(x, layer.weight, layer.bias)
+        return layer(x)
+
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
                 input_padding_mask=None):
         """
@@ -90,14 +102,22 @@ class MSDeformAttn(nn.Module):
             raise RuntimeError("MSDeformAttn: Not implemented on the CPU (this build has no CPU fallback)")
         # no device->host sync here: the level table is validated on the device side of the op
 
-        value = self.value_proj(input_flatten)
+        value = self._proj(self.value_proj, input_flatten)
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], float(0))
         value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
-        sampling_offsets = self.sampling_offsets(query).view(
+        sampling_offsets = self._proj(self.sampling_offsets, query).view(
             N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
-        attention_weights = self.attention_weights(query).view(
+        attention_weights = self._proj(self.attention_weights, query).view(
             N, Len_q, self.n_heads, self.n_levels * self.n_points)
+        if (self.fuse_prologue and reference_points.shape[-1] == 2 and reference_points.dtype == torch.float32
+                and sampling_offsets.dtype == torch.float32 and value.dtype in (torch.float32, torch.bfloat16)
+                and MSDA.ms_deform_attn_fused_supported(self.n_heads, self.d_model // self.n_heads, self.n_levels,
+                                                        self.n_points, value.dtype == torch.bfloat16)):
+            output = MSDeformAttnFusedFunction.apply(
+                value, input_spatial_shapes, input_level_start_index, reference_points.contiguous(),
+                sampling_offsets, attention_weights)
+            return self._proj(self.output_proj, output)
         attention_weights = F.softmax(attention_weights, -1).view(
             N, Len_q, self.n_heads, self.n_levels, self.n_points)
         if reference_points.shape[-1] == 2:
@@ -113,4 +133,4 @@ class MSDeformAttn(nn.Module):
         output = MSDeformAttnFunction.apply(
             value, input_spatial_shapes, input_level_start_index, sampling_locations.contiguous(),
             attention_weights, self.im2col_step)
-        return self.output_proj(output)
+        return self._proj(self.output_proj, output)

@@ -46,6 +46,7 @@
 #ifndef BM2F_MSDA_H_
 #define BM2F_MSDA_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -127,6 +128,50 @@ int bm2f_msda_backward(const void *value, const int64_t *spatial_shapes,
                        int batch, int spatial_size, int num_heads, int channels,
                        int num_levels, int num_query, int num_point,
                        int dtype, const bm2f_msda_tuning_t *tuning, void *stream);
+
+/*
+ * Fused variants: the sampling kernels also do the element-wise prologue of MSDeformAttn.forward
+ * (ops/modules/ms_deform_attn.py:101-109) in registers —
+ *     attention_weights = softmax(attn_logits over the L*P points of a (query, head))
+ *     sampling_loc      = reference_points[:, :, None, :, None, :] + sampling_offsets / (W_l, H_l)
+ * so the normalised weights and the locations are never materialised, and the backward returns the
+ * gradients of the raw Linear outputs (softmax backward and the 1/(W,H) scaling included).
+ *   reference_points (N, Lq, L, 2) float32, (x, y) in [0,1]   — the 2-d branch of the module; they get no
+ *   gradient (Mask2Former builds them from the level shapes, msdeformattn.py:141-153).
+ *   sampling_offsets (N, Lq, M, L, P, 2) float32 in pixels;  attn_logits (N, Lq, M, L, P) float32.
+ * Shapes outside D=32, M=8, P=4, L<=4 (f32) / L=3 (bf16) return BM2F_ERR_UNSUPPORTED: compose the
+ * prologue yourself and call bm2f_msda_forward/backward.  bm2f_msda_fused_supported() tells in advance.
+ */
+int bm2f_msda_fused_supported(int num_heads, int channels, int num_levels, int num_point, int dtype);
+
+int bm2f_msda_fused_forward(const void *value, const int64_t *spatial_shapes,
+                            const int64_t *level_start_index, const void *reference_points,
+                            const void *sampling_offsets, const void *attn_logits, void *output,
+                            int batch, int spatial_size, int num_heads, int channels,
+                            int num_levels, int num_query, int num_point,
+                            int dtype, const bm2f_msda_tuning_t *tuning, void *stream);
+
+int bm2f_msda_fused_backward(const void *value, const int64_t *spatial_shapes,
+                             const int64_t *level_start_index, const void *reference_points,
+                             const void *sampling_offsets, const void *attn_logits,
+                             const void *grad_output, void *grad_value,
+                             void *grad_sampling_offsets, void *grad_attn_logits,
+                             int batch, int spatial_size, int num_heads, int channels,
+                             int num_levels, int num_query, int num_point,
+                             int dtype, const bm2f_msda_tuning_t *tuning, void *stream);
+
+/*
+ * Projection GEMM on the 5th-generation tensor cores (tcgen05 + TMEM), for the four nn.Linear layers of
+ * MSDeformAttn (ops/modules/ms_deform_attn.py:59-62; applied at :98, :101, :102, :124):
+ *     y[rows, out_features] = x[rows, in_features] * weight[out_features, in_features]^T + bias
+ * float32 in / out, in_features = 256 (d_model), out_features in {256, 288, 192, 96}.
+ * split = 3: three-term TF32 split with fp32 accumulation (fp32-grade result, what the fp32 reference
+ * module needs); split = 1: single TF32 pass.  `workspace` = bm2f_linear_workspace_bytes() of device
+ * memory for the hi/lo halves of the weight (rewritten on every call).  bias may be NULL.
+ */
+size_t bm2f_linear_workspace_bytes(int out_features, int in_features);
+int bm2f_linear_forward(const void *x, const void *weight, const void *bias, void *y, void *workspace,
+                        int rows, int out_features, int in_features, int split, void *stream);
 
 /*
  * Host-buffer convenience used for end-to-end measurement and by non-torch callers:

@@ -152,3 +152,39 @@ def torch_port_forward_backward(value, shapes, loc, attn, grad_out):
     out = torch_port_forward(value, shapes, loc, attn)
     out.backward(grad_out.reshape(out.shape))
     return out.detach(), value.grad, loc.grad, attn.grad
+
+
+# --------------------------------------------------------------------------------------
+# Fused op (softmax + location arithmetic + sampling): float64 numpy on top of the C oracle.
+# Restates ops/modules/ms_deform_attn.py:101-109 and their derivatives.
+# --------------------------------------------------------------------------------------
+def _fused_prologue(shapes, ref, offsets, logits):
+    shapes = np.asarray(shapes, dtype=np.int64)
+    ref = np.asarray(ref, dtype=np.float64)
+    offsets = np.asarray(offsets, dtype=np.float64)
+    logits = np.asarray(logits, dtype=np.float64)
+    N, Lq, M, L, P, _ = offsets.shape
+    z = logits.reshape(N, Lq, M, L * P)
+    z = z - z.max(-1, keepdims=True)
+    e = np.exp(z)
+    attn = (e / e.sum(-1, keepdims=True)).reshape(N, Lq, M, L, P)
+    norm = np.stack((shapes[:, 1], shapes[:, 0]), -1).astype(np.float64)          # (L,2) = (W,H)
+    loc = ref[:, :, None, :, None, :] + offsets / norm[None, None, None, :, None, :]
+    return loc, attn, norm
+
+
+def fused_forward(value, shapes, start, ref, offsets, logits):
+    loc, attn, _ = _fused_prologue(shapes, ref, offsets, logits)
+    return forward(value, shapes, start, loc, attn)
+
+
+def fused_backward(value, shapes, start, ref, offsets, logits, grad_out):
+    """Returns (grad_value, grad_offsets, grad_logits)."""
+    loc, attn, norm = _fused_prologue(shapes, ref, offsets, logits)
+    gv, gl, ga = backward(value, shapes, start, loc, attn, grad_out)
+    g_off = gl / norm[None, None, None, :, None, :]
+    N, Lq, M, L, P = attn.shape
+    a = attn.reshape(N, Lq, M, L * P)
+    g = ga.reshape(N, Lq, M, L * P)
+    g_logits = (a * (g - (a * g).sum(-1, keepdims=True))).reshape(N, Lq, M, L, P)
+    return gv, g_off, g_logits

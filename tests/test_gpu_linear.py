@@ -1,0 +1,59 @@
+"""GPU: tcgen05 projection GEMM (csrc/linear_tf32x3.cuh) against a float64 matmul."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def msda(built):
+    import bm2f_b200
+    return bm2f_b200.load_extension()
+
+
+@pytest.mark.parametrize("out_features", [256, 288, 192, 96])
+@pytest.mark.parametrize("rows", [128, 5376, 1000, 77])          # full tiles, many tiles, ragged tails
+def test_linear_tf32x3_matches_fp64(msda, out_features, rows):
+    torch.manual_seed(rows + out_features)
+    dev = torch.device("cuda:0")
+    x = torch.randn(rows, 256, device=dev)
+    w = torch.randn(out_features, 256, device=dev) / 16
+    b = torch.randn(out_features, device=dev)
+    ref = (x.double() @ w.double().t() + b.double())
+    y3 = msda.linear_tf32x3(x, w, b, 3)
+    err3 = (y3.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err3 <= 2e-6, err3                                     # fp32-grade (cuBLAS fp32 gives ~1e-6 here)
+    y1 = msda.linear_tf32x3(x, w, b, 1)
+    err1 = (y1.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err1 <= 2e-3, err1                                     # single TF32 pass
+    assert err3 < err1
+    ynb = msda.linear_tf32x3(x, w, None, 3)
+    assert torch.allclose(ynb + b, y3, atol=1e-5, rtol=1e-5)
+
+
+def test_linear_batched_input_and_autograd(msda):
+    from bm2f_b200.ops.functions.linear_func import linear_tf32x3
+    torch.manual_seed(0)
+    dev = torch.device("cuda:0")
+    lin = torch.nn.Linear(256, 288).to(dev)
+    x = torch.randn(2, 300, 256, device=dev, requires_grad=True)
+    y = linear_tf32x3(x, lin.weight, lin.bias)
+    assert y.shape == (2, 300, 288)
+    y.square().sum().backward()
+    x2 = x.detach().clone().requires_grad_(True)
+    lin2 = torch.nn.Linear(256, 288).to(dev)
+    lin2.load_state_dict(lin.state_dict())
+    y2 = lin2(x2)
+    y2.square().sum().backward()
+    assert torch.allclose(y, y2, atol=2e-5, rtol=1e-5)
+    assert torch.allclose(x.grad, x2.grad, atol=1e-3, rtol=1e-4)
+    assert torch.allclose(lin.weight.grad, lin2.weight.grad, atol=1e-2, rtol=1e-4)
+
+
+def test_linear_rejects_unsupported(msda):
+    dev = torch.device("cuda:0")
+    with pytest.raises(RuntimeError, match="unsupported layer shape"):
+        msda.linear_tf32x3(torch.zeros(4, 128, device=dev), torch.zeros(256, 128, device=dev), None, 3)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        msda.linear_tf32x3(torch.zeros(4, 256), torch.zeros(256, 256), None, 3)

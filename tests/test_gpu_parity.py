@@ -301,3 +301,57 @@ def test_host_entry_matches_device_entry(built):
     assert rel_err(gv.numpy(), ref["grad_value"]) <= 1e-5
     assert rel_err(gl.numpy(), ref["grad_loc"]) <= 1e-5
     assert rel_err(ga.numpy(), ref["grad_attn"]) <= 1e-5
+
+
+# ----------------------------------------------------------------------------------------------
+# 6. fused entry points (softmax + location arithmetic inside the kernels)
+# ----------------------------------------------------------------------------------------------
+def _fused_inputs(levels, batch, seed):
+    g = torch.Generator().manual_seed(seed)
+    base = W.make_inputs(levels, batch, seed=seed)
+    L = len(levels)
+    S = base["value"].shape[1]
+    ref = W.reference_points(levels, batch)                                       # (N,S,L,2)
+    offsets = (W.compass_offset_bias(8, L, 4)[None, None] + torch.randn(batch, S, 8, L, 4, 2, generator=g)).contiguous()
+    logits = (torch.randn(batch, S, 8, L, 4, generator=g) * 1.5).contiguous()
+    return base, ref, offsets, logits
+
+
+@pytest.mark.parametrize("levels,batch,staging", [(SMALL_LEVELS, 3, 1), (SMALL_LEVELS, 3, 2),
+                                                   (((5, 7), (9, 13)), 2, 1), (W.WORKLOADS[1].levels, 1, 1)])
+def test_fused_vs_oracle(levels, batch, staging, built):
+    base, ref, offsets, logits = _fused_inputs(levels, batch, 900 + len(levels))
+    dev = _dev()
+    sh, st = base["shapes"].to(dev), base["start"].to(dev)
+    v, r, o, lg, go = (t.to(dev).contiguous() for t in (base["value"], ref, offsets, logits, base["grad_out"]))
+    N, S, M, D = v.shape
+    L = len(levels)
+    dims = (N, S, M, D, L, S, 4)
+    out = torch.full((N, S, M * D), float("nan"), device=dev)
+    gv, goff, glog = torch.full_like(v, float("nan")), torch.full_like(o, float("nan")), torch.full_like(lg, float("nan"))
+    stream = torch.cuda.current_stream().cuda_stream
+    tun = cabi.make_tuning(staging=staging)
+    cabi.fused_forward(v.data_ptr(), sh.data_ptr(), st.data_ptr(), r.data_ptr(), o.data_ptr(), lg.data_ptr(),
+                       out.data_ptr(), dims, cabi.DTYPE_F32, tun, stream)
+    cabi.fused_backward(v.data_ptr(), sh.data_ptr(), st.data_ptr(), r.data_ptr(), o.data_ptr(), lg.data_ptr(),
+                        go.data_ptr(), gv.data_ptr(), goff.data_ptr(), glog.data_ptr(), dims, cabi.DTYPE_F32, tun, stream)
+    torch.cuda.synchronize()
+    a = [t.numpy() for t in (base["value"], base["shapes"], base["start"], ref, offsets, logits)]
+    ref_out = O.fused_forward(*a)
+    rgv, rgo, rgl = O.fused_backward(*a, base["grad_out"].numpy())
+    assert np.abs(out.cpu().numpy() - ref_out).max() <= 2e-5 * max(1.0, np.abs(ref_out).max())
+    loc = ref.numpy()[:, :, None, :, None, :] + offsets.numpy() / np.stack(
+        (base["shapes"].numpy()[:, 1], base["shapes"].numpy()[:, 0]), -1)[None, None, None, :, None, :]
+    ok = smooth_mask(loc, base["shapes"].numpy(), eps=1e-3)
+    assert rel_err(gv.cpu().numpy(), rgv) <= 1e-4
+    assert rel_err(glog.cpu().numpy(), rgl) <= 1e-4
+    assert rel_err(goff.cpu().numpy() * ok, rgo * ok) <= 1e-4
+
+
+def test_fused_rejects_unsupported_shapes(built):
+    assert cabi.lib().bm2f_msda_fused_supported(8, 32, 3, 4, cabi.DTYPE_F32) == 1
+    assert cabi.lib().bm2f_msda_fused_supported(8, 32, 3, 4, cabi.DTYPE_BF16) == 1
+    assert cabi.lib().bm2f_msda_fused_supported(8, 64, 3, 4, cabi.DTYPE_F32) == 0
+    assert cabi.lib().bm2f_msda_fused_supported(4, 32, 3, 4, cabi.DTYPE_F32) == 0
+    assert cabi.lib().bm2f_msda_fused_supported(8, 32, 5, 4, cabi.DTYPE_F32) == 0
+    assert cabi.lib().bm2f_msda_fused_supported(8, 32, 3, 4, cabi.DTYPE_F64) == 0
