@@ -23,7 +23,7 @@
 
 namespace bm2f {
 
-constexpr int kGemmK = 256;         // d_model
+constexpr int kGemmKMax = 288;      // reduction length is a runtime multiple of 32 (256 forward, 96..288 for grad_x)
 constexpr int kGemmBlockM = 128;
 constexpr int kGemmBlockK = 32;     // floats per k-block = 128 bytes = one SWIZZLE_128B row
 constexpr int kGemmStages = 2;
@@ -33,7 +33,7 @@ struct LinearParams {
     const float *x;      // (M, K)
     const float *bias;   // (N) or nullptr
     float *y;            // (M, N)
-    int M, N;
+    int M, N, K;
     int split;           // 3 = tf32x3 (fp32-grade), 1 = single TF32 pass
 };
 
@@ -144,7 +144,7 @@ linear_tf32x3_kernel(const LinearParams p, const __grid_constant__ CUtensorMap t
     constexpr int kXBytes = kGemmBlockM * kGemmBlockK * 4;              // 16 KB
     constexpr int kWBytes = N * kGemmBlockK * 4;                        // N x 128 B
     constexpr int kStageBytes = 2 * kXBytes + 2 * kWBytes;
-    constexpr int kKBlocks = kGemmK / kGemmBlockK;                      // 8
+    const int kKBlocks = p.K / kGemmBlockK;                             // 8 for the forward layers
     constexpr uint32_t kTmemCols = (N <= 32) ? 32 : (N <= 64) ? 64 : (N <= 128) ? 128 : (N <= 256) ? 256 : 512;
     static_assert(NT % 16 == 0 && NT <= 256, "UMMA N for M = 128");
     static_assert((NT * 128) % 1024 == 0, "second tile must start on a swizzle atom");
@@ -237,7 +237,7 @@ linear_tf32x3_kernel(const LinearParams p, const __grid_constant__ CUtensorMap t
             for (int j = 0; j < 8; ++j) {
                 const int r = rsub + 16 * j;
                 const int gr = row0 + r;
-                v[j] = gr < p.M ? __ldg(reinterpret_cast<const float4 *>(p.x + static_cast<size_t>(gr) * kGemmK +
+                v[j] = gr < p.M ? __ldg(reinterpret_cast<const float4 *>(p.x + static_cast<size_t>(gr) * p.K +
                                                                            kb * kGemmBlockK) + c16)
                                 : make_float4(0.f, 0.f, 0.f, 0.f);
             }
@@ -298,11 +298,13 @@ constexpr int linear_smem_bytes()
 }
 
 // W (N, K) -> W_hi, W_lo (exact TF32 split); tiny, run once per weight version
-__global__ void split_tf32_kernel(const float *__restrict__ w, float *__restrict__ hi, float *__restrict__ lo, int n)
+// transpose != 0: w is (cols, rows) row-major and hi / lo receive its transpose (rows, cols)
+__global__ void split_tf32_kernel(const float *__restrict__ w, float *__restrict__ hi, float *__restrict__ lo, int n,
+                                  int rows, int cols, int transpose)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
-        const float x = w[i];
+        const float x = transpose ? w[(i % cols) * rows + i / cols] : w[i];
         const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
         hi[i] = h;
         lo[i] = x - h;

@@ -515,8 +515,8 @@ int launch_linear(const LinearParams &p, const float *w_hi, const float *w_lo, c
     constexpr int N = NT * NH;
     CUtensorMap mh, ml;
     int rc;
-    if ((rc = make_map(&mh, w_hi, N, kGemmK, NT, kGemmBlockK, true))) return rc;
-    if ((rc = make_map(&ml, w_lo, N, kGemmK, NT, kGemmBlockK, true))) return rc;
+    if ((rc = make_map(&mh, w_hi, N, p.K, NT, kGemmBlockK, true))) return rc;
+    if ((rc = make_map(&ml, w_lo, N, p.K, NT, kGemmBlockK, true))) return rc;
     constexpr int smem = linear_smem_bytes<NT, NH>();
     static bool attr_set = false;   // idempotent; a race only repeats the same call
     if (!attr_set) {
@@ -539,14 +539,16 @@ size_t bm2f_linear_workspace_bytes(int out_features, int in_features)
     return static_cast<size_t>(2) * out_features * in_features * sizeof(float);
 }
 
-int bm2f_linear_forward(const void *x, const void *weight, const void *bias, void *y, void *workspace, int rows,
-                        int out_features, int in_features, int split, void *stream)
+namespace {
+// y[rows, n_out] = x[rows, k_red] * w'[n_out, k_red]^T (+ bias); w' = weight or its transpose
+int linear_common(const void *x, const void *weight, const void *bias, void *y, void *workspace, int rows, int n_out,
+                  int k_red, int transpose_weight, int split, void *stream)
 {
     if (!x || !weight || !y || !workspace) return fail(BM2F_ERR_INVALID, "null pointer");
     if (rows <= 0) return fail(BM2F_ERR_INVALID, "rows must be positive");
-    if (in_features != kGemmK)
-        return fail(BM2F_ERR_UNSUPPORTED, "tcgen05 projection GEMM is built for in_features = %d (got %d)", kGemmK,
-                    in_features);
+    if (k_red <= 0 || k_red % kGemmBlockK != 0 || k_red > kGemmKMax)
+        return fail(BM2F_ERR_UNSUPPORTED, "tcgen05 projection GEMM needs a reduction length that is a multiple of %d "
+                    "and <= %d (got %d)", kGemmBlockK, kGemmKMax, k_red);
     if (split != 1 && split != 3) return fail(BM2F_ERR_INVALID, "split must be 3 (tf32x3) or 1 (single TF32 pass)");
     if (!aligned16(x) || !aligned16(y) || !aligned16(weight) || !aligned16(workspace) || (bias && !aligned16(bias)))
         return fail(BM2F_ERR_UNSUPPORTED, "linear: tensors must be 16-byte aligned");
@@ -556,22 +558,37 @@ int bm2f_linear_forward(const void *x, const void *weight, const void *bias, voi
     if (cc < 10) return fail(BM2F_ERR_CUDA, "this library contains sm_100a code only; device has cc %d.x", cc);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float *w_hi = static_cast<float *>(workspace);
-    float *w_lo = w_hi + static_cast<size_t>(out_features) * in_features;
-    const int n = out_features * in_features;
-    split_tf32_kernel<<<(n + 255) / 256, 256, 0, st>>>(static_cast<const float *>(weight), w_hi, w_lo, n);
+    float *w_lo = w_hi + static_cast<size_t>(n_out) * k_red;
+    const int n = n_out * k_red;
+    split_tf32_kernel<<<(n + 255) / 256, 256, 0, st>>>(static_cast<const float *>(weight), w_hi, w_lo, n, n_out, k_red,
+                                                       transpose_weight);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "launch split_tf32_kernel");
     g_launches.fetch_add(1, std::memory_order_relaxed);
     LinearParams p{static_cast<const float *>(x), static_cast<const float *>(bias), static_cast<float *>(y), rows,
-                   out_features, split};
-    switch (out_features) {
+                   n_out, k_red, split};
+    switch (n_out) {
     case 256: return launch_linear<256, 1>(p, w_hi, w_lo, st);
     case 288: return launch_linear<144, 2>(p, w_hi, w_lo, st);
     case 192: return launch_linear<192, 1>(p, w_hi, w_lo, st);
     case 96: return launch_linear<96, 1>(p, w_hi, w_lo, st);
     default:
-        return fail(BM2F_ERR_UNSUPPORTED, "linear: out_features %d not instantiated (256, 288, 192, 96)", out_features);
+        return fail(BM2F_ERR_UNSUPPORTED, "linear: output width %d not instantiated (256, 288, 192, 96)", n_out);
     }
+}
+}  // namespace
+
+int bm2f_linear_forward(const void *x, const void *weight, const void *bias, void *y, void *workspace, int rows,
+                        int out_features, int in_features, int split, void *stream)
+{
+    return linear_common(x, weight, bias, y, workspace, rows, out_features, in_features, 0, split, stream);
+}
+
+int bm2f_linear_backward_input(const void *grad_y, const void *weight, void *grad_x, void *workspace, int rows,
+                               int out_features, int in_features, int split, void *stream)
+{
+    // grad_x[rows, in] = grad_y[rows, out] * weight[out, in]: a GEMM over k = out with w' = weight^T (in, out)
+    return linear_common(grad_y, weight, nullptr, grad_x, workspace, rows, in_features, out_features, 1, split, stream);
 }
 
 // ---------------------------------------------------------------------------------------------

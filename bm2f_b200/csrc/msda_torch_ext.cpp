@@ -236,6 +236,29 @@ bool linear_tf32x3_supported(int64_t in_features, int64_t out_features)
     return in_features == 256 && (out_features == 256 || out_features == 288 || out_features == 192 || out_features == 96);
 }
 
+// grad_x = grad_y @ weight on the tensor cores (reduction over out_features, output width in_features = 256)
+at::Tensor linear_tf32x3_backward_input(const at::Tensor &grad_y, const at::Tensor &weight, int64_t split)
+{
+    TORCH_CHECK(grad_y.is_cuda() && weight.is_cuda(), "linear_tf32x3_backward_input: CUDA tensors only");
+    TORCH_CHECK(grad_y.scalar_type() == at::kFloat && weight.scalar_type() == at::kFloat, "float32 only");
+    TORCH_CHECK(weight.dim() == 2 && grad_y.size(-1) == weight.size(0), "shape mismatch");
+    TORCH_CHECK(linear_tf32x3_supported(weight.size(1), weight.size(0)), "unsupported layer shape");
+    const c10::cuda::CUDAGuard guard(grad_y.device());
+    auto g = grad_y.contiguous();
+    auto wc = weight.contiguous();
+    const int64_t rows = g.numel() / g.size(-1);
+    auto sizes = g.sizes().vec();
+    sizes.back() = wc.size(1);
+    auto gx = at::empty(sizes, g.options());
+    auto ws = at::empty({static_cast<int64_t>(bm2f_linear_workspace_bytes(wc.size(0), wc.size(1)) / 4)}, g.options());
+    const int rc = bm2f_linear_backward_input(g.data_ptr(), wc.data_ptr(), gx.data_ptr(), ws.data_ptr(),
+                                              static_cast<int>(rows), static_cast<int>(wc.size(0)),
+                                              static_cast<int>(wc.size(1)), static_cast<int>(split),
+                                              at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == BM2F_OK, "linear_tf32x3_backward_input: ", bm2f_msda_last_error());
+    return gx;
+}
+
 at::Tensor linear_tf32x3(const at::Tensor &x, const at::Tensor &weight, const c10::optional<at::Tensor> &bias,
                          int64_t split)
 {
@@ -279,6 +302,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("ms_deform_attn_fused_backward", &ms_deform_attn_fused_backward, "backward of the fused op");
     m.def("linear_tf32x3", &linear_tf32x3, "tcgen05 projection GEMM (y = x W^T + b), split=3: tf32x3, 1: tf32");
     m.def("linear_tf32x3_supported", &linear_tf32x3_supported);
+    m.def("linear_tf32x3_backward_input", &linear_tf32x3_backward_input, "grad_x = grad_y @ weight (tcgen05)");
     m.def("abi_version", []() { return bm2f_msda_abi_version(); });
     m.def("build_info", []() { return std::string(bm2f_msda_build_info()); });
     m.def("launch_count", []() { return bm2f_msda_launch_count(); });

@@ -3,8 +3,8 @@
 `linear_tf32x3(x, weight, bias)` = `F.linear` for the module's four nn.Linear layers
 (ops/modules/ms_deform_attn.py:59-62) with the forward GEMM done by the tcgen05 kernel in
 csrc/linear_tf32x3.cuh (three-term TF32 split, fp32 accumulation in TMEM: fp32-grade results).
-The backward (grad_x = g W, grad_W = g^T x, grad_b = sum g) is left to cuBLAS through torch in this
-round; only the forward runs on hand-written tcgen05 code."""
+grad_x = g W runs on the same kernel (reduction over out_features); grad_W = g^T x and grad_b = sum g
+reduce over the ~10^5 rows and are left to cuBLAS through torch in this round."""
 from __future__ import annotations
 
 import torch
@@ -21,6 +21,7 @@ class LinearTF32x3Function(Function):
     def forward(ctx, x, weight, bias, split):
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
+        ctx.split = split
         return MSDA.linear_tf32x3(x, weight, bias, split)
 
     @staticmethod
@@ -28,7 +29,8 @@ class LinearTF32x3Function(Function):
     def backward(ctx, g):
         x, weight = ctx.saved_tensors
         g2 = g.reshape(-1, g.shape[-1])
-        gx = (g2 @ weight).view_as(x) if ctx.needs_input_grad[0] else None
+        gx = MSDA.linear_tf32x3_backward_input(g2.contiguous(), weight, ctx.split).view_as(x) \
+            if ctx.needs_input_grad[0] else None
         gw = g2.t() @ x.reshape(-1, x.shape[-1]) if ctx.needs_input_grad[1] else None
         gb = g2.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return gx, gw, gb, None

@@ -164,7 +164,8 @@ int bm2f_msda_fused_backward(const void *value, const int64_t *spatial_shapes,
  * Projection GEMM on the 5th-generation tensor cores (tcgen05 + TMEM), for the four nn.Linear layers of
  * MSDeformAttn (ops/modules/ms_deform_attn.py:59-62; applied at :98, :101, :102, :124):
  *     y[rows, out_features] = x[rows, in_features] * weight[out_features, in_features]^T + bias
- * float32 in / out, in_features = 256 (d_model), out_features in {256, 288, 192, 96}.
+ * float32 in / out; output width in {256, 288, 192, 96}, reduction length a multiple of 32 up to 288
+ * (forward: in_features = 256 = d_model; bm2f_linear_backward_input: grad_x = grad_y * weight, width 256).
  * split = 3: three-term TF32 split with fp32 accumulation (fp32-grade result, what the fp32 reference
  * module needs); split = 1: single TF32 pass.  `workspace` = bm2f_linear_workspace_bytes() of device
  * memory for the hi/lo halves of the weight (rewritten on every call).  bias may be NULL.
@@ -172,6 +173,8 @@ int bm2f_msda_fused_backward(const void *value, const int64_t *spatial_shapes,
 size_t bm2f_linear_workspace_bytes(int out_features, int in_features);
 int bm2f_linear_forward(const void *x, const void *weight, const void *bias, void *y, void *workspace,
                         int rows, int out_features, int in_features, int split, void *stream);
+int bm2f_linear_backward_input(const void *grad_y, const void *weight, void *grad_x, void *workspace,
+                               int rows, int out_features, int in_features, int split, void *stream);
 
 /*
  * Host-buffer convenience used for end-to-end measurement and by non-torch callers:

@@ -1,0 +1,32 @@
+"""tcgen05 projection GEMM vs torch F.linear (fp32 cuBLAS, TF32 off / on) at the cfg-2 row count."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import torch.nn.functional as F
+import bm2f_b200
+MSDA = bm2f_b200.load_extension()
+dev = torch.device("cuda:0")
+rows = int(sys.argv[1]) if len(sys.argv) > 1 else 16 * 21504
+x = torch.randn(rows, 256, device=dev)
+def t(fn, reps=10):
+    fn(); fn(); torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize(); best = min(best, a.elapsed_time(b))
+    return best
+for n in (256, 288, 192, 96):
+    w = torch.randn(n, 256, device=dev) / 16; b = torch.randn(n, device=dev)
+    ref = x.double() @ w.double().t() + b.double()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    t_fp32 = t(lambda: F.linear(x, w, b)); e_fp32 = ((F.linear(x, w, b).double() - ref).abs().max() / ref.abs().max()).item()
+    torch.backends.cuda.matmul.allow_tf32 = True
+    t_tf32 = t(lambda: F.linear(x, w, b)); e_tf32 = ((F.linear(x, w, b).double() - ref).abs().max() / ref.abs().max()).item()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    t3 = t(lambda: MSDA.linear_tf32x3(x, w, b, 3)); e3 = ((MSDA.linear_tf32x3(x, w, b, 3).double() - ref).abs().max() / ref.abs().max()).item()
+    t1 = t(lambda: MSDA.linear_tf32x3(x, w, b, 1)); e1 = ((MSDA.linear_tf32x3(x, w, b, 1).double() - ref).abs().max() / ref.abs().max()).item()
+    gb = rows * (256 + n) * 4 / 1e9
+    fl = 2.0 * rows * 256 * n / 1e12
+    print(f"N={n:3d} rows={rows}: cuBLAS fp32 {t_fp32:.3f} ms (err {e_fp32:.1e}) | cuBLAS tf32 {t_tf32:.3f} ms (err {e_tf32:.1e}) | "
+          f"tcgen05 tf32x3 {t3:.3f} ms (err {e3:.1e}, {gb/t3*1e3:.0f} GB/s, {3*fl/t3*1e3:.0f} TF/s tf32) | tcgen05 tf32x1 {t1:.3f} ms (err {e1:.1e}, {gb/t1*1e3:.0f} GB/s)")

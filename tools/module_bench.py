@@ -74,9 +74,9 @@ def main():
     variants = {"fused+tcgen05": (True, True), "fused+torch_linear": (True, False), "unfused+torch_linear": (False, False)}
     res = {}
     outs = {}
-    for name, (fuse, tc) in list(variants.items()) + ([("reference_op", None)] if REF is not None else []):
+    for name, cfg in list(variants.items()) + ([("reference_op", None)] if REF is not None else []):
         if name != "reference_op":
-            mod.fuse_prologue, mod.tcgen05_linear = fuse, tc
+            mod.fuse_prologue, mod.tcgen05_linear = cfg
         kind = "reference_op" if name == "reference_op" else "ours"
         for _ in range(2):
             outs[name] = run(kind).detach()
