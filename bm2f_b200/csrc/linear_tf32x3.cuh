@@ -14,7 +14,7 @@
 //   warp 1      lane 0 = MMA issuer: tcgen05.mma.cta_group::1.kind::tf32, M=128, N=tile width, K=8 per instruction
 //   warps 2..5  X producers: coalesced 128-bit global loads, split into hi / lo, written to shared memory in
 //               the UMMA K-major SWIZZLE_128B layout; after the main loop the same warps are the epilogue:
-//               tcgen05.ld (TMEM -> registers), + bias, 128-bit stores.
+//               tcgen05.ld (TMEM -> registers), + bias, swizzled staging tile, TMA store (cp.async.bulk.tensor).
 // Two shared-memory stages of one k-block (32 floats = one 128-byte swizzle row) each, full/empty mbarriers;
 // tcgen05.commit releases a stage when the MMAs that read it have retired.
 #pragma once
@@ -138,7 +138,7 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity
 template <int NT, int NH>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_tf32x3_kernel(const LinearParams p, const __grid_constant__ CUtensorMap tm_whi,
-                     const __grid_constant__ CUtensorMap tm_wlo)
+                     const __grid_constant__ CUtensorMap tm_wlo, const __grid_constant__ CUtensorMap tm_y)
 {
     constexpr int N = NT * NH;
     constexpr int kXBytes = kGemmBlockM * kGemmBlockK * 4;              // 16 KB
@@ -167,6 +167,7 @@ linear_tf32x3_kernel(const LinearParams p, const __grid_constant__ CUtensorMap t
         fence_mbar_init();
         tma_prefetch_desc(&tm_whi);
         tma_prefetch_desc(&tm_wlo);
+        tma_prefetch_desc(&tm_y);
     }
     if (warp == 0) tmem_alloc(&tmem_base_slot, kTmemCols);
     tc_fence_before();
@@ -230,17 +231,20 @@ linear_tf32x3_kernel(const LinearParams p, const __grid_constant__ CUtensorMap t
         const int t = threadIdx.x - 64;                // 0..127
         const int c16 = t & 7;                         // 16-byte chunk inside the 128-byte row
         const int rsub = t >> 3;                       // 0..15
-        for (int kb = 0; kb < kKBlocks; ++kb) {
-            const int s = kb % kGemmStages;
-            float4 v[8];
+        auto load_x = [&](int kb, float4 (&v)[8]) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int r = rsub + 16 * j;
-                const int gr = row0 + r;
+                const int gr = row0 + rsub + 16 * j;
                 v[j] = gr < p.M ? __ldg(reinterpret_cast<const float4 *>(p.x + static_cast<size_t>(gr) * p.K +
                                                                            kb * kGemmBlockK) + c16)
                                 : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+        };
+        float4 cur[8], nxt[8];
+        load_x(0, cur);
+        for (int kb = 0; kb < kKBlocks; ++kb) {
+            const int s = kb % kGemmStages;
+            if (kb + 1 < kKBlocks) load_x(kb + 1, nxt);        // next k-block's loads fly while this one is converted
             mbar_wait_bounded(&empty_bar[s], ((kb / kGemmStages) & 1) ^ 1);
             unsigned char *x_hi = stage_ptr(s);
             unsigned char *x_lo = x_hi + kXBytes;
@@ -249,39 +253,54 @@ linear_tf32x3_kernel(const LinearParams p, const __grid_constant__ CUtensorMap t
                 const int r = rsub + 16 * j;
                 const uint32_t off = r * 128 + ((c16 ^ (r & 7)) << 4);      // SWIZZLE_128B
                 float4 hi, lo;
-                hi.x = __uint_as_float(__float_as_uint(v[j].x) & 0xffffe000u); lo.x = v[j].x - hi.x;
-                hi.y = __uint_as_float(__float_as_uint(v[j].y) & 0xffffe000u); lo.y = v[j].y - hi.y;
-                hi.z = __uint_as_float(__float_as_uint(v[j].z) & 0xffffe000u); lo.z = v[j].z - hi.z;
-                hi.w = __uint_as_float(__float_as_uint(v[j].w) & 0xffffe000u); lo.w = v[j].w - hi.w;
+                hi.x = __uint_as_float(__float_as_uint(cur[j].x) & 0xffffe000u); lo.x = cur[j].x - hi.x;
+                hi.y = __uint_as_float(__float_as_uint(cur[j].y) & 0xffffe000u); lo.y = cur[j].y - hi.y;
+                hi.z = __uint_as_float(__float_as_uint(cur[j].z) & 0xffffe000u); lo.z = cur[j].z - hi.z;
+                hi.w = __uint_as_float(__float_as_uint(cur[j].w) & 0xffffe000u); lo.w = cur[j].w - hi.w;
                 *reinterpret_cast<float4 *>(x_hi + off) = hi;
                 *reinterpret_cast<float4 *>(x_lo + off) = lo;
             }
             fence_async_smem();                        // generic-proxy writes -> visible to the tensor core (async proxy)
             mbar_arrive(&full_bar[s]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
         }
-        // epilogue: thread <-> one output row; warp w may touch TMEM lanes 32*(w%4) .. +31
+        // epilogue: thread <-> one output row; warp w may touch TMEM lanes 32*(w%4) .. +31.  Each 32-column
+        // chunk goes TMEM -> registers (+bias) -> a SWIZZLE_128B staging tile in the (now idle) stage memory
+        // -> one TMA store of a 128 x 32 box; rows past M are clipped by the tensor map.
         mbar_wait_bounded(&acc_bar, 0);
         tc_fence_after();
         const int q = warp & 3;
         const int r = q * 32 + lane;
-        const int gr = row0 + r;
-        float *yrow = p.y + static_cast<size_t>(gr) * p.N;
 #pragma unroll 1
-        for (int c0 = 0; c0 < N; c0 += 32) {
+        for (int c0 = 0, it = 0; c0 < N; c0 += 32, ++it) {
             float acc[32];
             tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, acc);
-            if (gr < p.M) {
+            unsigned char *stg = smem + (it & 1) * kXBytes;             // two 16 KB staging tiles
+            if (it >= 2) {                                               // tile written two chunks ago must be drained
+                if (t == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
 #pragma unroll
-                for (int c = 0; c < 32; c += 4) {
-                    float4 o = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
-                    if (p.bias) {
-                        const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + c0 + c));
-                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                    }
-                    *reinterpret_cast<float4 *>(yrow + c0 + c) = o;
+            for (int c = 0; c < 32; c += 4) {
+                float4 o = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+                if (p.bias) {
+                    const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + c0 + c));
+                    o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
                 }
+                *reinterpret_cast<float4 *>(stg + r * 128 + ((((c >> 2) ^ (r & 7))) << 4)) = o;
+            }
+            fence_async_smem();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (t == 0) {
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                 reinterpret_cast<uint64_t>(&tm_y)),
+                             "r"(smem_u32(stg)), "r"(c0), "r"(row0)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         }
+        if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         tc_fence_before();
     }
     __syncthreads();
@@ -289,6 +308,205 @@ linear_tf32x3_kernel(const LinearParams p, const __grid_constant__ CUtensorMap t
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }
+}
+
+
+// ------------------------------------------------------------------------------------------------------
+// Persistent variant (N <= 256): one CTA per SM loops over its row tiles; the accumulator is double-buffered in
+// TMEM so the epilogue of tile i (warps 6..9: TMEM -> staging tile -> TMA store) overlaps the MMAs of tile
+// i+1, and the shared-memory stage ring / X register prefetch run across tile boundaries.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kGemmThreadsPersistent = 320;
+
+template <int NT>
+__global__ void __launch_bounds__(kGemmThreadsPersistent, 1)
+linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CUtensorMap tm_whi,
+                                const __grid_constant__ CUtensorMap tm_wlo, const __grid_constant__ CUtensorMap tm_y)
+{
+    constexpr int N = NT;
+    constexpr int kXBytes = kGemmBlockM * kGemmBlockK * 4;
+    constexpr int kWBytes = N * kGemmBlockK * 4;
+    constexpr int kStageBytes = 2 * kXBytes + 2 * kWBytes;
+    constexpr uint32_t kTmemCols = (2 * N <= 64) ? 64 : (2 * N <= 128) ? 128 : (2 * N <= 256) ? 256 : 512;
+    static_assert(NT % 16 == 0 && NT <= 256, "UMMA N for M = 128, two accumulators in 512 TMEM columns");
+
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char *staging = smem + kGemmStages * kStageBytes;            // 2 x 16 KB epilogue tiles
+    __shared__ uint64_t full_bar[kGemmStages], empty_bar[kGemmStages], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kKBlocks = p.K / kGemmBlockK;
+    const int num_tiles = (p.M + kGemmBlockM - 1) / kGemmBlockM;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGemmStages; ++s) {
+            mbar_init(&full_bar[s], 128 + 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);        // tcgen05.commit after the last k-block of a tile
+            mbar_init(&acc_empty[b], 128);     // every epilogue thread, after its last TMEM read of the tile
+        }
+        fence_mbar_init();
+        tma_prefetch_desc(&tm_whi);
+        tma_prefetch_desc(&tm_wlo);
+        tma_prefetch_desc(&tm_y);
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+    auto stage_ptr = [&](int s) { return smem + s * kStageBytes; };
+
+    if (warp == 0) {
+        if (lane == 0) {                                   // ---- TMA producer (W_hi, W_lo) ----
+            int g = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < kKBlocks; ++kb, ++g) {
+                    const int s = g % kGemmStages;
+                    mbar_wait_bounded(&empty_bar[s], ((g / kGemmStages) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[s], p.split == 3 ? 2 * kWBytes : kWBytes);
+                    unsigned char *w_hi = stage_ptr(s) + 2 * kXBytes;
+                    tma_load_2d(w_hi, &tm_whi, kb * kGemmBlockK, 0, &full_bar[s]);
+                    if (p.split == 3) tma_load_2d(w_hi + kWBytes, &tm_wlo, kb * kGemmBlockK, 0, &full_bar[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                   // ---- MMA issuer ----
+            constexpr uint32_t idesc = umma_idesc_tf32(kGemmBlockM, NT);
+            int g = 0, i = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
+                const int b = i & 1;
+                mbar_wait_bounded(&acc_empty[b], ((i >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d = tmem_base + b * NT;
+                for (int kb = 0; kb < kKBlocks; ++kb, ++g) {
+                    const int s = g % kGemmStages;
+                    mbar_wait_bounded(&full_bar[s], (g / kGemmStages) & 1);
+                    tc_fence_after();
+                    const uint32_t x_hi = smem_u32(stage_ptr(s));
+                    const uint32_t x_lo = x_hi + kXBytes;
+                    const uint32_t w_hi = x_hi + 2 * kXBytes;
+                    const uint32_t w_lo = w_hi + kWBytes;
+#pragma unroll
+                    for (int k = 0; k < kGemmBlockK / 8; ++k) {
+                        const uint32_t koff = k * 32;
+                        const uint64_t a_hi = umma_desc_k128(x_hi + koff);
+                        const uint64_t b_hi = umma_desc_k128(w_hi + koff);
+                        umma_tf32(d, a_hi, b_hi, idesc, (kb | k) ? 1u : 0u);
+                        if (p.split == 3) {
+                            umma_tf32(d, umma_desc_k128(x_lo + koff), b_hi, idesc, 1u);
+                            umma_tf32(d, a_hi, umma_desc_k128(w_lo + koff), idesc, 1u);
+                        }
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&acc_full[b]);
+            }
+        }
+    } else if (warp < 6) {
+        // ---- X producers (warps 2..5): global -> registers -> hi/lo -> swizzled shared memory ----
+        const int t = threadIdx.x - 64;
+        const int c16 = t & 7, rsub = t >> 3;
+        auto load_x = [&](int tile, int kb, float4 (&v)[8]) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int gr = tile * kGemmBlockM + rsub + 16 * j;
+                v[j] = gr < p.M ? __ldg(reinterpret_cast<const float4 *>(p.x + static_cast<size_t>(gr) * p.K +
+                                                                           kb * kGemmBlockK) + c16)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        float4 cur[8], nxt[8];
+        int tile = blockIdx.x, kb = 0, g = 0;
+        if (tile < num_tiles) load_x(tile, 0, cur);
+        while (tile < num_tiles) {
+            int ntile = tile, nkb = kb + 1;
+            if (nkb == kKBlocks) { nkb = 0; ntile += gridDim.x; }
+            if (ntile < num_tiles) load_x(ntile, nkb, nxt);
+            const int s = g % kGemmStages;
+            mbar_wait_bounded(&empty_bar[s], ((g / kGemmStages) & 1) ^ 1);
+            unsigned char *x_hi = stage_ptr(s);
+            unsigned char *x_lo = x_hi + kXBytes;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int r = rsub + 16 * j;
+                const uint32_t off = r * 128 + ((c16 ^ (r & 7)) << 4);
+                float4 hi, lo;
+                hi.x = __uint_as_float(__float_as_uint(cur[j].x) & 0xffffe000u); lo.x = cur[j].x - hi.x;
+                hi.y = __uint_as_float(__float_as_uint(cur[j].y) & 0xffffe000u); lo.y = cur[j].y - hi.y;
+                hi.z = __uint_as_float(__float_as_uint(cur[j].z) & 0xffffe000u); lo.z = cur[j].z - hi.z;
+                hi.w = __uint_as_float(__float_as_uint(cur[j].w) & 0xffffe000u); lo.w = cur[j].w - hi.w;
+                *reinterpret_cast<float4 *>(x_hi + off) = hi;
+                *reinterpret_cast<float4 *>(x_lo + off) = lo;
+            }
+            fence_async_smem();
+            mbar_arrive(&full_bar[s]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+            tile = ntile; kb = nkb; ++g;
+        }
+    } else {
+        // ---- epilogue (warps 6..9) ----
+        const int t = threadIdx.x - 192;
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        int i = 0, chunk = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
+            const int b = i & 1;
+            mbar_wait_bounded(&acc_full[b], (i >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < N; c0 += 32, ++chunk) {
+                float acc[32];
+                tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * NT + c0, acc);
+                if (c0 + 32 >= N) {                      // last TMEM read of this tile: hand the accumulator back
+                    tc_fence_before();
+                    mbar_arrive(&acc_empty[b]);
+                }
+                unsigned char *stg = staging + (chunk & 1) * kXBytes;
+                if (chunk >= 2) {
+                    if (t == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+#pragma unroll
+                for (int c = 0; c < 32; c += 4) {
+                    float4 o = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+                    if (p.bias) {
+                        const float4 bb = __ldg(reinterpret_cast<const float4 *>(p.bias + c0 + c));
+                        o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                    }
+                    *reinterpret_cast<float4 *>(stg + r * 128 + ((((c >> 2) ^ (r & 7))) << 4)) = o;
+                }
+                fence_async_smem();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (t == 0) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                     reinterpret_cast<uint64_t>(&tm_y)),
+                                 "r"(smem_u32(stg)), "r"(c0), "r"(tile * kGemmBlockM)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+        }
+        if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+template <int NT>
+constexpr int linear_persistent_smem_bytes()
+{
+    return kGemmStages * (2 * kGemmBlockM * kGemmBlockK * 4 + 2 * NT * kGemmBlockK * 4) + 2 * kGemmBlockM * kGemmBlockK * 4 + 1024;
 }
 
 template <int NT, int NH>

@@ -517,6 +517,8 @@ int launch_linear(const LinearParams &p, const float *w_hi, const float *w_lo, c
     int rc;
     if ((rc = make_map(&mh, w_hi, N, p.K, NT, kGemmBlockK, true))) return rc;
     if ((rc = make_map(&ml, w_lo, N, p.K, NT, kGemmBlockK, true))) return rc;
+    CUtensorMap my;
+    if ((rc = make_map(&my, p.y, p.M, N, kGemmBlockM, 32, true))) return rc;
     constexpr int smem = linear_smem_bytes<NT, NH>();
     static bool attr_set = false;   // idempotent; a race only repeats the same call
     if (!attr_set) {
@@ -525,9 +527,33 @@ int launch_linear(const LinearParams &p, const float *w_hi, const float *w_lo, c
         attr_set = true;
     }
     const int grid = (p.M + kGemmBlockM - 1) / kGemmBlockM;
-    linear_tf32x3_kernel<NT, NH><<<grid, kGemmThreads, smem, st>>>(p, mh, ml);
+    linear_tf32x3_kernel<NT, NH><<<grid, kGemmThreads, smem, st>>>(p, mh, ml, my);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "launch linear_tf32x3_kernel");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return BM2F_OK;
+}
+template <int NT>
+int launch_linear_persistent(const LinearParams &p, const float *w_hi, const float *w_lo, int sms, cudaStream_t st)
+{
+    CUtensorMap mh, ml, my;
+    int rc;
+    if ((rc = make_map(&mh, w_hi, NT, p.K, NT, kGemmBlockK, true))) return rc;
+    if ((rc = make_map(&ml, w_lo, NT, p.K, NT, kGemmBlockK, true))) return rc;
+    if ((rc = make_map(&my, p.y, p.M, NT, kGemmBlockM, 32, true))) return rc;
+    constexpr int smem = linear_persistent_smem_bytes<NT>();
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(linear_tf32x3_persistent_kernel<NT>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(persistent linear smem)");
+        attr_set = true;
+    }
+    const int tiles = (p.M + kGemmBlockM - 1) / kGemmBlockM;
+    const int grid = tiles < sms ? tiles : sms;
+    linear_tf32x3_persistent_kernel<NT><<<grid, kGemmThreadsPersistent, smem, st>>>(p, mh, ml, my);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "launch linear_tf32x3_persistent_kernel");
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return BM2F_OK;
 }
@@ -549,6 +575,9 @@ int linear_common(const void *x, const void *weight, const void *bias, void *y, 
     if (k_red <= 0 || k_red % kGemmBlockK != 0 || k_red > kGemmKMax)
         return fail(BM2F_ERR_UNSUPPORTED, "tcgen05 projection GEMM needs a reduction length that is a multiple of %d "
                     "and <= %d (got %d)", kGemmBlockK, kGemmKMax, k_red);
+    // split 3 / 1: persistent kernel (double-buffered TMEM accumulator); 13 / 11: one tile per CTA (kept for A/B)
+    const bool one_tile = split >= 10;
+    if (one_tile) split -= 10;
     if (split != 1 && split != 3) return fail(BM2F_ERR_INVALID, "split must be 3 (tf32x3) or 1 (single TF32 pass)");
     if (!aligned16(x) || !aligned16(y) || !aligned16(weight) || !aligned16(workspace) || (bias && !aligned16(bias)))
         return fail(BM2F_ERR_UNSUPPORTED, "linear: tensors must be 16-byte aligned");
@@ -567,6 +596,14 @@ int linear_common(const void *x, const void *weight, const void *bias, void *y, 
     g_launches.fetch_add(1, std::memory_order_relaxed);
     LinearParams p{static_cast<const float *>(x), static_cast<const float *>(bias), static_cast<float *>(y), rows,
                    n_out, k_red, split};
+    if (!one_tile) {
+        switch (n_out) {
+        case 256: return launch_linear_persistent<256>(p, w_hi, w_lo, sms, st);
+        case 192: return launch_linear_persistent<192>(p, w_hi, w_lo, sms, st);
+        case 96: return launch_linear_persistent<96>(p, w_hi, w_lo, sms, st);
+        default: break;      // 288 = 2 x 144 columns does not fit two accumulators: one-tile kernel
+        }
+    }
     switch (n_out) {
     case 256: return launch_linear<256, 1>(p, w_hi, w_lo, st);
     case 288: return launch_linear<144, 2>(p, w_hi, w_lo, st);

@@ -30,6 +30,21 @@ def test_linear_tf32x3_matches_fp64(msda, out_features, rows):
     assert err3 < err1
     ynb = msda.linear_tf32x3(x, w, None, 3)
     assert torch.allclose(ynb + b, y3, atol=1e-5, rtol=1e-5)
+    # split + 10 = the one-tile-per-CTA kernel; 3 / 1 = persistent kernel (where the width allows it)
+    y13 = msda.linear_tf32x3(x, w, b, 13)
+    assert torch.equal(y13, y3) or (y13 - y3).abs().max().item() <= 1e-6 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("rows", [128 * 148 * 3 + 5, 128 * 149])      # several tiles per persistent CTA, ragged
+def test_linear_persistent_many_tiles(msda, rows):
+    torch.manual_seed(rows)
+    dev = torch.device("cuda:0")
+    x = torch.randn(rows, 256, device=dev)
+    w = torch.randn(192, 256, device=dev) / 16
+    b = torch.randn(192, device=dev)
+    ref = x.double() @ w.double().t() + b.double()
+    y = msda.linear_tf32x3(x, w, b, 3)
+    assert (y.double() - ref).abs().max().item() / ref.abs().max().item() <= 5e-6
 
 
 def test_linear_batched_input_and_autograd(msda):

@@ -25,8 +25,10 @@ for n in (256, 288, 192, 96):
     t_tf32 = t(lambda: F.linear(x, w, b)); e_tf32 = ((F.linear(x, w, b).double() - ref).abs().max() / ref.abs().max()).item()
     torch.backends.cuda.matmul.allow_tf32 = False
     t3 = t(lambda: MSDA.linear_tf32x3(x, w, b, 3)); e3 = ((MSDA.linear_tf32x3(x, w, b, 3).double() - ref).abs().max() / ref.abs().max()).item()
+    t13 = t(lambda: MSDA.linear_tf32x3(x, w, b, 13))
     t1 = t(lambda: MSDA.linear_tf32x3(x, w, b, 1)); e1 = ((MSDA.linear_tf32x3(x, w, b, 1).double() - ref).abs().max() / ref.abs().max()).item()
     gb = rows * (256 + n) * 4 / 1e9
     fl = 2.0 * rows * 256 * n / 1e12
     print(f"N={n:3d} rows={rows}: cuBLAS fp32 {t_fp32:.3f} ms (err {e_fp32:.1e}) | cuBLAS tf32 {t_tf32:.3f} ms (err {e_tf32:.1e}) | "
-          f"tcgen05 tf32x3 {t3:.3f} ms (err {e3:.1e}, {gb/t3*1e3:.0f} GB/s, {3*fl/t3*1e3:.0f} TF/s tf32) | tcgen05 tf32x1 {t1:.3f} ms (err {e1:.1e}, {gb/t1*1e3:.0f} GB/s)")
+          f"tcgen05 tf32x3 persistent {t3:.3f} ms (err {e3:.1e}, {gb/t3*1e3:.0f} GB/s, {3*fl/t3*1e3:.0f} TF/s tf32) | "
+          f"one-tile {t13:.3f} ms | tf32x1 persistent {t1:.3f} ms (err {e1:.1e}, {gb/t1*1e3:.0f} GB/s)")
