@@ -57,7 +57,8 @@ def _run(cmd, log=None):
 
 
 def build_lib(force=False, ptxas_log=None) -> str:
-    srcs = [os.path.join(CSRC, f) for f in ("msda_api.cu", "msda_fast.cuh", "msda_generic.cuh", "msda_common.cuh")]
+    import glob
+    srcs = glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(CSRC, "msda_api.cu")]   # every header the unit includes
     srcs.append(os.path.join(ROOT, "include", "bm2f_msda.h"))
     if force or _stale(LIB, srcs):
         cmd = [_nvcc()] + NVCC_FLAGS + ["-shared", "-Xptxas", "-v", "-o", LIB, os.path.join(CSRC, "msda_api.cu")]

@@ -20,7 +20,7 @@ SYMBOLS = (
     "bm2f_msda_set_default_tuning", "bm2f_msda_check_im2col_step", "bm2f_msda_forward",
     "bm2f_msda_backward", "bm2f_msda_forward_backward_host", "bm2f_msda_fused_supported",
     "bm2f_msda_fused_forward", "bm2f_msda_fused_backward", "bm2f_linear_workspace_bytes", "bm2f_linear_forward",
-    "bm2f_linear_backward_input",
+    "bm2f_linear_backward_input", "bm2f_linear_backward_weight",
 )
 
 
@@ -69,6 +69,8 @@ def lib():
         L.bm2f_linear_forward.restype = ci
         L.bm2f_linear_backward_input.argtypes = [vp] * 4 + [ci] * 4 + [vp]
         L.bm2f_linear_backward_input.restype = ci
+        L.bm2f_linear_backward_weight.argtypes = [vp] * 4 + [ci] * 4 + [vp]
+        L.bm2f_linear_backward_weight.restype = ci
         L.bm2f_msda_forward_backward_host.argtypes = [vp] * 10 + [ci] * 8 + [tp]
         L.bm2f_msda_forward_backward_host.restype = ci
         _lib = L

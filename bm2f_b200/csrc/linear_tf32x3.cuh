@@ -37,6 +37,11 @@ struct LinearParams {
     int split;           // 3 = tf32x3 (fp32-grade), 1 = single TF32 pass
 };
 
+
+// x = hi + lo with hi exactly representable in TF32 (10 explicit mantissa bits), rounded to nearest so that the
+// low parts have no sign bias (matters for the 10^5-term weight-gradient reductions)
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+
 // ---- tcgen05 / TMEM wrappers -------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_slot, uint32_t ncols)
 {
@@ -253,10 +258,10 @@ linear_tf32x3_kernel(const LinearParams p, const __grid_constant__ CUtensorMap t
                 const int r = rsub + 16 * j;
                 const uint32_t off = r * 128 + ((c16 ^ (r & 7)) << 4);      // SWIZZLE_128B
                 float4 hi, lo;
-                hi.x = __uint_as_float(__float_as_uint(cur[j].x) & 0xffffe000u); lo.x = cur[j].x - hi.x;
-                hi.y = __uint_as_float(__float_as_uint(cur[j].y) & 0xffffe000u); lo.y = cur[j].y - hi.y;
-                hi.z = __uint_as_float(__float_as_uint(cur[j].z) & 0xffffe000u); lo.z = cur[j].z - hi.z;
-                hi.w = __uint_as_float(__float_as_uint(cur[j].w) & 0xffffe000u); lo.w = cur[j].w - hi.w;
+                hi.x = tf32_hi(cur[j].x); lo.x = cur[j].x - hi.x;
+                hi.y = tf32_hi(cur[j].y); lo.y = cur[j].y - hi.y;
+                hi.z = tf32_hi(cur[j].z); lo.z = cur[j].z - hi.z;
+                hi.w = tf32_hi(cur[j].w); lo.w = cur[j].w - hi.w;
                 *reinterpret_cast<float4 *>(x_hi + off) = hi;
                 *reinterpret_cast<float4 *>(x_lo + off) = lo;
             }
@@ -437,10 +442,10 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
                 const int r = rsub + 16 * j;
                 const uint32_t off = r * 128 + ((c16 ^ (r & 7)) << 4);
                 float4 hi, lo;
-                hi.x = __uint_as_float(__float_as_uint(cur[j].x) & 0xffffe000u); lo.x = cur[j].x - hi.x;
-                hi.y = __uint_as_float(__float_as_uint(cur[j].y) & 0xffffe000u); lo.y = cur[j].y - hi.y;
-                hi.z = __uint_as_float(__float_as_uint(cur[j].z) & 0xffffe000u); lo.z = cur[j].z - hi.z;
-                hi.w = __uint_as_float(__float_as_uint(cur[j].w) & 0xffffe000u); lo.w = cur[j].w - hi.w;
+                hi.x = tf32_hi(cur[j].x); lo.x = cur[j].x - hi.x;
+                hi.y = tf32_hi(cur[j].y); lo.y = cur[j].y - hi.y;
+                hi.z = tf32_hi(cur[j].z); lo.z = cur[j].z - hi.z;
+                hi.w = tf32_hi(cur[j].w); lo.w = cur[j].w - hi.w;
                 *reinterpret_cast<float4 *>(x_hi + off) = hi;
                 *reinterpret_cast<float4 *>(x_lo + off) = lo;
             }
@@ -509,6 +514,199 @@ constexpr int linear_persistent_smem_bytes()
     return kGemmStages * (2 * kGemmBlockM * kGemmBlockK * 4 + 2 * NT * kGemmBlockK * 4) + 2 * kGemmBlockM * kGemmBlockK * 4 + 1024;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Weight / bias gradient of the projections on tcgen05:
+//     dW[n, k] = sum_r G[r, n] * X[r, k]        db[n] = sum_r G[r, n]         (r over ~10^5 rows)
+// The reduction index r is the ROW of both inputs, so producer threads transpose on the fly: four rows of one
+// feature become one 16-byte chunk of that feature's K-major (K = r) SWIZZLE_128B row — lane = feature makes
+// both the global loads (32 x 4 B contiguous) and the swizzled 128-bit shared stores conflict-free.
+//   A = G^T tile (128 features n x 32 rows), B = [X^T ; ones ; 0] tile (256 features k + 1 row of ones x 32 rows):
+//   column 256 of the accumulator is the bias gradient.  TF32 3-term split as in the forward kernel.
+// grid = (n tiles) x (row chunks): every CTA accumulates its chunk in TMEM and adds the 128 x 257 partial result
+// to dW / db with red.global.add (outputs must be zeroed by the caller).
+// ------------------------------------------------------------------------------------------------------
+constexpr int kDwThreads = 320;        // warp 0: TMEM + constants, warp 1: MMA issuer, warps 2..9: transposing producers
+constexpr int kDwNB = 272;             // 256 features + ones row, padded to a multiple of 16
+
+struct LinearDwParams {
+    const float *g;      // (M, N)  grad_y
+    const float *x;      // (M, 256)
+    float *dw;           // (N, 256), accumulated into
+    float *db;           // (N) or nullptr, accumulated into
+    int M, N;
+    int rows_per_chunk;  // multiple of 32
+    int split;
+};
+
+__global__ void __launch_bounds__(kDwThreads, 1) linear_dw_tf32x3_kernel(const LinearDwParams p)
+{
+    constexpr int kABytes = 128 * 128;                 // 128 features x 128 B
+    constexpr int kBBytes = kDwNB * 128;               // 272 features x 128 B
+    constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+    constexpr int kKx = 256;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t full_bar[kGemmStages], empty_bar[kGemmStages], acc_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * 128;
+    const int r_begin = blockIdx.y * p.rows_per_chunk;
+    const int r_end = min(p.M, r_begin + p.rows_per_chunk);
+    const int kblocks = r_end > r_begin ? (r_end - r_begin + 31) / 32 : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGemmStages; ++s) {
+            mbar_init(&full_bar[s], 256);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&acc_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(&tmem_base_slot, 512);
+        // constant rows of B: row 256 = ones (hi only), rows 257..271 = 0, in both stages
+        for (int s = 0; s < kGemmStages; ++s) {
+            unsigned char *b_hi = smem + s * kStageBytes + 2 * kABytes;
+            unsigned char *b_lo = b_hi + kBBytes;
+            for (int e = lane; e < 16 * 8; e += 32) {              // 16 rows x 8 chunks
+                const int row = 256 + e / 8, ch = e % 8;
+                const float v = (row == 256) ? 1.f : 0.f;
+                const uint32_t off = row * 128 + ((ch ^ (row & 7)) << 4);
+                *reinterpret_cast<float4 *>(b_hi + off) = make_float4(v, v, v, v);
+                *reinterpret_cast<float4 *>(b_lo + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        fence_async_smem();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+    auto stage_ptr = [&](int s) { return smem + s * kStageBytes; };
+
+    if (warp == 1) {
+        if (lane == 0 && kblocks > 0) {
+            // UMMA N is limited to 256: features 0..255 in one instruction, the ones/zero rows 256..271 (bias
+            // gradient column) in a second N = 16 instruction on the same A operand
+            constexpr uint32_t idesc = umma_idesc_tf32(128, 256);
+            constexpr uint32_t idesc_b = umma_idesc_tf32(128, kDwNB - 256);
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % kGemmStages;
+                mbar_wait_bounded(&full_bar[s], (kb / kGemmStages) & 1);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(stage_ptr(s));
+                const uint32_t a_lo = a_hi + kABytes;
+                const uint32_t b_hi = a_hi + 2 * kABytes;
+                const uint32_t b_lo = b_hi + kBBytes;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t koff = k * 32;
+                    const uint32_t acc = (kb | k) ? 1u : 0u;
+                    const uint64_t da = umma_desc_k128(a_hi + koff), dbd = umma_desc_k128(b_hi + koff);
+                    const uint64_t dones = umma_desc_k128(b_hi + 256 * 128 + koff);
+                    umma_tf32(tmem_base, da, dbd, idesc, acc);
+                    umma_tf32(tmem_base + 256, da, dones, idesc_b, acc);
+                    if (p.split == 3) {
+                        const uint64_t dal = umma_desc_k128(a_lo + koff);
+                        umma_tf32(tmem_base, dal, dbd, idesc, 1u);
+                        umma_tf32(tmem_base + 256, dal, dones, idesc_b, 1u);
+                        umma_tf32(tmem_base, da, umma_desc_k128(b_lo + koff), idesc, 1u);
+                    }
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(&acc_bar);
+        }
+    } else if (warp >= 2) {
+        // ---- transposing producers: 256 threads, 12 (feature, row-quad) items each per k-block ----
+        const int t = threadIdx.x - 64;
+        auto load_items = [&](int kb, float (&v)[12][4]) {
+            const int rb = r_begin + kb * 32;
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                const int e = t + 256 * j;
+                const int rq = e / 384, f = e % 384;
+                const bool is_a = f < 128;
+                const int feat = is_a ? n0 + f : f - 128;
+                const bool fok = is_a ? (feat < p.N) : true;
+                const float *src = is_a ? p.g + feat : p.x + feat;
+                const int ld = is_a ? p.N : kKx;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = rb + rq * 4 + i;
+                    v[j][i] = (fok && r < r_end) ? __ldg(src + static_cast<size_t>(r) * ld) : 0.f;
+                }
+            }
+        };
+        float cur[12][4], nxt[12][4];
+        if (kblocks > 0) load_items(0, cur);
+        for (int kb = 0; kb < kblocks; ++kb) {
+            const int s = kb % kGemmStages;
+            if (kb + 1 < kblocks) load_items(kb + 1, nxt);
+            mbar_wait_bounded(&empty_bar[s], ((kb / kGemmStages) & 1) ^ 1);
+            unsigned char *a_hi = stage_ptr(s);
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                const int e = t + 256 * j;
+                const int rq = e / 384, f = e % 384;
+                const bool is_a = f < 128;
+                const int row = is_a ? f : f - 128;
+                unsigned char *hi_base = is_a ? a_hi : a_hi + 2 * kABytes;
+                unsigned char *lo_base = is_a ? a_hi + kABytes : a_hi + 2 * kABytes + kBBytes;
+                const uint32_t off = row * 128 + ((rq ^ (row & 7)) << 4);
+                float4 hi, lo;
+                hi.x = tf32_hi(cur[j][0]); lo.x = cur[j][0] - hi.x;
+                hi.y = tf32_hi(cur[j][1]); lo.y = cur[j][1] - hi.y;
+                hi.z = tf32_hi(cur[j][2]); lo.z = cur[j][2] - hi.z;
+                hi.w = tf32_hi(cur[j][3]); lo.w = cur[j][3] - hi.w;
+                *reinterpret_cast<float4 *>(hi_base + off) = hi;
+                *reinterpret_cast<float4 *>(lo_base + off) = lo;
+            }
+            fence_async_smem();
+            mbar_arrive(&full_bar[s]);
+#pragma unroll
+            for (int j = 0; j < 12; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cur[j][i] = nxt[j][i];
+        }
+        // ---- epilogue (warps 2..5): TMEM lane = feature n, columns = k (0..255) and the bias column 256 ----
+        if (warp < 6 && kblocks > 0) {
+            mbar_wait_bounded(&acc_bar, 0);
+            tc_fence_after();
+            const int q = warp & 3;
+            const int n = n0 + q * 32 + lane;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 288; c0 += 32) {
+                float acc[32];
+                tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, acc);
+                if (n < p.N) {
+                    if (c0 < 256) {
+                        float *dst = p.dw + static_cast<size_t>(n) * kKx + c0;
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4) {
+                            const float r4[4] = {acc[c], acc[c + 1], acc[c + 2], acc[c + 3]};
+                            VecIO<float, 4>::red_add(dst + c, r4);
+                        }
+                    } else if (p.db) {
+                        const float r1[1] = {acc[0]};
+                        VecIO<float, 1>::red_add(p.db + n, r1);
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+constexpr int linear_dw_smem_bytes() { return kGemmStages * (2 * 128 * 128 + 2 * kDwNB * 128) + 1024; }
+
 template <int NT, int NH>
 constexpr int linear_smem_bytes()
 {
@@ -523,7 +721,7 @@ __global__ void split_tf32_kernel(const float *__restrict__ w, float *__restrict
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         const float x = transpose ? w[(i % cols) * rows + i / cols] : w[i];
-        const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+        const float h = tf32_hi(x);
         hi[i] = h;
         lo[i] = x - h;
     }

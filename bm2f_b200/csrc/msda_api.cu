@@ -621,6 +621,44 @@ int bm2f_linear_forward(const void *x, const void *weight, const void *bias, voi
     return linear_common(x, weight, bias, y, workspace, rows, out_features, in_features, 0, split, stream);
 }
 
+int bm2f_linear_backward_weight(const void *grad_y, const void *x, void *grad_weight, void *grad_bias, int rows,
+                                int out_features, int in_features, int split, void *stream)
+{
+    if (!grad_y || !x || !grad_weight) return fail(BM2F_ERR_INVALID, "null pointer");
+    if (rows <= 0 || out_features <= 0) return fail(BM2F_ERR_INVALID, "rows / out_features must be positive");
+    if (in_features != 256)
+        return fail(BM2F_ERR_UNSUPPORTED, "weight-gradient GEMM is built for in_features = 256 (got %d)", in_features);
+    if (out_features > 4096) return fail(BM2F_ERR_UNSUPPORTED, "out_features too large");
+    if (split != 1 && split != 3) return fail(BM2F_ERR_INVALID, "split must be 3 (tf32x3) or 1 (single TF32 pass)");
+    int sms = 0, cc = 0;
+    int rc = device_info(&sms, &cc);
+    if (rc) return rc;
+    if (cc < 10) return fail(BM2F_ERR_CUDA, "this library contains sm_100a code only; device has cc %d.x", cc);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(grad_weight, 0, static_cast<size_t>(out_features) * in_features * 4, st);
+    if (e == cudaSuccess && grad_bias) e = cudaMemsetAsync(grad_bias, 0, static_cast<size_t>(out_features) * 4, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(grad_weight / grad_bias)");
+    const int n_tiles = (out_features + 127) / 128;
+    int chunks = sms / n_tiles;
+    if (chunks < 1) chunks = 1;
+    int rows_per_chunk = ((rows + chunks - 1) / chunks + 31) / 32 * 32;
+    chunks = (rows + rows_per_chunk - 1) / rows_per_chunk;
+    LinearDwParams p{static_cast<const float *>(grad_y), static_cast<const float *>(x), static_cast<float *>(grad_weight),
+                     static_cast<float *>(grad_bias), rows, out_features, rows_per_chunk, split};
+    constexpr int smem = linear_dw_smem_bytes();
+    static bool attr_set = false;
+    if (!attr_set) {
+        e = cudaFuncSetAttribute(linear_dw_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dW smem)");
+        attr_set = true;
+    }
+    linear_dw_tf32x3_kernel<<<dim3(n_tiles, chunks), kDwThreads, smem, st>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "launch linear_dw_tf32x3_kernel");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return BM2F_OK;
+}
+
 int bm2f_linear_backward_input(const void *grad_y, const void *weight, void *grad_x, void *workspace, int rows,
                                int out_features, int in_features, int split, void *stream)
 {

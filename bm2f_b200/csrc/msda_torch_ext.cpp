@@ -236,6 +236,29 @@ bool linear_tf32x3_supported(int64_t in_features, int64_t out_features)
     return in_features == 256 && (out_features == 256 || out_features == 288 || out_features == 192 || out_features == 96);
 }
 
+// (grad_weight, grad_bias) = (grad_y^T x, column sums of grad_y) on the tensor cores
+std::vector<at::Tensor> linear_tf32x3_backward_weight(const at::Tensor &grad_y, const at::Tensor &x, int64_t split,
+                                                      bool with_bias)
+{
+    TORCH_CHECK(grad_y.is_cuda() && x.is_cuda(), "linear_tf32x3_backward_weight: CUDA tensors only");
+    TORCH_CHECK(grad_y.scalar_type() == at::kFloat && x.scalar_type() == at::kFloat, "float32 only");
+    TORCH_CHECK(x.size(-1) == 256, "in_features must be 256");
+    const c10::cuda::CUDAGuard guard(x.device());
+    auto g = grad_y.contiguous();
+    auto xc = x.contiguous();
+    const int64_t rows = xc.numel() / 256;
+    const int64_t n = g.size(-1);
+    TORCH_CHECK(g.numel() == rows * n, "grad_y / x row count mismatch");
+    auto gw = at::empty({n, 256}, xc.options());
+    auto gb = with_bias ? at::empty({n}, xc.options()) : at::Tensor();
+    const int rc = bm2f_linear_backward_weight(g.data_ptr(), xc.data_ptr(), gw.data_ptr(),
+                                               with_bias ? gb.data_ptr() : nullptr, static_cast<int>(rows),
+                                               static_cast<int>(n), 256, static_cast<int>(split),
+                                               at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == BM2F_OK, "linear_tf32x3_backward_weight: ", bm2f_msda_last_error());
+    return {gw, gb};
+}
+
 // grad_x = grad_y @ weight on the tensor cores (reduction over out_features, output width in_features = 256)
 at::Tensor linear_tf32x3_backward_input(const at::Tensor &grad_y, const at::Tensor &weight, int64_t split)
 {
@@ -302,6 +325,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("ms_deform_attn_fused_backward", &ms_deform_attn_fused_backward, "backward of the fused op");
     m.def("linear_tf32x3", &linear_tf32x3, "tcgen05 projection GEMM (y = x W^T + b), split=3: tf32x3, 1: tf32");
     m.def("linear_tf32x3_supported", &linear_tf32x3_supported);
+    m.def("linear_tf32x3_backward_weight", &linear_tf32x3_backward_weight, "grad_W = grad_y^T x, grad_b = sum grad_y (tcgen05)");
     m.def("linear_tf32x3_backward_input", &linear_tf32x3_backward_input, "grad_x = grad_y @ weight (tcgen05)");
     m.def("abi_version", []() { return bm2f_msda_abi_version(); });
     m.def("build_info", []() { return std::string(bm2f_msda_build_info()); });

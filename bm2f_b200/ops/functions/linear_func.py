@@ -4,7 +4,8 @@
 (ops/modules/ms_deform_attn.py:59-62) with the forward GEMM done by the tcgen05 kernel in
 csrc/linear_tf32x3.cuh (three-term TF32 split, fp32 accumulation in TMEM: fp32-grade results).
 grad_x = g W runs on the same kernel (reduction over out_features); grad_W = g^T x and grad_b = sum g
-reduce over the ~10^5 rows and are left to cuBLAS through torch in this round."""
+(reductions over the ~10^5 rows) run on a transposing split-K tcgen05 kernel.  `USE_TCGEN05_DW = False`
+sends the weight gradient back to cuBLAS through torch."""
 from __future__ import annotations
 
 import torch
@@ -14,6 +15,7 @@ from torch.autograd.function import once_differentiable
 from ... import load_extension
 
 MSDA = load_extension()
+USE_TCGEN05_DW = True
 
 
 class LinearTF32x3Function(Function):
@@ -31,8 +33,16 @@ class LinearTF32x3Function(Function):
         g2 = g.reshape(-1, g.shape[-1])
         gx = MSDA.linear_tf32x3_backward_input(g2.contiguous(), weight, ctx.split).view_as(x) \
             if ctx.needs_input_grad[0] else None
-        gw = g2.t() @ x.reshape(-1, x.shape[-1]) if ctx.needs_input_grad[1] else None
-        gb = g2.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        gw = gb = None
+        want_b = ctx.has_bias and ctx.needs_input_grad[2]
+        if ctx.needs_input_grad[1] and USE_TCGEN05_DW:
+            gw, gb_ = MSDA.linear_tf32x3_backward_weight(g2.contiguous(), x.reshape(-1, x.shape[-1]), ctx.split, want_b)
+            gb = gb_ if want_b else None
+        else:
+            if ctx.needs_input_grad[1]:
+                gw = g2.t() @ x.reshape(-1, x.shape[-1])
+            if want_b:
+                gb = g2.sum(0)
         return gx, gw, gb, None
 
 

@@ -175,6 +175,10 @@ int bm2f_linear_forward(const void *x, const void *weight, const void *bias, voi
                         int rows, int out_features, int in_features, int split, void *stream);
 int bm2f_linear_backward_input(const void *grad_y, const void *weight, void *grad_x, void *workspace,
                                int rows, int out_features, int in_features, int split, void *stream);
+/* grad_weight[out, 256] = grad_y^T x and grad_bias[out] = column sums of grad_y (may be NULL); both are
+ * zeroed and then accumulated with red.global.add by row-chunk CTAs (summation order is free). */
+int bm2f_linear_backward_weight(const void *grad_y, const void *x, void *grad_weight, void *grad_bias,
+                                int rows, int out_features, int in_features, int split, void *stream);
 
 /*
  * Host-buffer convenience used for end-to-end measurement and by non-torch callers:

@@ -84,3 +84,20 @@ def test_linear_backward_input_matches_fp64(msda, out_features):
     gx = msda.linear_tf32x3_backward_input(g, w, 3)
     assert gx.shape == (1000, 256)
     assert (gx.double() - ref).abs().max().item() / ref.abs().max().item() <= 5e-6
+
+
+@pytest.mark.parametrize("out_features", [256, 192, 96, 288])
+@pytest.mark.parametrize("rows", [5376, 1000, 31, 128 * 148 + 77])
+def test_linear_backward_weight_matches_fp64(msda, out_features, rows):
+    torch.manual_seed(out_features + rows)
+    dev = torch.device("cuda:0")
+    g = torch.randn(rows, out_features, device=dev)
+    x = torch.randn(rows, 256, device=dev)
+    ref_w = g.double().t() @ x.double()
+    ref_b = g.double().sum(0)
+    gw, gb = msda.linear_tf32x3_backward_weight(g, x, 3, True)
+    assert gw.shape == (out_features, 256) and gb.shape == (out_features,)
+    assert (gw.double() - ref_w).abs().max().item() / ref_w.abs().max().item() <= 1e-5
+    assert (gb.double() - ref_b).abs().max().item() / ref_b.abs().max().item() <= 1e-5
+    gw2, gb2 = msda.linear_tf32x3_backward_weight(g, x, 3, False)
+    assert not gb2.defined() if hasattr(gb2, "defined") else gb2 is None or gb2.numel() == 0

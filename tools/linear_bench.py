@@ -32,3 +32,12 @@ for n in (256, 288, 192, 96):
     print(f"N={n:3d} rows={rows}: cuBLAS fp32 {t_fp32:.3f} ms (err {e_fp32:.1e}) | cuBLAS tf32 {t_tf32:.3f} ms (err {e_tf32:.1e}) | "
           f"tcgen05 tf32x3 persistent {t3:.3f} ms (err {e3:.1e}, {gb/t3*1e3:.0f} GB/s, {3*fl/t3*1e3:.0f} TF/s tf32) | "
           f"one-tile {t13:.3f} ms | tf32x1 persistent {t1:.3f} ms (err {e1:.1e}, {gb/t1*1e3:.0f} GB/s)")
+# ---- weight gradient
+for n in (256, 192, 96):
+    g = torch.randn(rows, n, device=dev)
+    ref = g.double().t() @ x.double()
+    t_fp32 = t(lambda: (g.t() @ x, g.sum(0)))
+    t_dw = t(lambda: MSDA.linear_tf32x3_backward_weight(g, x, 3, True))
+    e = ((MSDA.linear_tf32x3_backward_weight(g, x, 3, True)[0].double() - ref).abs().max() / ref.abs().max()).item()
+    e32 = (((g.t() @ x).double() - ref).abs().max() / ref.abs().max()).item()
+    print(f"dW N={n:3d} rows={rows}: cuBLAS fp32 (+sum) {t_fp32:.3f} ms (err {e32:.1e}) | tcgen05 tf32x3 {t_dw:.3f} ms (err {e:.1e}, {rows*(256+n)*4/1e9/t_dw*1e3:.0f} GB/s)")
