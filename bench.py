@@ -365,6 +365,16 @@ def run_ours(args, wl):
             red_gbs = W.gather_bytes(wl.S, "fwd", wl.dtype) * nb / (kms["bwd"] * 1e-3) / 1e9
             gather["bwd"]["red_line_traffic_GBs"] = red_gbs
             gather["bwd"]["frac_of_measured_red_peak"] = red_gbs / peaks_g["red_v4_l2_resident"]
+        # the HBM roofline is not the binding one for this op (gather/scatter demand is 15x the compulsory HBM
+        # bytes): name the limit that binds the dominant kernel and the fraction reached
+        if dom == "bwd" and "bwd" in gather:
+            roofline["binding_limit"] = ("L2 red.global.add.v4.f32 line rate, measured %.0f GB/s "
+                                         "(profiles/r01_microbench.txt)" % peaks_g["red_v4_l2_resident"])
+            roofline["frac_of_binding_limit"] = gather["bwd"]["frac_of_measured_red_peak"]
+        elif "fwd" in gather:
+            roofline["binding_limit"] = ("L1 gather line rate of the 8 lanes x 16 B access shape, measured %.0f GB/s "
+                                         "(profiles/r01_microbench.txt)" % peaks_g["l1_resident_8x16B"])
+            roofline["frac_of_binding_limit"] = gather["fwd"]["frac_of_measured_l1_gather_peak"]
 
     # ---- reference CUDA op, same inputs, same timing (only when oracle/_ref was built) ----------------
     ref_cuda = None

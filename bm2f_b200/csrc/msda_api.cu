@@ -260,7 +260,7 @@ int run_fast(bool bwd, FastParams p, const Dims &d, int dtype, const bm2f_msda_t
         auto jobs = [&](int r) {
             return static_cast<long long>(d.N) * d.M * ((d.Lq + c.sw * r - 1) / (c.sw * r));
         };
-        while (rows > 4 && jobs(rows) < 16ll * grid_max) rows >>= 1;
+        while (rows > 1 && jobs(rows) < 16ll * grid_max) rows >>= 1;   // small problems: more, shorter jobs
     }
     p.rows = rows;
     p.order = t.order;

@@ -41,7 +41,7 @@ struct FastParams {
 };
 
 struct QLevel {
-    int qstart, Hq, Wq, nstrips, nchunks, job_base;
+    int qstart, qend, Hq, Wq, nstrips, nchunks, job_base;   // queries [qstart, qend) walked as an Hq x Wq grid
 };
 
 template <int L_>
@@ -72,19 +72,30 @@ __device__ __forceinline__ void build_tabs(Tabs<L_> &t, const FastParams &p)
         int q0 = 0;
         for (int l = 0; l < L_; ++l) {
             QLevel &q = t.ql[l];
+            const int npix = t.H[l] * t.W[l];
             q.qstart = q0;
-            q.Hq = t.H[l];
-            q.Wq = t.W[l];
+            q.qend = q0 + npix;
+            // column strips only pay off when they tile the level width without much waste; otherwise this
+            // level is walked in raster order, SW consecutive pixels per stage (e.g. W = 20 or 40 with SW = 32)
+            const int padded = (t.W[l] + SW - 1) / SW * SW;
+            if ((padded - t.W[l]) * 8 <= t.W[l]) {
+                q.Hq = t.H[l];
+                q.Wq = t.W[l];
+            } else {
+                q.Wq = SW;
+                q.Hq = (npix + SW - 1) / SW;
+            }
             q.nstrips = (q.Wq + SW - 1) / SW;
             q.nchunks = (q.Hq + p.rows - 1) / p.rows;
             q.job_base = jobs;
             jobs += q.nstrips * q.nchunks;
-            q0 += q.Hq * q.Wq;
+            q0 += npix;
         }
         t.nql = L_;
     } else {
         QLevel &q = t.ql[0];
         q.qstart = 0;
+        q.qend = p.Lq;
         q.Wq = SW;
         q.Hq = (p.Lq + SW - 1) / SW;
         q.nstrips = 1;
@@ -120,7 +131,7 @@ __device__ __forceinline__ void for_each_stage(const Tabs<L_> &t, const FastPara
         const int nq_row = min(SW, ql.Wq - x0);
         for (int y = chunk * p.rows; y < y_end; ++y, ++s) {
             const int q_base = ql.qstart + y * ql.Wq + x0;
-            f(s, b, m, q_base, min(nq_row, p.Lq - q_base));
+            f(s, b, m, q_base, min(nq_row, ql.qend - q_base));
         }
     }
 }
