@@ -23,7 +23,7 @@
 
 namespace bm2f {
 
-constexpr int kGemmKMax = 288;      // reduction length is a runtime multiple of 32 (256 forward, 96..288 for grad_x)
+constexpr int kGemmKMax = 4096;     // reduction length is a runtime multiple of 32 (256 for the projections, 1024 in the FFN)
 constexpr int kGemmBlockM = 128;
 constexpr int kGemmBlockK = 32;     // floats per k-block = 128 bytes = one SWIZZLE_128B row
 constexpr int kGemmStages = 2;
@@ -33,7 +33,10 @@ struct LinearParams {
     const float *x;      // (M, K)
     const float *bias;   // (N) or nullptr
     float *y;            // (M, N)
-    int M, N, K;
+    int M, N, K;        // N = total output width (row stride of y and rows of the weight)
+    int slices;         // persistent kernel: N / NT column slices, tile = (row tile, slice)
+    int relu;           // epilogue: y = max(y, 0)
+    const float *out_mask;  // optional (M, N): epilogue zeroes y where out_mask <= 0 (ReLU backward of the previous layer)
     int split;           // 3 = tf32x3 (fp32-grade), 1 = single TF32 pass
 };
 
@@ -343,7 +346,22 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kKBlocks = p.K / kGemmBlockK;
-    const int num_tiles = (p.M + kGemmBlockM - 1) / kGemmBlockM;
+    const int slices = p.slices;
+    const int num_tiles = ((p.M + kGemmBlockM - 1) / kGemmBlockM) * slices;   // tile = row_tile * slices + slice
+    // (row tile, slice) of a tile index advance incrementally: an integer division per tile / k-block in the
+    // single-threaded TMA and MMA roles costs ~200 cycles of latency each and made this kernel 1.7x slower (measured)
+    const int step_rt = gridDim.x / slices, step_sl = gridDim.x % slices;
+    struct TileIter {
+        int tile, rt, sl;
+    };
+    auto first_tile = [&]() { return TileIter{static_cast<int>(blockIdx.x), static_cast<int>(blockIdx.x) / slices,
+                                              static_cast<int>(blockIdx.x) % slices}; };
+    auto next_tile = [&](TileIter &t) {
+        t.tile += gridDim.x;
+        t.rt += step_rt;
+        t.sl += step_sl;
+        if (t.sl >= slices) { t.sl -= slices; ++t.rt; }
+    };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kGemmStages; ++s) {
@@ -369,14 +387,15 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
     if (warp == 0) {
         if (lane == 0) {                                   // ---- TMA producer (W_hi, W_lo) ----
             int g = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (TileIter ti = first_tile(); ti.tile < num_tiles; next_tile(ti)) {
+                const int wrow = ti.sl * NT;
                 for (int kb = 0; kb < kKBlocks; ++kb, ++g) {
                     const int s = g % kGemmStages;
                     mbar_wait_bounded(&empty_bar[s], ((g / kGemmStages) & 1) ^ 1);
                     mbar_arrive_expect_tx(&full_bar[s], p.split == 3 ? 2 * kWBytes : kWBytes);
                     unsigned char *w_hi = stage_ptr(s) + 2 * kXBytes;
-                    tma_load_2d(w_hi, &tm_whi, kb * kGemmBlockK, 0, &full_bar[s]);
-                    if (p.split == 3) tma_load_2d(w_hi + kWBytes, &tm_wlo, kb * kGemmBlockK, 0, &full_bar[s]);
+                    tma_load_2d(w_hi, &tm_whi, kb * kGemmBlockK, wrow, &full_bar[s]);
+                    if (p.split == 3) tma_load_2d(w_hi + kWBytes, &tm_wlo, kb * kGemmBlockK, wrow, &full_bar[s]);
                 }
             }
         }
@@ -417,51 +436,64 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
         // ---- X producers (warps 2..5): global -> registers -> hi/lo -> swizzled shared memory ----
         const int t = threadIdx.x - 64;
         const int c16 = t & 7, rsub = t >> 3;
-        auto load_x = [&](int tile, int kb, float4 (&v)[8]) {
+        auto load_x = [&](int rt, int kb, float4 (&v)[8]) {
+            const int rbase = rt * kGemmBlockM + rsub;
+            const size_t cbase = static_cast<size_t>(kb) * kGemmBlockK;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int gr = tile * kGemmBlockM + rsub + 16 * j;
-                v[j] = gr < p.M ? __ldg(reinterpret_cast<const float4 *>(p.x + static_cast<size_t>(gr) * p.K +
-                                                                           kb * kGemmBlockK) + c16)
+                const int gr = rbase + 16 * j;
+                v[j] = gr < p.M ? __ldg(reinterpret_cast<const float4 *>(p.x + static_cast<size_t>(gr) * p.K + cbase) + c16)
                                 : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
-        float4 cur[8], nxt[8];
-        int tile = blockIdx.x, kb = 0, g = 0;
-        if (tile < num_tiles) load_x(tile, 0, cur);
-        while (tile < num_tiles) {
-            int ntile = tile, nkb = kb + 1;
-            if (nkb == kKBlocks) { nkb = 0; ntile += gridDim.x; }
-            if (ntile < num_tiles) load_x(ntile, nkb, nxt);
-            const int s = g % kGemmStages;
-            mbar_wait_bounded(&empty_bar[s], ((g / kGemmStages) & 1) ^ 1);
-            unsigned char *x_hi = stage_ptr(s);
-            unsigned char *x_lo = x_hi + kXBytes;
+        // kXDepth k-blocks of X are in flight per thread (registers): with one block in flight the kernel is bound by
+        // global-load latency (16 KB per SM outstanding), measured 2x slower on the 1024-wide FFN shapes
+        constexpr int kXDepth = 3;
+        float4 buf[kXDepth][8];
+        TileIter lt = first_tile(), ct = first_tile();   // load iterator (kXDepth - 1 k-blocks ahead), convert iterator
+        int lkb = 0, kb = 0, g = 0;
+        auto advance = [&](TileIter &tl, int &k) {
+            if (++k == kKBlocks) { k = 0; next_tile(tl); }
+        };
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int r = rsub + 16 * j;
-                const uint32_t off = r * 128 + ((c16 ^ (r & 7)) << 4);
-                float4 hi, lo;
-                hi.x = tf32_hi(cur[j].x); lo.x = cur[j].x - hi.x;
-                hi.y = tf32_hi(cur[j].y); lo.y = cur[j].y - hi.y;
-                hi.z = tf32_hi(cur[j].z); lo.z = cur[j].z - hi.z;
-                hi.w = tf32_hi(cur[j].w); lo.w = cur[j].w - hi.w;
-                *reinterpret_cast<float4 *>(x_hi + off) = hi;
-                *reinterpret_cast<float4 *>(x_lo + off) = lo;
+        for (int d = 0; d < kXDepth - 1; ++d) {
+            if (lt.tile < num_tiles) load_x(lt.rt, lkb, buf[d]);
+            advance(lt, lkb);
+        }
+        while (ct.tile < num_tiles) {
+#pragma unroll
+            for (int u = 0; u < kXDepth; ++u) {
+                if (ct.tile >= num_tiles) break;
+                if (lt.tile < num_tiles) load_x(lt.rt, lkb, buf[(u + kXDepth - 1) % kXDepth]);
+                advance(lt, lkb);
+                const int s = g % kGemmStages;
+                mbar_wait_bounded(&empty_bar[s], ((g / kGemmStages) & 1) ^ 1);
+                unsigned char *x_hi = stage_ptr(s);
+                unsigned char *x_lo = x_hi + kXBytes;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int r = rsub + 16 * j;
+                    const uint32_t off = r * 128 + ((c16 ^ (r & 7)) << 4);
+                    const float4 v = buf[u][j];
+                    float4 hi, lo;
+                    hi.x = tf32_hi(v.x); lo.x = v.x - hi.x;
+                    hi.y = tf32_hi(v.y); lo.y = v.y - hi.y;
+                    hi.z = tf32_hi(v.z); lo.z = v.z - hi.z;
+                    hi.w = tf32_hi(v.w); lo.w = v.w - hi.w;
+                    *reinterpret_cast<float4 *>(x_hi + off) = hi;
+                    *reinterpret_cast<float4 *>(x_lo + off) = lo;
+                }
+                fence_async_smem();
+                mbar_arrive(&full_bar[s]);
+                advance(ct, kb);
+                ++g;
             }
-            fence_async_smem();
-            mbar_arrive(&full_bar[s]);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
-            tile = ntile; kb = nkb; ++g;
         }
     } else {
         // ---- epilogue (warps 6..9) ----
-        const int t = threadIdx.x - 192;
         const int q = warp & 3;
-        const int r = q * 32 + lane;
         int i = 0, chunk = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
+        for (TileIter ti = first_tile(); ti.tile < num_tiles; next_tile(ti), ++i) {
             const int b = i & 1;
             mbar_wait_bounded(&acc_full[b], (i >> 1) & 1);
             tc_fence_after();
@@ -473,32 +505,42 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
                     tc_fence_before();
                     mbar_arrive(&acc_empty[b]);
                 }
-                unsigned char *stg = staging + (chunk & 1) * kXBytes;
+                // every epilogue warp owns a private pair of 32-row x 128-byte staging tiles and issues its own
+                // TMA store (box 32 x 32): no CTA-level barrier in the epilogue, four independent store pipelines
+                unsigned char *stg = staging + q * (2 * 4096) + (chunk & 1) * 4096;
+                const int grow = ti.rt * kGemmBlockM + q * 32 + lane;     // this thread's output row
                 if (chunk >= 2) {
-                    if (t == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
                 }
 #pragma unroll
                 for (int c = 0; c < 32; c += 4) {
                     float4 o = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
                     if (p.bias) {
-                        const float4 bb = __ldg(reinterpret_cast<const float4 *>(p.bias + c0 + c));
+                        const float4 bb = __ldg(reinterpret_cast<const float4 *>(p.bias + ti.sl * NT + c0 + c));
                         o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
                     }
-                    *reinterpret_cast<float4 *>(stg + r * 128 + ((((c >> 2) ^ (r & 7))) << 4)) = o;
+                    if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    if (p.out_mask && grow < p.M) {
+                        const float4 mk = __ldg(reinterpret_cast<const float4 *>(
+                            p.out_mask + static_cast<size_t>(grow) * p.N + ti.sl * NT + c0 + c));
+                        o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f;
+                        o.z = mk.z > 0.f ? o.z : 0.f; o.w = mk.w > 0.f ? o.w : 0.f;
+                    }
+                    *reinterpret_cast<float4 *>(stg + lane * 128 + ((((c >> 2) ^ (lane & 7))) << 4)) = o;
                 }
                 fence_async_smem();
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (t == 0) {
+                __syncwarp();
+                if (lane == 0) {
                     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                                      reinterpret_cast<uint64_t>(&tm_y)),
-                                 "r"(smem_u32(stg)), "r"(c0), "r"(tile * kGemmBlockM)
+                                 "r"(smem_u32(stg)), "r"(ti.sl * NT + c0), "r"(ti.rt * kGemmBlockM + q * 32)
                                  : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
         }
-        if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -530,10 +572,10 @@ constexpr int kDwNB = 272;             // 256 features + ones row, padded to a m
 
 struct LinearDwParams {
     const float *g;      // (M, N)  grad_y
-    const float *x;      // (M, 256)
-    float *dw;           // (N, 256), accumulated into
+    const float *x;      // (M, ldx); blockIdx.z selects a 256-feature slice of it
+    float *dw;           // (N, ldx), accumulated into
     float *db;           // (N) or nullptr, accumulated into
-    int M, N;
+    int M, N, ldx;
     int rows_per_chunk;  // multiple of 32
     int split;
 };
@@ -543,7 +585,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) linear_dw_tf32x3_kernel(const L
     constexpr int kABytes = 128 * 128;                 // 128 features x 128 B
     constexpr int kBBytes = kDwNB * 128;               // 272 features x 128 B
     constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
-    constexpr int kKx = 256;
+    const int k0 = blockIdx.z * 256;                   // feature slice of x handled by this CTA
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t full_bar[kGemmStages], empty_bar[kGemmStages], acc_bar;
@@ -619,27 +661,31 @@ __global__ void __launch_bounds__(kDwThreads, 1) linear_dw_tf32x3_kernel(const L
             umma_commit(&acc_bar);
         }
     } else if (warp >= 2) {
-        // ---- transposing producers: 256 threads, 12 (feature, row-quad) items each per k-block ----
+        // ---- transposing producers: 256 threads; a thread owns 3 features (one of G, two of X) x 4 row quads ----
+        // item (a, b): feature slot a in {A: n0 + fl, B: k0 + fl, B: k0 + 128 + fl}, rows 4*(qh + 2b) .. +3 of the k-block.
+        // lane <-> consecutive features: global loads are 128-byte coalesced, the swizzled 16-byte stores of a
+        // quarter-warp hit 8 different bank groups.
         const int t = threadIdx.x - 64;
-        auto load_items = [&](int kb, float (&v)[12][4]) {
-            const int rb = r_begin + kb * 32;
+        const int fl = t & 127, qh = t >> 7;
+        const bool a_ok = n0 + fl < p.N;
+        const float *src[3] = {p.g + n0 + fl, p.x + k0 + fl, p.x + k0 + 128 + fl};
+        const int ld[3] = {p.N, p.ldx, p.ldx};
+        const uint32_t tile_off[3] = {static_cast<uint32_t>(fl) * 128u, 2u * kABytes + static_cast<uint32_t>(fl) * 128u,
+                                      2u * kABytes + static_cast<uint32_t>(fl + 128) * 128u};
+        const uint32_t lo_off[3] = {kABytes, kBBytes, kBBytes};
+        auto load_items = [&](int kb, float (&v)[3][4][4]) {
+            const int rb = r_begin + kb * 32 + qh * 4;
 #pragma unroll
-            for (int j = 0; j < 12; ++j) {
-                const int e = t + 256 * j;
-                const int rq = e / 384, f = e % 384;
-                const bool is_a = f < 128;
-                const int feat = is_a ? n0 + f : f - 128;
-                const bool fok = is_a ? (feat < p.N) : true;
-                const float *src = is_a ? p.g + feat : p.x + feat;
-                const int ld = is_a ? p.N : kKx;
+            for (int a = 0; a < 3; ++a)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int r = rb + rq * 4 + i;
-                    v[j][i] = (fok && r < r_end) ? __ldg(src + static_cast<size_t>(r) * ld) : 0.f;
-                }
-            }
+                for (int b = 0; b < 4; ++b)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = rb + b * 8 + i;
+                        v[a][b][i] = ((a > 0 || a_ok) && r < r_end) ? __ldg(src[a] + static_cast<size_t>(r) * ld[a]) : 0.f;
+                    }
         };
-        float cur[12][4], nxt[12][4];
+        float cur[3][4][4], nxt[3][4][4];
         if (kblocks > 0) load_items(0, cur);
         for (int kb = 0; kb < kblocks; ++kb) {
             const int s = kb % kGemmStages;
@@ -647,28 +693,27 @@ __global__ void __launch_bounds__(kDwThreads, 1) linear_dw_tf32x3_kernel(const L
             mbar_wait_bounded(&empty_bar[s], ((kb / kGemmStages) & 1) ^ 1);
             unsigned char *a_hi = stage_ptr(s);
 #pragma unroll
-            for (int j = 0; j < 12; ++j) {
-                const int e = t + 256 * j;
-                const int rq = e / 384, f = e % 384;
-                const bool is_a = f < 128;
-                const int row = is_a ? f : f - 128;
-                unsigned char *hi_base = is_a ? a_hi : a_hi + 2 * kABytes;
-                unsigned char *lo_base = is_a ? a_hi + kABytes : a_hi + 2 * kABytes + kBBytes;
-                const uint32_t off = row * 128 + ((rq ^ (row & 7)) << 4);
-                float4 hi, lo;
-                hi.x = tf32_hi(cur[j][0]); lo.x = cur[j][0] - hi.x;
-                hi.y = tf32_hi(cur[j][1]); lo.y = cur[j][1] - hi.y;
-                hi.z = tf32_hi(cur[j][2]); lo.z = cur[j][2] - hi.z;
-                hi.w = tf32_hi(cur[j][3]); lo.w = cur[j][3] - hi.w;
-                *reinterpret_cast<float4 *>(hi_base + off) = hi;
-                *reinterpret_cast<float4 *>(lo_base + off) = lo;
-            }
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int rq = qh + 2 * b;                                    // 16-byte chunk = row quad
+                    unsigned char *hi_p = a_hi + tile_off[a] + ((rq ^ (fl & 7)) << 4);
+                    float4 hi, lo;
+                    hi.x = tf32_hi(cur[a][b][0]); lo.x = cur[a][b][0] - hi.x;
+                    hi.y = tf32_hi(cur[a][b][1]); lo.y = cur[a][b][1] - hi.y;
+                    hi.z = tf32_hi(cur[a][b][2]); lo.z = cur[a][b][2] - hi.z;
+                    hi.w = tf32_hi(cur[a][b][3]); lo.w = cur[a][b][3] - hi.w;
+                    *reinterpret_cast<float4 *>(hi_p) = hi;
+                    *reinterpret_cast<float4 *>(hi_p + lo_off[a]) = lo;
+                }
             fence_async_smem();
             mbar_arrive(&full_bar[s]);
 #pragma unroll
-            for (int j = 0; j < 12; ++j)
+            for (int a = 0; a < 3; ++a)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) cur[j][i] = nxt[j][i];
+                for (int b = 0; b < 4; ++b)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) cur[a][b][i] = nxt[a][b][i];
         }
         // ---- epilogue (warps 2..5): TMEM lane = feature n, columns = k (0..255) and the bias column 256 ----
         if (warp < 6 && kblocks > 0) {
@@ -682,13 +727,13 @@ __global__ void __launch_bounds__(kDwThreads, 1) linear_dw_tf32x3_kernel(const L
                 tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, acc);
                 if (n < p.N) {
                     if (c0 < 256) {
-                        float *dst = p.dw + static_cast<size_t>(n) * kKx + c0;
+                        float *dst = p.dw + static_cast<size_t>(n) * p.ldx + k0 + c0;
 #pragma unroll
                         for (int c = 0; c < 32; c += 4) {
                             const float r4[4] = {acc[c], acc[c + 1], acc[c + 2], acc[c + 3]};
                             VecIO<float, 4>::red_add(dst + c, r4);
                         }
-                    } else if (p.db) {
+                    } else if (p.db && blockIdx.z == 0) {
                         const float r1[1] = {acc[0]};
                         VecIO<float, 1>::red_add(p.db + n, r1);
                     }

@@ -18,6 +18,7 @@
 #include "msda_fast.cuh"
 #include "msda_generic.cuh"
 #include "linear_tf32x3.cuh"
+#include "ln_kernels.cuh"
 
 namespace {
 
@@ -538,9 +539,9 @@ int launch_linear_persistent(const LinearParams &p, const float *w_hi, const flo
 {
     CUtensorMap mh, ml, my;
     int rc;
-    if ((rc = make_map(&mh, w_hi, NT, p.K, NT, kGemmBlockK, true))) return rc;
-    if ((rc = make_map(&ml, w_lo, NT, p.K, NT, kGemmBlockK, true))) return rc;
-    if ((rc = make_map(&my, p.y, p.M, NT, kGemmBlockM, 32, true))) return rc;
+    if ((rc = make_map(&mh, w_hi, p.N, p.K, NT, kGemmBlockK, true))) return rc;
+    if ((rc = make_map(&ml, w_lo, p.N, p.K, NT, kGemmBlockK, true))) return rc;
+    if ((rc = make_map(&my, p.y, p.M, p.N, 32, 32, true))) return rc;      // one 32 x 32 box per epilogue warp
     constexpr int smem = linear_persistent_smem_bytes<NT>();
     static bool attr_set = false;
     if (!attr_set) {
@@ -549,7 +550,7 @@ int launch_linear_persistent(const LinearParams &p, const float *w_hi, const flo
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(persistent linear smem)");
         attr_set = true;
     }
-    const int tiles = (p.M + kGemmBlockM - 1) / kGemmBlockM;
+    const int tiles = ((p.M + kGemmBlockM - 1) / kGemmBlockM) * p.slices;
     const int grid = tiles < sms ? tiles : sms;
     linear_tf32x3_persistent_kernel<NT><<<grid, kGemmThreadsPersistent, smem, st>>>(p, mh, ml, my);
     const cudaError_t e = cudaGetLastError();
@@ -568,7 +569,7 @@ size_t bm2f_linear_workspace_bytes(int out_features, int in_features)
 namespace {
 // y[rows, n_out] = x[rows, k_red] * w'[n_out, k_red]^T (+ bias); w' = weight or its transpose
 int linear_common(const void *x, const void *weight, const void *bias, void *y, void *workspace, int rows, int n_out,
-                  int k_red, int transpose_weight, int split, void *stream)
+                  int k_red, int transpose_weight, int split, void *stream, int relu = 0, const void *mask = nullptr /* output mask */)
 {
     if (!x || !weight || !y || !workspace) return fail(BM2F_ERR_INVALID, "null pointer");
     if (rows <= 0) return fail(BM2F_ERR_INVALID, "rows must be positive");
@@ -594,16 +595,23 @@ int linear_common(const void *x, const void *weight, const void *bias, void *y, 
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "launch split_tf32_kernel");
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    LinearParams p{static_cast<const float *>(x), static_cast<const float *>(bias), static_cast<float *>(y), rows,
-                   n_out, k_red, split};
+    LinearParams p{};
+    p.x = static_cast<const float *>(x); p.bias = static_cast<const float *>(bias); p.y = static_cast<float *>(y);
+    p.M = rows; p.N = n_out; p.K = k_red; p.slices = 1; p.relu = relu; p.out_mask = static_cast<const float *>(mask);
+    p.split = split;
+    if (mask && !aligned16(mask)) return fail(BM2F_ERR_UNSUPPORTED, "linear: mask must be 16-byte aligned");
     if (!one_tile) {
+        if (n_out % 256 == 0) {      // 256-wide column slices (1024-wide FFN layer = 4 slices sharing the row tile)
+            p.slices = n_out / 256;
+            return launch_linear_persistent<256>(p, w_hi, w_lo, sms, st);
+        }
         switch (n_out) {
-        case 256: return launch_linear_persistent<256>(p, w_hi, w_lo, sms, st);
         case 192: return launch_linear_persistent<192>(p, w_hi, w_lo, sms, st);
         case 96: return launch_linear_persistent<96>(p, w_hi, w_lo, sms, st);
         default: break;      // 288 = 2 x 144 columns does not fit two accumulators: one-tile kernel
         }
     }
+    if (relu || mask) return fail(BM2F_ERR_UNSUPPORTED, "linear: relu / mask need the persistent kernel (width %% 256 == 0, 192 or 96)");
     switch (n_out) {
     case 256: return launch_linear<256, 1>(p, w_hi, w_lo, st);
     case 288: return launch_linear<144, 2>(p, w_hi, w_lo, st);
@@ -621,14 +629,22 @@ int bm2f_linear_forward(const void *x, const void *weight, const void *bias, voi
     return linear_common(x, weight, bias, y, workspace, rows, out_features, in_features, 0, split, stream);
 }
 
-int bm2f_linear_backward_weight(const void *grad_y, const void *x, void *grad_weight, void *grad_bias, int rows,
-                                int out_features, int in_features, int split, void *stream)
+int bm2f_linear_relu_forward(const void *x, const void *weight, const void *bias, void *y, void *workspace, int rows,
+                             int out_features, int in_features, int split, void *stream)
+{
+    return linear_common(x, weight, bias, y, workspace, rows, out_features, in_features, 0, split, stream, 1);
+}
+
+namespace {
+int linear_dw_common(const void *grad_y, const void *x, void *grad_weight, void *grad_bias, int rows,
+                     int out_features, int in_features, int split, void *stream)
 {
     if (!grad_y || !x || !grad_weight) return fail(BM2F_ERR_INVALID, "null pointer");
     if (rows <= 0 || out_features <= 0) return fail(BM2F_ERR_INVALID, "rows / out_features must be positive");
-    if (in_features != 256)
-        return fail(BM2F_ERR_UNSUPPORTED, "weight-gradient GEMM is built for in_features = 256 (got %d)", in_features);
-    if (out_features > 4096) return fail(BM2F_ERR_UNSUPPORTED, "out_features too large");
+    if (in_features <= 0 || in_features % 256 != 0)
+        return fail(BM2F_ERR_UNSUPPORTED, "weight-gradient GEMM needs in_features to be a multiple of 256 (got %d)",
+                    in_features);
+    if (out_features > 8192 || in_features > 8192) return fail(BM2F_ERR_UNSUPPORTED, "layer too large");
     if (split != 1 && split != 3) return fail(BM2F_ERR_INVALID, "split must be 3 (tf32x3) or 1 (single TF32 pass)");
     int sms = 0, cc = 0;
     int rc = device_info(&sms, &cc);
@@ -639,12 +655,15 @@ int bm2f_linear_backward_weight(const void *grad_y, const void *x, void *grad_we
     if (e == cudaSuccess && grad_bias) e = cudaMemsetAsync(grad_bias, 0, static_cast<size_t>(out_features) * 4, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(grad_weight / grad_bias)");
     const int n_tiles = (out_features + 127) / 128;
-    int chunks = sms / n_tiles;
+    const int k_slices = in_features / 256;
+    int chunks = sms / (n_tiles * k_slices);
     if (chunks < 1) chunks = 1;
     int rows_per_chunk = ((rows + chunks - 1) / chunks + 31) / 32 * 32;
     chunks = (rows + rows_per_chunk - 1) / rows_per_chunk;
-    LinearDwParams p{static_cast<const float *>(grad_y), static_cast<const float *>(x), static_cast<float *>(grad_weight),
-                     static_cast<float *>(grad_bias), rows, out_features, rows_per_chunk, split};
+    LinearDwParams p{};
+    p.g = static_cast<const float *>(grad_y); p.x = static_cast<const float *>(x);
+    p.dw = static_cast<float *>(grad_weight); p.db = static_cast<float *>(grad_bias);
+    p.M = rows; p.N = out_features; p.ldx = in_features; p.rows_per_chunk = rows_per_chunk; p.split = split;
     constexpr int smem = linear_dw_smem_bytes();
     static bool attr_set = false;
     if (!attr_set) {
@@ -652,11 +671,18 @@ int bm2f_linear_backward_weight(const void *grad_y, const void *x, void *grad_we
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dW smem)");
         attr_set = true;
     }
-    linear_dw_tf32x3_kernel<<<dim3(n_tiles, chunks), kDwThreads, smem, st>>>(p);
+    linear_dw_tf32x3_kernel<<<dim3(n_tiles, chunks, k_slices), kDwThreads, smem, st>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "launch linear_dw_tf32x3_kernel");
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return BM2F_OK;
+}
+}  // namespace
+
+int bm2f_linear_backward_weight(const void *grad_y, const void *x, void *grad_weight, void *grad_bias, int rows,
+                                int out_features, int in_features, int split, void *stream)
+{
+    return linear_dw_common(grad_y, x, grad_weight, grad_bias, rows, out_features, in_features, split, stream);
 }
 
 int bm2f_linear_backward_input(const void *grad_y, const void *weight, void *grad_x, void *workspace, int rows,
@@ -664,6 +690,69 @@ int bm2f_linear_backward_input(const void *grad_y, const void *weight, void *gra
 {
     // grad_x[rows, in] = grad_y[rows, out] * weight[out, in]: a GEMM over k = out with w' = weight^T (in, out)
     return linear_common(grad_y, weight, nullptr, grad_x, workspace, rows, in_features, out_features, 1, split, stream);
+}
+
+int bm2f_linear_backward_input_masked(const void *grad_y, const void *weight, const void *mask, void *grad_x,
+                                      void *workspace, int rows, int out_features, int in_features, int split,
+                                      void *stream)
+{
+    // grad_x = (grad_y * weight) where mask > 0, else 0: the ReLU backward of the layer that produced this layer's
+    // input is applied in the GEMM epilogue, so the masked gradient is produced in one pass
+    if (!mask) return fail(BM2F_ERR_INVALID, "null mask");
+    return linear_common(grad_y, weight, nullptr, grad_x, workspace, rows, in_features, out_features, 1, split, stream, 0,
+                         mask);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused residual-add + LayerNorm (ln_kernels.cuh)
+// ---------------------------------------------------------------------------------------------
+int bm2f_add_layernorm_forward(const void *x, const void *residual, const void *gamma, const void *beta, float eps,
+                               void *z, void *y, void *mean, void *rstd, int rows, int channels, void *stream)
+{
+    if (!x || !residual || !gamma || !beta || !z || !y || !mean || !rstd) return fail(BM2F_ERR_INVALID, "null pointer");
+    if (rows <= 0) return fail(BM2F_ERR_INVALID, "rows must be positive");
+    if (channels != kLnC) return fail(BM2F_ERR_UNSUPPORTED, "add+LayerNorm is built for %d channels (got %d)", kLnC, channels);
+    if (!aligned16(x) || !aligned16(residual) || !aligned16(gamma) || !aligned16(beta) || !aligned16(z) || !aligned16(y))
+        return fail(BM2F_ERR_UNSUPPORTED, "add+LayerNorm: tensors must be 16-byte aligned");
+    int sms = 0, cc = 0;
+    int rc = device_info(&sms, &cc);
+    if (rc) return rc;
+    const int blocks = (rows + 7) / 8 < sms * 8 ? (rows + 7) / 8 : sms * 8;
+    add_layernorm_fwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const float *>(x), static_cast<const float *>(residual), static_cast<const float *>(gamma),
+        static_cast<const float *>(beta), eps, static_cast<float *>(z), static_cast<float *>(y),
+        static_cast<float *>(mean), static_cast<float *>(rstd), rows);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "launch add_layernorm_fwd_kernel");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return BM2F_OK;
+}
+
+int bm2f_add_layernorm_backward(const void *grad_y, const void *z, const void *mean, const void *rstd, const void *gamma,
+                                void *grad_z, void *grad_gamma, void *grad_beta, int rows, int channels, void *stream)
+{
+    if (!grad_y || !z || !mean || !rstd || !gamma || !grad_z || !grad_gamma || !grad_beta)
+        return fail(BM2F_ERR_INVALID, "null pointer");
+    if (rows <= 0) return fail(BM2F_ERR_INVALID, "rows must be positive");
+    if (channels != kLnC) return fail(BM2F_ERR_UNSUPPORTED, "add+LayerNorm is built for %d channels (got %d)", kLnC, channels);
+    if (!aligned16(grad_y) || !aligned16(z) || !aligned16(gamma) || !aligned16(grad_z))
+        return fail(BM2F_ERR_UNSUPPORTED, "add+LayerNorm: tensors must be 16-byte aligned");
+    int sms = 0, cc = 0;
+    int rc = device_info(&sms, &cc);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(grad_gamma, 0, kLnC * 4, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(grad_beta, 0, kLnC * 4, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(grad_gamma / grad_beta)");
+    const int blocks = (rows + 7) / 8 < sms * 4 ? (rows + 7) / 8 : sms * 4;
+    add_layernorm_bwd_kernel<<<blocks, 256, 0, st>>>(static_cast<const float *>(grad_y), static_cast<const float *>(z),
+                                                     static_cast<const float *>(mean), static_cast<const float *>(rstd),
+                                                     static_cast<const float *>(gamma), static_cast<float *>(grad_z),
+                                                     static_cast<float *>(grad_gamma), static_cast<float *>(grad_beta), rows);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "launch add_layernorm_bwd_kernel");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return BM2F_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -233,7 +233,8 @@ std::vector<at::Tensor> ms_deform_attn_fused_backward(const at::Tensor &value, c
 // ---- tcgen05 projection GEMM (forward of nn.Linear, fp32) -------------------------------------------------
 bool linear_tf32x3_supported(int64_t in_features, int64_t out_features)
 {
-    return in_features == 256 && (out_features == 256 || out_features == 288 || out_features == 192 || out_features == 96);
+    const bool width_ok = out_features % 256 == 0 || out_features == 288 || out_features == 192 || out_features == 96;
+    return in_features % 256 == 0 && in_features <= 4096 && width_ok && out_features <= 4096;
 }
 
 // (grad_weight, grad_bias) = (grad_y^T x, column sums of grad_y) on the tensor cores
@@ -242,18 +243,19 @@ std::vector<at::Tensor> linear_tf32x3_backward_weight(const at::Tensor &grad_y, 
 {
     TORCH_CHECK(grad_y.is_cuda() && x.is_cuda(), "linear_tf32x3_backward_weight: CUDA tensors only");
     TORCH_CHECK(grad_y.scalar_type() == at::kFloat && x.scalar_type() == at::kFloat, "float32 only");
-    TORCH_CHECK(x.size(-1) == 256, "in_features must be 256");
     const c10::cuda::CUDAGuard guard(x.device());
     auto g = grad_y.contiguous();
     auto xc = x.contiguous();
-    const int64_t rows = xc.numel() / 256;
+    const int64_t k = xc.size(-1);
+    TORCH_CHECK(k % 256 == 0, "in_features must be a multiple of 256");
+    const int64_t rows = xc.numel() / k;
     const int64_t n = g.size(-1);
     TORCH_CHECK(g.numel() == rows * n, "grad_y / x row count mismatch");
-    auto gw = at::empty({n, 256}, xc.options());
+    auto gw = at::empty({n, k}, xc.options());
     auto gb = with_bias ? at::empty({n}, xc.options()) : at::Tensor();
     const int rc = bm2f_linear_backward_weight(g.data_ptr(), xc.data_ptr(), gw.data_ptr(),
                                                with_bias ? gb.data_ptr() : nullptr, static_cast<int>(rows),
-                                               static_cast<int>(n), 256, static_cast<int>(split),
+                                               static_cast<int>(n), static_cast<int>(k), static_cast<int>(split),
                                                at::cuda::getCurrentCUDAStream().stream());
     TORCH_CHECK(rc == BM2F_OK, "linear_tf32x3_backward_weight: ", bm2f_msda_last_error());
     return {gw, gb};
@@ -313,6 +315,107 @@ at::Tensor linear_tf32x3(const at::Tensor &x, const at::Tensor &weight, const c1
     return y;
 }
 
+
+// ---- FFN layer with fused ReLU and fused residual + LayerNorm (encoder layer, msdeformattn.py:92-131) -----
+at::Tensor linear_relu_tf32x3(const at::Tensor &x, const at::Tensor &weight, const at::Tensor &bias, int64_t split)
+{
+    TORCH_CHECK(x.is_cuda() && weight.is_cuda() && bias.is_cuda(), "linear_relu_tf32x3: CUDA tensors only");
+    TORCH_CHECK(x.scalar_type() == at::kFloat && weight.scalar_type() == at::kFloat, "float32 only");
+    TORCH_CHECK(weight.dim() == 2 && x.size(-1) == weight.size(1), "shape mismatch");
+    const c10::cuda::CUDAGuard guard(x.device());
+    auto xc = x.contiguous();
+    auto wc = weight.contiguous();
+    auto bc = bias.contiguous();
+    const int64_t rows = xc.numel() / xc.size(-1);
+    auto sizes = xc.sizes().vec();
+    sizes.back() = wc.size(0);
+    auto y = at::empty(sizes, xc.options());
+    auto ws = at::empty({static_cast<int64_t>(bm2f_linear_workspace_bytes(wc.size(0), wc.size(1)) / 4)}, xc.options());
+    const int rc = bm2f_linear_relu_forward(xc.data_ptr(), wc.data_ptr(), bc.data_ptr(), y.data_ptr(), ws.data_ptr(),
+                                            static_cast<int>(rows), static_cast<int>(wc.size(0)),
+                                            static_cast<int>(wc.size(1)), static_cast<int>(split),
+                                            at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == BM2F_OK, "linear_relu_tf32x3: ", bm2f_msda_last_error());
+    return y;
+}
+
+// backward of y = linear2(relu(linear1(x))) given h = relu(linear1(x)):
+// returns (grad_x, grad_W1, grad_b1, grad_W2, grad_b2); every GEMM on tcgen05, the ReLU mask applied in an epilogue
+std::vector<at::Tensor> ffn_tf32x3_backward(const at::Tensor &grad_y, const at::Tensor &x, const at::Tensor &h,
+                                            const at::Tensor &w1, const at::Tensor &w2, int64_t split)
+{
+    TORCH_CHECK(grad_y.is_cuda() && x.is_cuda() && h.is_cuda() && w1.is_cuda() && w2.is_cuda(), "CUDA tensors only");
+    const c10::cuda::CUDAGuard guard(x.device());
+    auto g = grad_y.contiguous();
+    auto xc = x.contiguous();
+    auto hc = h.contiguous();
+    auto w1c = w1.contiguous();
+    auto w2c = w2.contiguous();
+    const int d = static_cast<int>(w1c.size(1)), f = static_cast<int>(w1c.size(0));      // d_model, d_ffn
+    TORCH_CHECK(w2c.size(0) == d && w2c.size(1) == f, "linear2 must be (d_model, d_ffn)");
+    const int64_t rows = xc.numel() / d;
+    auto stream = at::cuda::getCurrentCUDAStream().stream();
+    auto ws = at::empty({static_cast<int64_t>(bm2f_linear_workspace_bytes(f, d) / 4)}, xc.options());
+    auto g1 = at::empty_like(hc);                                   // grad of the hidden activation, ReLU-masked
+    int rc = bm2f_linear_backward_input_masked(g.data_ptr(), w2c.data_ptr(), hc.data_ptr(), g1.data_ptr(), ws.data_ptr(),
+                                               static_cast<int>(rows), d, f, static_cast<int>(split), stream);
+    TORCH_CHECK(rc == BM2F_OK, "ffn backward (masked grad_h): ", bm2f_msda_last_error());
+    auto gw2 = at::empty_like(w2c);
+    auto gb2 = at::empty({d}, xc.options());
+    rc = bm2f_linear_backward_weight(g.data_ptr(), hc.data_ptr(), gw2.data_ptr(), gb2.data_ptr(), static_cast<int>(rows),
+                                     d, f, static_cast<int>(split), stream);
+    TORCH_CHECK(rc == BM2F_OK, "ffn backward (grad_W2): ", bm2f_msda_last_error());
+    auto gx = at::empty_like(xc);
+    rc = bm2f_linear_backward_input(g1.data_ptr(), w1c.data_ptr(), gx.data_ptr(), ws.data_ptr(), static_cast<int>(rows), f,
+                                    d, static_cast<int>(split), stream);
+    TORCH_CHECK(rc == BM2F_OK, "ffn backward (grad_x): ", bm2f_msda_last_error());
+    auto gw1 = at::empty_like(w1c);
+    auto gb1 = at::empty({f}, xc.options());
+    rc = bm2f_linear_backward_weight(g1.data_ptr(), xc.data_ptr(), gw1.data_ptr(), gb1.data_ptr(), static_cast<int>(rows),
+                                     f, d, static_cast<int>(split), stream);
+    TORCH_CHECK(rc == BM2F_OK, "ffn backward (grad_W1): ", bm2f_msda_last_error());
+    return {gx, gw1, gb1, gw2, gb2};
+}
+
+std::vector<at::Tensor> add_layernorm_forward(const at::Tensor &x, const at::Tensor &residual, const at::Tensor &gamma,
+                                              const at::Tensor &beta, double eps)
+{
+    TORCH_CHECK(x.is_cuda() && residual.is_cuda(), "add_layernorm: CUDA tensors only (no CPU path)");
+    TORCH_CHECK(x.scalar_type() == at::kFloat && x.size(-1) == 256 && x.sizes() == residual.sizes(),
+                "add_layernorm: float32, 256 channels, equal shapes");
+    const c10::cuda::CUDAGuard guard(x.device());
+    auto xc = x.contiguous();
+    auto rc_ = residual.contiguous();
+    const int64_t rows = xc.numel() / 256;
+    auto z = at::empty_like(xc);
+    auto y = at::empty_like(xc);
+    auto mean = at::empty({rows}, xc.options());
+    auto rstd = at::empty({rows}, xc.options());
+    const int rc = bm2f_add_layernorm_forward(xc.data_ptr(), rc_.data_ptr(), gamma.contiguous().data_ptr(),
+                                              beta.contiguous().data_ptr(), static_cast<float>(eps), z.data_ptr(),
+                                              y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), static_cast<int>(rows), 256,
+                                              at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == BM2F_OK, "add_layernorm_forward: ", bm2f_msda_last_error());
+    return {y, z, mean, rstd};
+}
+
+std::vector<at::Tensor> add_layernorm_backward(const at::Tensor &grad_y, const at::Tensor &z, const at::Tensor &mean,
+                                               const at::Tensor &rstd, const at::Tensor &gamma)
+{
+    const c10::cuda::CUDAGuard guard(z.device());
+    auto g = grad_y.contiguous();
+    const int64_t rows = z.numel() / 256;
+    auto dz = at::empty_like(z);
+    auto dgamma = at::empty({256}, z.options());
+    auto dbeta = at::empty({256}, z.options());
+    const int rc = bm2f_add_layernorm_backward(g.data_ptr(), z.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                               gamma.contiguous().data_ptr(), dz.data_ptr(), dgamma.data_ptr(),
+                                               dbeta.data_ptr(), static_cast<int>(rows), 256,
+                                               at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == BM2F_OK, "add_layernorm_backward: ", bm2f_msda_last_error());
+    return {dz, dgamma, dbeta};
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
@@ -327,6 +430,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("linear_tf32x3_supported", &linear_tf32x3_supported);
     m.def("linear_tf32x3_backward_weight", &linear_tf32x3_backward_weight, "grad_W = grad_y^T x, grad_b = sum grad_y (tcgen05)");
     m.def("linear_tf32x3_backward_input", &linear_tf32x3_backward_input, "grad_x = grad_y @ weight (tcgen05)");
+    m.def("linear_relu_tf32x3", &linear_relu_tf32x3, "y = relu(x W^T + b) on tcgen05");
+    m.def("ffn_tf32x3_backward", &ffn_tf32x3_backward, "backward of linear2(relu(linear1(x)))");
+    m.def("add_layernorm_forward", &add_layernorm_forward, "z = x + r, y = LayerNorm(z)");
+    m.def("add_layernorm_backward", &add_layernorm_backward);
     m.def("abi_version", []() { return bm2f_msda_abi_version(); });
     m.def("build_info", []() { return std::string(bm2f_msda_build_info()); });
     m.def("launch_count", []() { return bm2f_msda_launch_count(); });

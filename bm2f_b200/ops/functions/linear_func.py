@@ -47,7 +47,8 @@ class LinearTF32x3Function(Function):
 
 
 def linear_tf32x3(x, weight, bias=None, split=3):
-    """Drop-in for F.linear(x, weight, bias) on CUDA float32 tensors with in_features = 256."""
+    """Drop-in for F.linear(x, weight, bias) on CUDA float32 tensors (in_features a multiple of 256, output width a
+    multiple of 256 or 288 / 192 / 96)."""
     return LinearTF32x3Function.apply(x, weight, bias, split)
 
 

@@ -164,7 +164,7 @@ int bm2f_msda_fused_backward(const void *value, const int64_t *spatial_shapes,
  * Projection GEMM on the 5th-generation tensor cores (tcgen05 + TMEM), for the four nn.Linear layers of
  * MSDeformAttn (ops/modules/ms_deform_attn.py:59-62; applied at :98, :101, :102, :124):
  *     y[rows, out_features] = x[rows, in_features] * weight[out_features, in_features]^T + bias
- * float32 in / out; output width in {256, 288, 192, 96}, reduction length a multiple of 32 up to 288
+ * float32 in / out; output width a multiple of 256 or one of {288, 192, 96}, reduction length a multiple of 32
  * (forward: in_features = 256 = d_model; bm2f_linear_backward_input: grad_x = grad_y * weight, width 256).
  * split = 3: three-term TF32 split with fp32 accumulation (fp32-grade result, what the fp32 reference
  * module needs); split = 1: single TF32 pass.  `workspace` = bm2f_linear_workspace_bytes() of device
@@ -175,10 +175,36 @@ int bm2f_linear_forward(const void *x, const void *weight, const void *bias, voi
                         int rows, int out_features, int in_features, int split, void *stream);
 int bm2f_linear_backward_input(const void *grad_y, const void *weight, void *grad_x, void *workspace,
                                int rows, int out_features, int in_features, int split, void *stream);
-/* grad_weight[out, 256] = grad_y^T x and grad_bias[out] = column sums of grad_y (may be NULL); both are
- * zeroed and then accumulated with red.global.add by row-chunk CTAs (summation order is free). */
+/* grad_weight[out, in] = grad_y^T x and grad_bias[out] = column sums of grad_y (may be NULL); both are
+ * zeroed and then accumulated with red.global.add by row-chunk CTAs (summation order is free).
+ * in_features must be a multiple of 256. */
 int bm2f_linear_backward_weight(const void *grad_y, const void *x, void *grad_weight, void *grad_bias,
                                 int rows, int out_features, int in_features, int split, void *stream);
+
+/* FFN of the encoder layer (reference: msdeformattn.py:116-120, linear2(relu(linear1(src)))):
+ *   bm2f_linear_relu_forward:            y = max(x W^T + b, 0), ReLU in the GEMM epilogue
+ *   bm2f_linear_backward_input_masked:   grad_x = (grad_y W) where mask > 0 else 0 — with mask = the hidden
+ *     activation this is linear2's input gradient with linear1's ReLU backward applied in the epilogue, so the
+ *     masked gradient is written once and feeds linear1's backward GEMMs directly.
+ * Output width a multiple of 256, or 192 / 96. */
+int bm2f_linear_relu_forward(const void *x, const void *weight, const void *bias, void *y, void *workspace,
+                             int rows, int out_features, int in_features, int split, void *stream);
+int bm2f_linear_backward_input_masked(const void *grad_y, const void *weight, const void *mask, void *grad_x,
+                                      void *workspace, int rows, int out_features, int in_features, int split,
+                                      void *stream);
+
+/*
+ * Fused residual-add + LayerNorm of the encoder layer (reference: msdeformattn.py:115-131,
+ * `src = src + dropout(src2); src = norm(src)` with dropout = 0), 256 channels, float32:
+ *   forward : z = x + residual (kept for backward), y = LayerNorm(z) * gamma + beta, per-row mean / rstd
+ *   backward: grad_z (= gradient of both x and residual), grad_gamma, grad_beta (zeroed, then accumulated)
+ */
+int bm2f_add_layernorm_forward(const void *x, const void *residual, const void *gamma, const void *beta,
+                               float eps, void *z, void *y, void *mean, void *rstd, int rows, int channels,
+                               void *stream);
+int bm2f_add_layernorm_backward(const void *grad_y, const void *z, const void *mean, const void *rstd,
+                                const void *gamma, void *grad_z, void *grad_gamma, void *grad_beta, int rows,
+                                int channels, void *stream);
 
 /*
  * Host-buffer convenience used for end-to-end measurement and by non-torch callers:

@@ -82,3 +82,22 @@ def test_byte_model_matches_survey():
     assert W.hbm_bytes(S, "fwd", "bf16") == 2176 * S
     assert W.gather_bytes(S, "fwd") == 49152 * S
     assert W.gather_bytes(S, "bwd") == 98304 * S
+
+
+def test_encoder_mirror_surface(built):
+    # reference: msdeformattn.py:22-60 (EncoderOnly), 92-113 (layer): names -> state-dict keys
+    from bm2f_b200.encoder import (MSDeformAttnTransformerEncoder, MSDeformAttnTransformerEncoderLayer,
+                                   MSDeformAttnTransformerEncoderOnly)
+    enc = MSDeformAttnTransformerEncoderOnly(d_model=256, nhead=8, num_encoder_layers=6, dim_feedforward=1024,
+                                             dropout=0.0, activation="relu", num_feature_levels=3, enc_n_points=4)
+    keys = set(enc.state_dict().keys())
+    assert "level_embed" in keys and enc.level_embed.shape == (3, 256)
+    for i in range(6):
+        for name in ("self_attn.sampling_offsets", "self_attn.attention_weights", "self_attn.value_proj",
+                     "self_attn.output_proj", "norm1", "linear1", "linear2", "norm2"):
+            assert f"encoder.layers.{i}.{name}.weight" in keys and f"encoder.layers.{i}.{name}.bias" in keys
+    assert len(keys) == 1 + 6 * 16
+    layer = MSDeformAttnTransformerEncoderLayer()
+    assert layer.linear1.out_features == 1024 and layer.self_attn.n_levels == 4 and layer.dropout1.p == 0.1
+    ref = MSDeformAttnTransformerEncoder.get_reference_points([(2, 3)], torch.ones(1, 1, 2), "cpu")
+    assert torch.allclose(ref, W.reference_points(((2, 3),), 1))
