@@ -36,6 +36,7 @@ struct LinearParams {
     int M, N, K;        // N = total output width (row stride of y and rows of the weight)
     int slices;         // persistent kernel: N / NT column slices, tile = (row tile, slice)
     int relu;           // epilogue: y = max(y, 0)
+    int store_mode;     // persistent kernel epilogue: 0 = per-warp TMA store, 1 = coalesced 128-bit stores through smem
     const float *out_mask;  // optional (M, N): epilogue zeroes y where out_mask <= 0 (ReLU backward of the previous layer)
     int split;           // 3 = tf32x3 (fp32-grade), 1 = single TF32 pass
 };
@@ -323,8 +324,11 @@ linear_tf32x3_kernel(const LinearParams p, const __grid_constant__ CUtensorMap t
 // Persistent variant (N <= 256): one CTA per SM loops over its row tiles; the accumulator is double-buffered in
 // TMEM so the epilogue of tile i (warps 6..9: TMEM -> staging tile -> TMA store) overlaps the MMAs of tile
 // i+1, and the shared-memory stage ring / X register prefetch run across tile boundaries.
+// Warps: 0 TMA (weights), 1 MMA issuer, 2..5 activation producers, 6..9 epilogue.
 // ------------------------------------------------------------------------------------------------------
-constexpr int kGemmThreadsPersistent = 320;
+constexpr int kGemmProducerWarps = 4;   // activation producers (8 measured slower at N = 256: the weight stream from L2 is the
+                                        // contended resource there; faster only for the 96-wide layer)
+constexpr int kGemmThreadsPersistent = (2 + kGemmProducerWarps + 4) * 32;
 
 template <int NT>
 __global__ void __launch_bounds__(kGemmThreadsPersistent, 1)
@@ -365,7 +369,7 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kGemmStages; ++s) {
-            mbar_init(&full_bar[s], 128 + 1);
+            mbar_init(&full_bar[s], kGemmProducerWarps * 32 + 1);
             mbar_init(&empty_bar[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -432,16 +436,18 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
                 umma_commit(&acc_full[b]);
             }
         }
-    } else if (warp < 6) {
-        // ---- X producers (warps 2..5): global -> registers -> hi/lo -> swizzled shared memory ----
+    } else if (warp < 2 + kGemmProducerWarps) {
+        // ---- X producers: global -> registers -> hi/lo -> swizzled shared memory ----
+        constexpr int kRowsPerPass = kGemmProducerWarps * 4;          // 8 threads per 128-byte row segment
+        constexpr int kPasses = kGemmBlockM / kRowsPerPass;
         const int t = threadIdx.x - 64;
         const int c16 = t & 7, rsub = t >> 3;
-        auto load_x = [&](int rt, int kb, float4 (&v)[8]) {
+        auto load_x = [&](int rt, int kb, float4 (&v)[kPasses]) {
             const int rbase = rt * kGemmBlockM + rsub;
             const size_t cbase = static_cast<size_t>(kb) * kGemmBlockK;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int gr = rbase + 16 * j;
+            for (int j = 0; j < kPasses; ++j) {
+                const int gr = rbase + kRowsPerPass * j;
                 v[j] = gr < p.M ? __ldg(reinterpret_cast<const float4 *>(p.x + static_cast<size_t>(gr) * p.K + cbase) + c16)
                                 : make_float4(0.f, 0.f, 0.f, 0.f);
             }
@@ -449,7 +455,7 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
         // kXDepth k-blocks of X are in flight per thread (registers): with one block in flight the kernel is bound by
         // global-load latency (16 KB per SM outstanding), measured 2x slower on the 1024-wide FFN shapes
         constexpr int kXDepth = 3;
-        float4 buf[kXDepth][8];
+        float4 buf[kXDepth][kPasses];
         TileIter lt = first_tile(), ct = first_tile();   // load iterator (kXDepth - 1 k-blocks ahead), convert iterator
         int lkb = 0, kb = 0, g = 0;
         auto advance = [&](TileIter &tl, int &k) {
@@ -471,8 +477,8 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
                 unsigned char *x_hi = stage_ptr(s);
                 unsigned char *x_lo = x_hi + kXBytes;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int r = rsub + 16 * j;
+                for (int j = 0; j < kPasses; ++j) {
+                    const int r = rsub + kRowsPerPass * j;
                     const uint32_t off = r * 128 + ((c16 ^ (r & 7)) << 4);
                     const float4 v = buf[u][j];
                     float4 hi, lo;
@@ -490,7 +496,7 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
             }
         }
     } else {
-        // ---- epilogue (warps 6..9) ----
+        // ---- epilogue (last 4 warps; warp % 4 selects the TMEM lane quarter) ----
         const int q = warp & 3;
         int i = 0, chunk = 0;
         for (TileIter ti = first_tile(); ti.tile < num_tiles; next_tile(ti), ++i) {
@@ -509,7 +515,7 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
                 // TMA store (box 32 x 32): no CTA-level barrier in the epilogue, four independent store pipelines
                 unsigned char *stg = staging + q * (2 * 4096) + (chunk & 1) * 4096;
                 const int grow = ti.rt * kGemmBlockM + q * 32 + lane;     // this thread's output row
-                if (chunk >= 2) {
+                if (chunk >= 2 && p.store_mode == 0) {
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                     __syncwarp();
                 }
@@ -529,18 +535,33 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
                     }
                     *reinterpret_cast<float4 *>(stg + lane * 128 + ((((c >> 2) ^ (lane & 7))) << 4)) = o;
                 }
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                                     reinterpret_cast<uint64_t>(&tm_y)),
-                                 "r"(smem_u32(stg)), "r"(ti.sl * NT + c0), "r"(ti.rt * kGemmBlockM + q * 32)
-                                 : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                if (p.store_mode == 0) {
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                         reinterpret_cast<uint64_t>(&tm_y)),
+                                     "r"(smem_u32(stg)), "r"(ti.sl * NT + c0), "r"(ti.rt * kGemmBlockM + q * 32)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                } else {
+                    // transposed read-back: 8 lanes cover one row's 128 bytes, every store instruction writes 4 full lines
+                    __syncwarp();
+                    const int ch = lane & 7;
+                    float *ybase = p.y + static_cast<size_t>(ti.rt * kGemmBlockM + q * 32) * p.N + ti.sl * NT + c0 + ch * 4;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int row = it * 4 + (lane >> 3);
+                        const float4 v = *reinterpret_cast<const float4 *>(stg + row * 128 + ((ch ^ (row & 7)) << 4));
+                        if (ti.rt * kGemmBlockM + q * 32 + row < p.M)
+                            *reinterpret_cast<float4 *>(ybase + static_cast<size_t>(row) * p.N) = v;
+                    }
+                    __syncwarp();
                 }
             }
         }
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (lane == 0 && p.store_mode == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();

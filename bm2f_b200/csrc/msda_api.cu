@@ -576,7 +576,10 @@ int linear_common(const void *x, const void *weight, const void *bias, void *y, 
     if (k_red <= 0 || k_red % kGemmBlockK != 0 || k_red > kGemmKMax)
         return fail(BM2F_ERR_UNSUPPORTED, "tcgen05 projection GEMM needs a reduction length that is a multiple of %d "
                     "and <= %d (got %d)", kGemmBlockK, kGemmKMax, k_red);
-    // split 3 / 1: persistent kernel (double-buffered TMEM accumulator); 13 / 11: one tile per CTA (kept for A/B)
+    // split 3 / 1: persistent kernel (double-buffered TMEM accumulator); +10: one tile per CTA (kept for A/B);
+    // +20: persistent kernel with coalesced-store epilogue instead of the TMA store (A/B)
+    const bool stg_epilogue = split >= 20;
+    if (stg_epilogue) split -= 20;
     const bool one_tile = split >= 10;
     if (one_tile) split -= 10;
     if (split != 1 && split != 3) return fail(BM2F_ERR_INVALID, "split must be 3 (tf32x3) or 1 (single TF32 pass)");
@@ -597,7 +600,7 @@ int linear_common(const void *x, const void *weight, const void *bias, void *y, 
     g_launches.fetch_add(1, std::memory_order_relaxed);
     LinearParams p{};
     p.x = static_cast<const float *>(x); p.bias = static_cast<const float *>(bias); p.y = static_cast<float *>(y);
-    p.M = rows; p.N = n_out; p.K = k_red; p.slices = 1; p.relu = relu; p.out_mask = static_cast<const float *>(mask);
+    p.M = rows; p.N = n_out; p.K = k_red; p.slices = 1; p.relu = relu; p.out_mask = static_cast<const float *>(mask); p.store_mode = stg_epilogue ? 1 : 0;
     p.split = split;
     if (mask && !aligned16(mask)) return fail(BM2F_ERR_UNSUPPORTED, "linear: mask must be 16-byte aligned");
     if (!one_tile) {

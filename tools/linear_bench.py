@@ -26,12 +26,13 @@ for n in (256, 288, 192, 96):
     torch.backends.cuda.matmul.allow_tf32 = False
     t3 = t(lambda: MSDA.linear_tf32x3(x, w, b, 3)); e3 = ((MSDA.linear_tf32x3(x, w, b, 3).double() - ref).abs().max() / ref.abs().max()).item()
     t13 = t(lambda: MSDA.linear_tf32x3(x, w, b, 13))
+    t23 = t(lambda: MSDA.linear_tf32x3(x, w, b, 23)); e23 = ((MSDA.linear_tf32x3(x, w, b, 23).double() - ref).abs().max() / ref.abs().max()).item()
     t1 = t(lambda: MSDA.linear_tf32x3(x, w, b, 1)); e1 = ((MSDA.linear_tf32x3(x, w, b, 1).double() - ref).abs().max() / ref.abs().max()).item()
     gb = rows * (256 + n) * 4 / 1e9
     fl = 2.0 * rows * 256 * n / 1e12
     print(f"N={n:3d} rows={rows}: cuBLAS fp32 {t_fp32:.3f} ms (err {e_fp32:.1e}) | cuBLAS tf32 {t_tf32:.3f} ms (err {e_tf32:.1e}) | "
           f"tcgen05 tf32x3 persistent {t3:.3f} ms (err {e3:.1e}, {gb/t3*1e3:.0f} GB/s, {3*fl/t3*1e3:.0f} TF/s tf32) | "
-          f"one-tile {t13:.3f} ms | tf32x1 persistent {t1:.3f} ms (err {e1:.1e}, {gb/t1*1e3:.0f} GB/s)")
+          f"one-tile {t13:.3f} ms | stg-epilogue {t23:.3f} ms (err {e23:.1e}) | tf32x1 persistent {t1:.3f} ms (err {e1:.1e}, {gb/t1*1e3:.0f} GB/s)")
 # ---- weight gradient
 for n in (256, 192, 96):
     g = torch.randn(rows, n, device=dev)
