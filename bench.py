@@ -220,7 +220,21 @@ def run_ours(args, wl):
         dist = dist_mod
 
     import bm2f_b200
+    from bm2f_b200 import build as b200_build
     from bm2f_b200 import cabi
+    # the native libraries normally travel with the tree; build them if this is a bare checkout
+    # (local rank 0 compiles, the other ranks wait for the files)
+    if not (os.path.exists(b200_build.LIB) and os.path.exists(b200_build.EXT)):
+        if local == 0:
+            log("[bench] native libraries missing: building (nvcc sm_100a + g++) ...")
+            b200_build.build_all()
+        else:
+            t_wait = time.time()
+            while not (os.path.exists(b200_build.LIB) and os.path.exists(b200_build.EXT)):
+                if time.time() - t_wait > 900:
+                    raise SystemExit("bench.py: timed out waiting for rank 0 to build the native libraries")
+                time.sleep(2)
+            time.sleep(5)
     MSDA = bm2f_b200.load_extension()
     if args.tuning:
         kv = dict(x.split("=") for x in args.tuning.split(","))

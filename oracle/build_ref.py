@@ -47,7 +47,7 @@ def build(force=False):
     gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     cu_obj = os.path.join(OUT_DIR, "ref_cuda_unit.o")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-           "--expt-relaxed-constexpr", "-DCUDA_HAS_FP16=1", "-D__CUDA_NO_HALF_OPERATORS__",
+           "--expt-relaxed-constexpr", "-w", "-Xcompiler", "-w", "-DCUDA_HAS_FP16=1", "-D__CUDA_NO_HALF_OPERATORS__",
            "-D__CUDA_NO_HALF_CONVERSIONS__", "-D__CUDA_NO_HALF2_OPERATORS__", "-ccbin", gxx,
            "-c", os.path.join(HERE, "ref_wrap", "ref_cuda_unit.cu"), "-o", cu_obj] + common + incflags
     print("nvcc reference .cu (about 2 min) ...", flush=True)
@@ -55,7 +55,7 @@ def build(force=False):
     objs.append(cu_obj)
     for src in ("vision.cpp", os.path.join("cpu", "ms_deform_attn_cpu.cpp")):
         o = os.path.join(OUT_DIR, os.path.basename(src) + ".o")
-        subprocess.check_call([gxx, "-O2", "-fPIC", "-std=c++17", "-Wno-deprecated-declarations", "-c",
+        subprocess.check_call([gxx, "-O2", "-fPIC", "-std=c++17", "-w", "-c",
                                os.path.join(REF_SRC, src), "-o", o] + common + incflags)
         objs.append(o)
     link = [gxx, "-shared", "-o", OUT] + objs
