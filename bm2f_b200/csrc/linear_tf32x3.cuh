@@ -44,7 +44,12 @@ struct LinearParams {
 
 // x = hi + lo with hi exactly representable in TF32 (10 explicit mantissa bits), rounded to nearest so that the
 // low parts have no sign bias (matters for the 10^5-term weight-gradient reductions)
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+__device__ __forceinline__ float tf32_hi(float x)
+{
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));      // one instruction: round to nearest, low 13 bits zero
+    return __uint_as_float(u);
+}
 
 // ---- tcgen05 / TMEM wrappers -------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_slot, uint32_t ncols)
