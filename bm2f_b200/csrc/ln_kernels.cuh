@@ -122,4 +122,21 @@ __global__ void __launch_bounds__(256) add_layernorm_bwd_kernel(const float *__r
     atomicAdd(dbeta + f, b);
 }
 
+
+// value.masked_fill(padding_mask[..., None], 0) without touching unmasked rows (reference:
+// ops/modules/ms_deform_attn.py:99-100; Mask2Former always passes an all-False mask, msdeformattn.py:62): one warp per
+// row reads the mask byte and only masked rows are written.  Used in place on tensors the caller owns.
+__global__ void __launch_bounds__(256) zero_masked_rows_kernel(float *__restrict__ x, const unsigned char *__restrict__ mask,
+                                                               int rows, int channels)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps) {
+        if (mask[row]) {
+            float4 *r = reinterpret_cast<float4 *>(x + static_cast<size_t>(row) * channels);
+            for (int c = lane; c < channels / 4; c += 32) r[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+
 }  // namespace bm2f

@@ -758,6 +758,23 @@ int bm2f_add_layernorm_backward(const void *grad_y, const void *z, const void *m
     return BM2F_OK;
 }
 
+int bm2f_zero_masked_rows(void *x, const void *row_mask, int rows, int channels, void *stream)
+{
+    if (!x || !row_mask) return fail(BM2F_ERR_INVALID, "null pointer");
+    if (rows <= 0 || channels <= 0 || channels % 4 != 0 || !aligned16(x))
+        return fail(BM2F_ERR_UNSUPPORTED, "zero_masked_rows: rows > 0, channels %% 4 == 0, 16-byte aligned rows");
+    int sms = 0, cc = 0;
+    int rc = device_info(&sms, &cc);
+    if (rc) return rc;
+    const int blocks = (rows + 7) / 8 < sms * 8 ? (rows + 7) / 8 : sms * 8;
+    zero_masked_rows_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<float *>(x), static_cast<const unsigned char *>(row_mask), rows, channels);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "launch zero_masked_rows_kernel");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return BM2F_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Host-buffer entry: chunked, double-buffered H2D -> kernels -> D2H.
 // ---------------------------------------------------------------------------------------------

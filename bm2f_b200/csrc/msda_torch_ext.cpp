@@ -377,6 +377,21 @@ std::vector<at::Tensor> ffn_tf32x3_backward(const at::Tensor &grad_y, const at::
     return {gx, gw1, gb1, gw2, gb2};
 }
 
+// in place: x[row] = 0 where mask[row]; x (..., C) float32 contiguous, mask (...) bool
+void zero_masked_rows_(at::Tensor x, const at::Tensor &mask)
+{
+    TORCH_CHECK(x.is_cuda() && mask.is_cuda(), "zero_masked_rows_: CUDA tensors only");
+    TORCH_CHECK(x.scalar_type() == at::kFloat && x.is_contiguous(), "zero_masked_rows_: contiguous float32 tensor");
+    TORCH_CHECK(mask.scalar_type() == at::kBool, "zero_masked_rows_: bool mask");
+    const int64_t c = x.size(-1);
+    auto m = mask.contiguous();
+    TORCH_CHECK(m.numel() * c == x.numel(), "zero_masked_rows_: mask must have one entry per row");
+    const c10::cuda::CUDAGuard guard(x.device());
+    const int rc = bm2f_zero_masked_rows(x.data_ptr(), m.data_ptr(), static_cast<int>(m.numel()), static_cast<int>(c),
+                                         at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == BM2F_OK, "zero_masked_rows_: ", bm2f_msda_last_error());
+}
+
 std::vector<at::Tensor> add_layernorm_forward(const at::Tensor &x, const at::Tensor &residual, const at::Tensor &gamma,
                                               const at::Tensor &beta, double eps)
 {
@@ -432,6 +447,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("linear_tf32x3_backward_input", &linear_tf32x3_backward_input, "grad_x = grad_y @ weight (tcgen05)");
     m.def("linear_relu_tf32x3", &linear_relu_tf32x3, "y = relu(x W^T + b) on tcgen05");
     m.def("ffn_tf32x3_backward", &ffn_tf32x3_backward, "backward of linear2(relu(linear1(x)))");
+    m.def("zero_masked_rows_", &zero_masked_rows_, "in-place masked_fill(mask[..., None], 0) touching only masked rows");
     m.def("add_layernorm_forward", &add_layernorm_forward, "z = x + r, y = LayerNorm(z)");
     m.def("add_layernorm_backward", &add_layernorm_backward);
     m.def("abi_version", []() { return bm2f_msda_abi_version(); });

@@ -20,11 +20,17 @@ USE_TCGEN05_DW = True
 
 class LinearTF32x3Function(Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, split):
+    def forward(ctx, x, weight, bias, split, row_mask=None):
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
         ctx.split = split
-        return MSDA.linear_tf32x3(x, weight, bias, split)
+        y = MSDA.linear_tf32x3(x, weight, bias, split)
+        if row_mask is not None:
+            # y.masked_fill(row_mask[..., None], 0) on the tensor this function owns: only masked rows are written.
+            # CONTRACT: the consumer must deliver a zero gradient for the masked rows (MSDeformAttnFusedFunction does:
+            # it zeroes those rows of grad_value), so backward needs no masking pass.
+            MSDA.zero_masked_rows_(y, row_mask)
+        return y
 
     @staticmethod
     @once_differentiable
@@ -43,13 +49,13 @@ class LinearTF32x3Function(Function):
                 gw = g2.t() @ x.reshape(-1, x.shape[-1])
             if want_b:
                 gb = g2.sum(0)
-        return gx, gw, gb, None
+        return gx, gw, gb, None, None
 
 
-def linear_tf32x3(x, weight, bias=None, split=3):
+def linear_tf32x3(x, weight, bias=None, split=3, row_mask=None):
     """Drop-in for F.linear(x, weight, bias) on CUDA float32 tensors (in_features a multiple of 256, output width a
     multiple of 256 or 288 / 192 / 96)."""
-    return LinearTF32x3Function.apply(x, weight, bias, split)
+    return LinearTF32x3Function.apply(x, weight, bias, split, row_mask)
 
 
 def supported(layer: torch.nn.Linear, x: torch.Tensor) -> bool:

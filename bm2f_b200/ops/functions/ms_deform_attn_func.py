@@ -13,6 +13,7 @@ Differences from the reference file, both deliberate:
 """
 from __future__ import annotations
 
+import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
@@ -51,11 +52,12 @@ class MSDeformAttnFusedFunction(Function):
 
     @staticmethod
     def forward(ctx, value, value_spatial_shapes, value_level_start_index, reference_points, sampling_offsets,
-                attention_logits):
+                attention_logits, value_padding_mask=None):
         output = MSDA.ms_deform_attn_fused_forward(value, value_spatial_shapes, value_level_start_index,
                                                    reference_points, sampling_offsets, attention_logits)
         ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, reference_points,
                               sampling_offsets, attention_logits)
+        ctx.value_padding_mask = value_padding_mask     # (N, S) bool or None: rows of `value` that were zero-filled
         return output
 
     @staticmethod
@@ -64,4 +66,10 @@ class MSDeformAttnFusedFunction(Function):
         value, shapes, start, ref, off, logits = ctx.saved_tensors
         grad_value, grad_off, grad_logits = MSDA.ms_deform_attn_fused_backward(
             value, shapes, start, ref, off, logits, grad_output.contiguous())
-        return grad_value, None, None, None, grad_off, grad_logits
+        if ctx.value_padding_mask is not None and grad_value.dtype == torch.float32:
+            # backward of value.masked_fill(mask[..., None], 0): only the masked rows of our own tensor are written
+            MSDA.zero_masked_rows_(grad_value.view(-1, grad_value.shape[-2] * grad_value.shape[-1]),
+                                   ctx.value_padding_mask)
+        elif ctx.value_padding_mask is not None:
+            grad_value = grad_value.masked_fill(ctx.value_padding_mask[..., None, None], 0)
+        return grad_value, None, None, None, grad_off, grad_logits, None

@@ -80,10 +80,11 @@ class MSDeformAttn(nn.Module):
         xavier_uniform_(self.output_proj.weight.data)
         constant_(self.output_proj.bias.data, 0.)
 
-    def _proj(self, layer, x):
+    def _proj(self, layer, x, row_mask=None):
         if self.tcgen05_linear and linear_func.supported(layer, x):
-            return linear_func.linear_tf32x3(x, layer.weight, layer.bias)
-        return layer(x)
+            return linear_func.linear_tf32x3(x, layer.weight, layer.bias, row_mask=row_mask)
+        y = layer(x)
+        return y if row_mask is None else y.masked_fill(row_mask[..., None], float(0))
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
                 input_padding_mask=None):
@@ -102,21 +103,27 @@ class MSDeformAttn(nn.Module):
             raise RuntimeError("MSDeformAttn: Not implemented on the CPU (this build has no CPU fallback)")
         # no device->host sync here: the level table is validated on the device side of the op
 
-        value = self._proj(self.value_proj, input_flatten)
-        if input_padding_mask is not None:
-            value = value.masked_fill(input_padding_mask[..., None], float(0))
+        use_fused = (self.fuse_prologue and reference_points.shape[-1] == 2 and reference_points.dtype == torch.float32
+                     and query.dtype == torch.float32
+                     and MSDA.ms_deform_attn_fused_supported(self.n_heads, self.d_model // self.n_heads, self.n_levels,
+                                                             self.n_points, False))
+        if use_fused:
+            # masked rows are zero-filled by a row-sparse in-place kernel inside the projection (forward) and inside
+            # the fused attention function (backward); both full-tensor masked_fill passes of the reference disappear
+            value = self._proj(self.value_proj, input_flatten, row_mask=input_padding_mask)
+        else:
+            value = self._proj(self.value_proj, input_flatten)
+            if input_padding_mask is not None:
+                value = value.masked_fill(input_padding_mask[..., None], float(0))
         value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
         sampling_offsets = self._proj(self.sampling_offsets, query).view(
             N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
         attention_weights = self._proj(self.attention_weights, query).view(
             N, Len_q, self.n_heads, self.n_levels * self.n_points)
-        if (self.fuse_prologue and reference_points.shape[-1] == 2 and reference_points.dtype == torch.float32
-                and sampling_offsets.dtype == torch.float32 and value.dtype in (torch.float32, torch.bfloat16)
-                and MSDA.ms_deform_attn_fused_supported(self.n_heads, self.d_model // self.n_heads, self.n_levels,
-                                                        self.n_points, value.dtype == torch.bfloat16)):
+        if use_fused and value.dtype == torch.float32 and sampling_offsets.dtype == torch.float32:
             output = MSDeformAttnFusedFunction.apply(
                 value, input_spatial_shapes, input_level_start_index, reference_points.contiguous(),
-                sampling_offsets, attention_weights)
+                sampling_offsets, attention_weights, input_padding_mask)
             return self._proj(self.output_proj, output)
         attention_weights = F.softmax(attention_weights, -1).view(
             N, Len_q, self.n_heads, self.n_levels, self.n_points)

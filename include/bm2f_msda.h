@@ -206,6 +206,11 @@ int bm2f_add_layernorm_backward(const void *grad_y, const void *z, const void *m
                                 const void *gamma, void *grad_z, void *grad_gamma, void *grad_beta, int rows,
                                 int channels, void *stream);
 
+/* In-place x[row, :] = 0 where row_mask[row] != 0 (bool / uint8 per row), float32 rows of `channels` values:
+ * `value.masked_fill(input_padding_mask[..., None], 0)` (ops/modules/ms_deform_attn.py:99-100) and its backward,
+ * writing only the masked rows instead of making a full pass. */
+int bm2f_zero_masked_rows(void *x, const void *row_mask, int rows, int channels, void *stream);
+
 /*
  * Host-buffer convenience used for end-to-end measurement and by non-torch callers:
  * every pointer is a HOST pointer (pinned memory gives full PCIe rate).  The library copies

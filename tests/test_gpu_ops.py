@@ -203,3 +203,37 @@ def test_module_padding_mask_and_box_reference(ops):
     assert y4.shape == (1, S, 256) and torch.isfinite(y4).all()
     with pytest.raises(ValueError):
         mod(x, ref2[..., :1], x, shapes, start, None)
+
+
+def test_module_padding_mask_fused_equals_reference_sequence(ops):
+    # non-trivial padding mask: the row-sparse masked_fill of the fused path (forward in the projection, backward in
+    # the fused attention function) must match value.masked_fill(...) of the reference op sequence
+    _, MSDeformAttn = ops
+    torch.manual_seed(5)
+    levels = ((6, 10), (12, 20), (24, 40))
+    dev = torch.device("cuda:0")
+    mod = MSDeformAttn(256, 3, 8, 4).to(dev)
+    with torch.no_grad():
+        mod.sampling_offsets.weight.normal_(0, 0.01)
+        mod.attention_weights.weight.normal_(0, 0.05)
+    shapes, start = W.level_tensors(levels, dev)
+    S = sum(h * w for h, w in levels)
+    src = torch.randn(2, S, 256, device=dev)
+    ref_pts = W.reference_points(levels, 2).to(dev)
+    mask = torch.rand(2, S, device=dev) < 0.2
+    go = torch.randn(2, S, 256, device=dev)
+
+    def run(fused):
+        mod.fuse_prologue = fused
+        mod.tcgen05_linear = fused
+        mod.zero_grad()
+        q = src.clone().requires_grad_(True)
+        x = src.clone().requires_grad_(True)
+        out = mod(q, ref_pts, x, shapes, start, mask)
+        out.backward(go)
+        return [out.detach(), q.grad, x.grad] + [p.grad.clone() for p in mod.parameters()]
+
+    a, b = run(True), run(False)
+    assert (a[0] - b[0]).abs().max().item() <= 5e-5 * max(1.0, b[0].abs().max().item())
+    for u, v in zip(a[1:], b[1:]):
+        assert rel_err(u.cpu().numpy(), v.cpu().numpy()) <= 1e-3

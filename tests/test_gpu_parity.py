@@ -355,3 +355,21 @@ def test_fused_rejects_unsupported_shapes(built):
     assert cabi.lib().bm2f_msda_fused_supported(4, 32, 3, 4, cabi.DTYPE_F32) == 0
     assert cabi.lib().bm2f_msda_fused_supported(8, 32, 5, 4, cabi.DTYPE_F32) == 0
     assert cabi.lib().bm2f_msda_fused_supported(8, 32, 3, 4, cabi.DTYPE_F64) == 0
+
+
+def test_fused_bf16_forward_vs_oracle(built):
+    levels = W.WORKLOADS[3].levels
+    base, ref, offsets, logits = _fused_inputs(levels, 1, 931)
+    dev = _dev()
+    sh, st = base["shapes"].to(dev), base["start"].to(dev)
+    v = base["value"].to(dev).bfloat16().contiguous()
+    r, o, lg = (t.to(dev).contiguous() for t in (ref, offsets, logits))
+    N, S, M, D = v.shape
+    out = torch.empty(N, S, M * D, device=dev, dtype=torch.bfloat16)
+    cabi.fused_forward(v.data_ptr(), sh.data_ptr(), st.data_ptr(), r.data_ptr(), o.data_ptr(), lg.data_ptr(),
+                       out.data_ptr(), (N, S, M, D, 3, S, 4), cabi.DTYPE_BF16, None,
+                       torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    want = O.fused_forward(v.float().cpu().numpy(), base["shapes"].numpy(), base["start"].numpy(), ref.numpy(),
+                           offsets.numpy(), logits.numpy())
+    assert rel_err(out.float().cpu().numpy(), want) <= 1e-2
