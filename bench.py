@@ -488,7 +488,7 @@ def run_e2e(cabi, wl, base, nb, bwd, steps, dist, world):
     d2h = wl.n_layers * nbytes(ho, hgv, hgl, hga)
     return {"value": nb * world / (dt / steps), "unit": "images/s", "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * dt / steps, "steps": steps,
-            "path": "bm2f_msda_forward_backward_host (C ABI), pinned host buffers, chunked double-buffered copies",
+            "path": "bm2f_msda_forward_backward_host (C ABI), pinned host buffers, chunked copies pipelined over three slots",
             "pcie_GBs_each_way": max(h2d, d2h) / (dt / steps) / 1e9}
 
 

@@ -19,6 +19,7 @@
 #include "msda_generic.cuh"
 #include "linear_tf32x3.cuh"
 #include "ln_kernels.cuh"
+#include "glue_kernels.cuh"
 
 namespace {
 
@@ -776,14 +777,144 @@ int bm2f_zero_masked_rows(void *x, const void *row_mask, int rows, int channels,
 }
 
 // ---------------------------------------------------------------------------------------------
+// pixel-decoder glue (glue_kernels.cuh)
+// ---------------------------------------------------------------------------------------------
+int bm2f_transpose_batched(const void *in, void *out, int batch, int rows, int cols, void *stream)
+{
+    if (!in || !out) return fail(BM2F_ERR_INVALID, "null pointer");
+    if (batch <= 0 || rows <= 0 || cols <= 0) return fail(BM2F_ERR_INVALID, "batch / rows / cols must be positive");
+    if (batch > 65535 || (rows + 31) / 32 > 65535) return fail(BM2F_ERR_UNSUPPORTED, "transpose: batch or rows too large");
+    const dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch);
+    transpose_batched_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const float *>(in),
+                                                                                  static_cast<float *>(out), rows, cols);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "launch transpose_batched_kernel");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return BM2F_OK;
+}
+
+size_t bm2f_groupnorm_tokens_workspace_bytes(int batch)
+{
+    return static_cast<size_t>(batch > 0 ? batch : 0) * kGnGroups * (2 * sizeof(double) + 2 * sizeof(float));
+}
+
+namespace {
+int gn_check(int batch, int tokens, int channels, int groups)
+{
+    if (batch <= 0 || tokens <= 0) return fail(BM2F_ERR_INVALID, "batch / tokens must be positive");
+    if (channels != kGnC || groups != kGnGroups)
+        return fail(BM2F_ERR_UNSUPPORTED, "token GroupNorm is built for %d channels in %d groups (got %d / %d)", kGnC,
+                    kGnGroups, channels, groups);
+    if (batch > 65535) return fail(BM2F_ERR_UNSUPPORTED, "token GroupNorm: batch too large");
+    return BM2F_OK;
+}
+int gn_chunks(int batch, int tokens, int sms)
+{
+    int chunks = (sms * 4 + batch - 1) / batch;          // ~4 CTAs per SM over the whole batch
+    const int max_chunks = (tokens + 7) / 8;             // at least one row per warp
+    if (chunks > max_chunks) chunks = max_chunks;
+    return chunks < 1 ? 1 : chunks;
+}
+}  // namespace
+
+int bm2f_groupnorm_tokens_forward(const void *y, const void *gamma, const void *beta, float eps, void *out,
+                                  int64_t out_batch_stride, void *mean, void *rstd, void *workspace, int batch, int tokens,
+                                  int channels, int groups, void *stream)
+{
+    if (!y || !gamma || !beta || !out || !mean || !rstd || !workspace) return fail(BM2F_ERR_INVALID, "null pointer");
+    int rc = gn_check(batch, tokens, channels, groups);
+    if (rc) return rc;
+    if (!aligned16(y) || !aligned16(out) || !aligned16(gamma) || !aligned16(beta) || out_batch_stride % 4 != 0)
+        return fail(BM2F_ERR_UNSUPPORTED, "token GroupNorm: tensors must be 16-byte aligned");
+    int sms = 0, cc = 0;
+    if ((rc = device_info(&sms, &cc))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double *sums = static_cast<double *>(workspace);
+    const int n_stats = batch * kGnGroups;
+    cudaError_t e = cudaMemsetAsync(sums, 0, static_cast<size_t>(n_stats) * 2 * sizeof(double), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(GroupNorm sums)");
+    const dim3 grid(gn_chunks(batch, tokens, sms), batch);
+    groupnorm_tokens_stats_kernel<<<grid, 256, 0, st>>>(static_cast<const float *>(y), sums, tokens);
+    groupnorm_tokens_finalize_kernel<<<(n_stats + 127) / 128, 128, 0, st>>>(
+        sums, static_cast<float *>(mean), static_cast<float *>(rstd), n_stats, static_cast<double>(tokens) * (kGnC / kGnGroups),
+        eps, 1);
+    groupnorm_tokens_apply_kernel<<<grid, 256, 0, st>>>(static_cast<const float *>(y), static_cast<const float *>(mean),
+                                                        static_cast<const float *>(rstd), static_cast<const float *>(gamma),
+                                                        static_cast<const float *>(beta), static_cast<float *>(out),
+                                                        static_cast<long long>(out_batch_stride), tokens);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "launch groupnorm_tokens kernels");
+    g_launches.fetch_add(3, std::memory_order_relaxed);
+    return BM2F_OK;
+}
+
+int bm2f_groupnorm_tokens_backward(const void *grad_out, int64_t grad_batch_stride, const void *y, const void *mean,
+                                   const void *rstd, const void *gamma, void *grad_y, void *grad_gamma, void *grad_beta,
+                                   void *workspace, int batch, int tokens, int channels, int groups, void *stream)
+{
+    if (!grad_out || !y || !mean || !rstd || !gamma || !grad_y || !grad_gamma || !grad_beta || !workspace)
+        return fail(BM2F_ERR_INVALID, "null pointer");
+    int rc = gn_check(batch, tokens, channels, groups);
+    if (rc) return rc;
+    if (!aligned16(grad_out) || !aligned16(y) || !aligned16(grad_y) || !aligned16(gamma) || grad_batch_stride % 4 != 0)
+        return fail(BM2F_ERR_UNSUPPORTED, "token GroupNorm: tensors must be 16-byte aligned");
+    int sms = 0, cc = 0;
+    if ((rc = device_info(&sms, &cc))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int n_stats = batch * kGnGroups;
+    double *sums = static_cast<double *>(workspace);
+    float *c1 = reinterpret_cast<float *>(sums + static_cast<size_t>(n_stats) * 2);
+    float *c2 = c1 + n_stats;
+    cudaError_t e = cudaMemsetAsync(sums, 0, static_cast<size_t>(n_stats) * 2 * sizeof(double), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(grad_gamma, 0, kGnC * sizeof(float), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(grad_beta, 0, kGnC * sizeof(float), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(GroupNorm backward sums)");
+    const dim3 grid(gn_chunks(batch, tokens, sms), batch);
+    groupnorm_tokens_bwd_stats_kernel<<<grid, 256, 0, st>>>(
+        static_cast<const float *>(grad_out), static_cast<long long>(grad_batch_stride), static_cast<const float *>(y),
+        static_cast<const float *>(mean), static_cast<const float *>(rstd), static_cast<const float *>(gamma), sums,
+        static_cast<float *>(grad_gamma), static_cast<float *>(grad_beta), tokens);
+    groupnorm_tokens_finalize_kernel<<<(n_stats + 127) / 128, 128, 0, st>>>(
+        sums, c1, c2, n_stats, static_cast<double>(tokens) * (kGnC / kGnGroups), 0.f, 0);
+    groupnorm_tokens_bwd_apply_kernel<<<grid, 256, 0, st>>>(
+        static_cast<const float *>(grad_out), static_cast<long long>(grad_batch_stride), static_cast<const float *>(y),
+        static_cast<const float *>(mean), static_cast<const float *>(rstd), c1, c2, static_cast<const float *>(gamma),
+        static_cast<float *>(grad_y), tokens);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "launch groupnorm_tokens backward kernels");
+    g_launches.fetch_add(3, std::memory_order_relaxed);
+    return BM2F_OK;
+}
+
+int bm2f_sine_position_embedding(void *out, int height, int width, int num_pos_feats, float temperature, float scale,
+                                 int normalize, void *stream)
+{
+    if (!out) return fail(BM2F_ERR_INVALID, "null pointer");
+    if (height <= 0 || width <= 0 || num_pos_feats <= 0) return fail(BM2F_ERR_INVALID, "height / width / num_pos_feats must be positive");
+    int sms = 0, cc = 0;
+    const int rc = device_info(&sms, &cc);
+    if (rc) return rc;
+    const size_t total = static_cast<size_t>(height) * width * 2 * num_pos_feats;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > static_cast<size_t>(sms) * 8) blocks = static_cast<size_t>(sms) * 8;
+    sine_pos_embed_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<float *>(out), height, width, num_pos_feats, temperature, scale, normalize);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "launch sine_pos_embed_kernel");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return BM2F_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Host-buffer entry: chunked, double-buffered H2D -> kernels -> D2H.
 // ---------------------------------------------------------------------------------------------
 namespace {
+constexpr int kHostSlots = 3;   // chunks in flight: one uploading, one computing / downloading, one draining
 struct HostPath {
     std::mutex mu;
     int dev = -1;
-    cudaStream_t streams[2] = {nullptr, nullptr};
-    void *ws[2] = {nullptr, nullptr};
+    cudaStream_t streams[kHostSlots] = {};
+    void *ws[kHostSlots] = {};
     size_t ws_bytes = 0;
     int64_t *tabs = nullptr;  // shapes (2L) + start (L)
 } g_host;
@@ -811,8 +942,9 @@ int bm2f_msda_forward_backward_host(const void *value_host, const int64_t *spati
     const size_t l_img = static_cast<size_t>(d.Lq) * d.M * d.L * d.P * 2 * el;
     const size_t a_img = static_cast<size_t>(d.Lq) * d.M * d.L * d.P * el;
 
-    // images per chunk: aim at >= 4 chunks so the two streams overlap copies and kernels
-    int chunk = d.N >= 8 ? d.N / 8 : 1;
+    // images per chunk: up to 16 chunks per call keep the pipeline's fill / drain (one chunk's upload at the start, one
+    // chunk's download at the end are not overlapped) at ~1/16 of the call
+    int chunk = d.N >= 16 ? d.N / 16 : 1;
     const size_t slot_bytes = static_cast<size_t>(chunk) *
                               (align256(v_img) + align256(l_img) + align256(a_img) + align256(o_img) +
                                (bwd ? align256(o_img) + align256(gv_img) + align256(l_img) + align256(a_img) : 0)) +
@@ -823,7 +955,7 @@ int bm2f_msda_forward_backward_host(const void *value_host, const int64_t *spati
     cudaError_t ce = cudaGetDevice(&dev);
     if (ce != cudaSuccess) return cuda_fail(ce, "cudaGetDevice");
     if (g_host.dev != dev || g_host.ws_bytes < slot_bytes) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kHostSlots; ++i) {
             if (g_host.ws[i]) cudaFree(g_host.ws[i]);
             g_host.ws[i] = nullptr;
             if (!g_host.streams[i] || g_host.dev != dev) {
@@ -856,8 +988,12 @@ int bm2f_msda_forward_backward_host(const void *value_host, const int64_t *spati
     auto hp = [](const void *base, size_t off) { return static_cast<const char *>(base) + off; };
     auto hpw = [](void *base, size_t off) { return static_cast<char *>(base) + off; };
 
+    // Per chunk, on its slot's stream: ALL uploads first (grad_output included), then both kernels, then all downloads.
+    // Copy engines serve requests in issue order, so an upload queued between a chunk's kernels and its downloads would
+    // hold back the next chunk's uploads (head-of-line blocking) — with this order the H2D engine, the SMs and the D2H
+    // engine each work on a different chunk.
     int slot = 0;
-    for (int b0 = 0; b0 < d.N; b0 += chunk, slot ^= 1) {
+    for (int b0 = 0; b0 < d.N; b0 += chunk, slot = (slot + 1) % kHostSlots) {
         const int nb = (d.N - b0 < chunk) ? d.N - b0 : chunk;
         cudaStream_t st = g_host.streams[slot];
         char *w = static_cast<char *>(g_host.ws[slot]);
@@ -871,15 +1007,17 @@ int bm2f_msda_forward_backward_host(const void *value_host, const int64_t *spati
         BM2F_CP(dv, hp(value_host, b0 * v_img), nb * v_img, cudaMemcpyHostToDevice, "H2D value")
         BM2F_CP(dl, hp(sampling_loc_host, b0 * l_img), nb * l_img, cudaMemcpyHostToDevice, "H2D sampling_loc")
         BM2F_CP(da, hp(attn_weight_host, b0 * a_img), nb * a_img, cudaMemcpyHostToDevice, "H2D attn_weight")
+        if (bwd) BM2F_CP(dgo, hp(grad_output_host, b0 * o_img), nb * o_img, cudaMemcpyHostToDevice, "H2D grad_output")
         rc = bm2f_msda_forward(dv, d_shapes, d_start, dl, da, dout, nb, d.S, d.M, d.D, d.L, d.Lq, d.P, dtype, tuning,
                                st);
         if (rc) return rc;
-        if (output_host) BM2F_CP(hpw(output_host, b0 * o_img), dout, nb * o_img, cudaMemcpyDeviceToHost, "D2H output")
         if (bwd) {
-            BM2F_CP(dgo, hp(grad_output_host, b0 * o_img), nb * o_img, cudaMemcpyHostToDevice, "H2D grad_output")
             rc = bm2f_msda_backward(dv, d_shapes, d_start, dl, da, dgo, dgv, dgl, dga, nb, d.S, d.M, d.D, d.L, d.Lq,
                                     d.P, dtype, tuning, st);
             if (rc) return rc;
+        }
+        if (output_host) BM2F_CP(hpw(output_host, b0 * o_img), dout, nb * o_img, cudaMemcpyDeviceToHost, "D2H output")
+        if (bwd) {
             if (grad_value_host)
                 BM2F_CP(hpw(grad_value_host, b0 * gv_img), dgv, nb * gv_img, cudaMemcpyDeviceToHost, "D2H grad_value")
             if (grad_sampling_loc_host)
@@ -891,7 +1029,7 @@ int bm2f_msda_forward_backward_host(const void *value_host, const int64_t *spati
         }
 #undef BM2F_CP
     }
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < kHostSlots; ++i)
         if ((ce = cudaStreamSynchronize(g_host.streams[i])) != cudaSuccess) return cuda_fail(ce, "host-path sync");
     return BM2F_OK;
 }

@@ -431,6 +431,79 @@ std::vector<at::Tensor> add_layernorm_backward(const at::Tensor &grad_y, const a
     return {dz, dgamma, dbeta};
 }
 
+// ---- pixel-decoder glue (msdeformattn.py:214-227, 316-325; position_encoding.py:29-52) -------------------------------
+at::Tensor transpose_batched(const at::Tensor &x)
+{
+    TORCH_CHECK(x.is_cuda(), "transpose_batched: CUDA tensors only (no CPU path)");
+    TORCH_CHECK(x.scalar_type() == at::kFloat && x.dim() == 3, "transpose_batched: float32 (batch, rows, cols)");
+    const c10::cuda::CUDAGuard guard(x.device());
+    auto xc = x.contiguous();
+    auto out = at::empty({xc.size(0), xc.size(2), xc.size(1)}, xc.options());
+    const int rc = bm2f_transpose_batched(xc.data_ptr(), out.data_ptr(), static_cast<int>(xc.size(0)),
+                                          static_cast<int>(xc.size(1)), static_cast<int>(xc.size(2)),
+                                          at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == BM2F_OK, "transpose_batched: ", bm2f_msda_last_error());
+    return out;
+}
+
+// y (batch, tokens, 256) -> out[:, token_offset : token_offset + tokens, :] of the (batch, S, 256) encoder input
+std::vector<at::Tensor> groupnorm_tokens_forward(const at::Tensor &y, const at::Tensor &gamma, const at::Tensor &beta,
+                                                 double eps, at::Tensor &out, int64_t token_offset)
+{
+    TORCH_CHECK(y.is_cuda() && out.is_cuda(), "groupnorm_tokens: CUDA tensors only (no CPU path)");
+    TORCH_CHECK(y.scalar_type() == at::kFloat && y.dim() == 3 && y.size(2) == 256 && y.is_contiguous(),
+                "groupnorm_tokens: y must be contiguous float32 (batch, tokens, 256)");
+    TORCH_CHECK(out.scalar_type() == at::kFloat && out.dim() == 3 && out.size(2) == 256 && out.is_contiguous() &&
+                    out.size(0) == y.size(0) && token_offset >= 0 && token_offset + y.size(1) <= out.size(1),
+                "groupnorm_tokens: out must be contiguous float32 (batch, S, 256) holding the level's token range");
+    const c10::cuda::CUDAGuard guard(y.device());
+    const int batch = static_cast<int>(y.size(0)), tokens = static_cast<int>(y.size(1));
+    auto mean = at::empty({batch, 32}, y.options());
+    auto rstd = at::empty({batch, 32}, y.options());
+    auto ws = at::empty({static_cast<int64_t>(bm2f_groupnorm_tokens_workspace_bytes(batch))}, y.options().dtype(at::kByte));
+    const int rc = bm2f_groupnorm_tokens_forward(
+        y.data_ptr(), gamma.contiguous().data_ptr(), beta.contiguous().data_ptr(), static_cast<float>(eps),
+        out.data_ptr<float>() + token_offset * 256, out.size(1) * 256, mean.data_ptr(), rstd.data_ptr(), ws.data_ptr(), batch,
+        tokens, 256, 32, at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == BM2F_OK, "groupnorm_tokens_forward: ", bm2f_msda_last_error());
+    return {mean, rstd};
+}
+
+std::vector<at::Tensor> groupnorm_tokens_backward(const at::Tensor &grad_out, int64_t token_offset, const at::Tensor &y,
+                                                  const at::Tensor &mean, const at::Tensor &rstd, const at::Tensor &gamma)
+{
+    TORCH_CHECK(grad_out.is_cuda() && grad_out.scalar_type() == at::kFloat && grad_out.dim() == 3 &&
+                    grad_out.size(2) == 256 && grad_out.is_contiguous() && grad_out.size(0) == y.size(0) &&
+                    token_offset >= 0 && token_offset + y.size(1) <= grad_out.size(1),
+                "groupnorm_tokens_backward: grad_out must be contiguous float32 (batch, S, 256)");
+    const c10::cuda::CUDAGuard guard(y.device());
+    const int batch = static_cast<int>(y.size(0)), tokens = static_cast<int>(y.size(1));
+    auto dy = at::empty_like(y);
+    auto dgamma = at::empty({256}, y.options());
+    auto dbeta = at::empty({256}, y.options());
+    auto ws = at::empty({static_cast<int64_t>(bm2f_groupnorm_tokens_workspace_bytes(batch))}, y.options().dtype(at::kByte));
+    const int rc = bm2f_groupnorm_tokens_backward(
+        grad_out.data_ptr<float>() + token_offset * 256, grad_out.size(1) * 256, y.data_ptr(), mean.data_ptr(),
+        rstd.data_ptr(), gamma.contiguous().data_ptr(), dy.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(),
+        batch, tokens, 256, 32, at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == BM2F_OK, "groupnorm_tokens_backward: ", bm2f_msda_last_error());
+    return {dy, dgamma, dbeta};
+}
+
+at::Tensor sine_position_embedding(const at::Tensor &like, int64_t height, int64_t width, int64_t num_pos_feats,
+                                   double temperature, double scale, bool normalize)
+{
+    TORCH_CHECK(like.is_cuda(), "sine_position_embedding: CUDA device only (no CPU path)");
+    const c10::cuda::CUDAGuard guard(like.device());
+    auto out = at::empty({height * width, 2 * num_pos_feats}, like.options().dtype(at::kFloat));
+    const int rc = bm2f_sine_position_embedding(out.data_ptr(), static_cast<int>(height), static_cast<int>(width),
+                                                static_cast<int>(num_pos_feats), static_cast<float>(temperature),
+                                                static_cast<float>(scale), normalize ? 1 : 0,
+                                                at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == BM2F_OK, "sine_position_embedding: ", bm2f_msda_last_error());
+    return out;
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
@@ -450,6 +523,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("zero_masked_rows_", &zero_masked_rows_, "in-place masked_fill(mask[..., None], 0) touching only masked rows");
     m.def("add_layernorm_forward", &add_layernorm_forward, "z = x + r, y = LayerNorm(z)");
     m.def("add_layernorm_backward", &add_layernorm_backward);
+    m.def("transpose_batched", &transpose_batched, "(B, R, C) -> (B, C, R)");
+    m.def("groupnorm_tokens_forward", &groupnorm_tokens_forward, "GroupNorm(32, 256) on token rows, written into the encoder input");
+    m.def("groupnorm_tokens_backward", &groupnorm_tokens_backward);
+    m.def("sine_position_embedding", &sine_position_embedding, "PositionEmbeddingSine for an all-False mask, token-major");
     m.def("abi_version", []() { return bm2f_msda_abi_version(); });
     m.def("build_info", []() { return std::string(bm2f_msda_build_info()); });
     m.def("launch_count", []() { return bm2f_msda_launch_count(); });

@@ -3,8 +3,8 @@
 
 Same class names, constructor arguments, sub-module names (hence state-dict keys: `self_attn.*`, `norm1`,
 `linear1`, `linear2`, `norm2`, `level_embed`, `encoder.layers.N.*`) and forward signatures as the reference, so
-checkpoints load.  Detectron2 is not needed for this part; `MSDeformAttnPixelDecoder` itself (input
-projections, FPN tail, registry) stays out of scope.
+checkpoints load.  Detectron2 is not needed for this part; the decoder around it (input projections, position
+embedding, FPN tail) is mirrored in `bm2f_b200.pixel_decoder`, which enters through `forward_tokens`.
 
 On CUDA float32 with dropout 0 (every config that selects this decoder sets DROPOUT 0.0) the layer runs:
     q = src + pos                         torch add
@@ -165,4 +165,17 @@ class MSDeformAttnTransformerEncoderOnly(nn.Module):
         valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
         memory = self.encoder(src_flatten, spatial_shapes, level_start_index, valid_ratios, lvl_pos_embed_flatten,
                               mask_flatten, spatial_shapes_list=shapes_list)
+        return memory, spatial_shapes, level_start_index
+
+    def forward_tokens(self, src_flatten, lvl_pos_embed_flatten, shapes_list):
+        """Token-major entry used by `bm2f_b200.pixel_decoder`: the caller already holds the concatenated encoder input
+        (N, S, C) and the level position embedding (1 or N, S, C), so the flatten / transpose / cat of `forward`
+        (msdeformattn.py:66-82) is skipped.  Masks are all-False in this decoder (msdeformattn.py:62), hence valid
+        ratios are 1 and no padding mask is passed (masked_fill with an all-False mask is the identity)."""
+        n, device = src_flatten.shape[0], src_flatten.device
+        spatial_shapes = torch.as_tensor(shapes_list, dtype=torch.long, device=device)
+        level_start_index = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
+        valid_ratios = torch.ones((n, len(shapes_list), 2), dtype=torch.float32, device=device)
+        memory = self.encoder(src_flatten, spatial_shapes, level_start_index, valid_ratios, lvl_pos_embed_flatten,
+                              None, spatial_shapes_list=list(shapes_list))
         return memory, spatial_shapes, level_start_index

@@ -212,6 +212,38 @@ int bm2f_add_layernorm_backward(const void *grad_y, const void *z, const void *m
 int bm2f_zero_masked_rows(void *x, const void *row_mask, int rows, int channels, void *stream);
 
 /*
+ * Pixel-decoder glue either side of the encoder, token-major float32 rows of 256 channels.
+ *
+ * bm2f_transpose_batched: in (batch, rows, cols) -> out (batch, cols, rows).  NCHW backbone feature
+ *   (N, C, H*W) -> token rows (N, H*W, C) for the 1x1 `input_proj` conv, which then is bm2f_linear_forward
+ *   (msdeformattn.py:214-227, 321), and the reverse for its input gradient.
+ *
+ * bm2f_groupnorm_tokens_forward: nn.GroupNorm(32, 256) (msdeformattn.py:217, 224) of y (batch, tokens, 256),
+ *   statistics over (tokens x 8 channels) per (image, group); row t of image n is written at
+ *   out + n * out_batch_stride + t * 256 (floats), i.e. straight into this level's slice of the concatenated
+ *   (N, S, 256) encoder input (replaces flatten(2).transpose(1, 2) + torch.cat, msdeformattn.py:73-80).
+ *   mean / rstd: (batch, 32) float32, kept for backward.  workspace: batch * 32 * 2 doubles.
+ * bm2f_groupnorm_tokens_backward: grad_out rows at grad_out + n * grad_batch_stride + t * 256;
+ *   grad_y (batch, tokens, 256) contiguous; grad_gamma / grad_beta (256) are zeroed, then accumulated.
+ *   workspace: batch * 32 * 2 doubles + batch * 32 * 2 floats (bm2f_groupnorm_tokens_workspace_bytes).
+ *
+ * bm2f_sine_position_embedding: PositionEmbeddingSine(num_pos_feats, temperature, normalize, scale) for an
+ *   all-False mask (transformer_decoder/position_encoding.py:29-52; msdeformattn.py:322 always passes none):
+ *   out (height * width, 2 * num_pos_feats) token-major, identical for every image of the batch.
+ */
+int bm2f_transpose_batched(const void *in, void *out, int batch, int rows, int cols, void *stream);
+size_t bm2f_groupnorm_tokens_workspace_bytes(int batch);
+int bm2f_groupnorm_tokens_forward(const void *y, const void *gamma, const void *beta, float eps, void *out,
+                                  int64_t out_batch_stride, void *mean, void *rstd, void *workspace, int batch,
+                                  int tokens, int channels, int groups, void *stream);
+int bm2f_groupnorm_tokens_backward(const void *grad_out, int64_t grad_batch_stride, const void *y, const void *mean,
+                                   const void *rstd, const void *gamma, void *grad_y, void *grad_gamma,
+                                   void *grad_beta, void *workspace, int batch, int tokens, int channels, int groups,
+                                   void *stream);
+int bm2f_sine_position_embedding(void *out, int height, int width, int num_pos_feats, float temperature, float scale,
+                                 int normalize, void *stream);
+
+/*
  * Host-buffer convenience used for end-to-end measurement and by non-torch callers:
  * every pointer is a HOST pointer (pinned memory gives full PCIe rate).  The library copies
  * the inputs to a device workspace it owns for the duration of the call, runs forward and,

@@ -188,3 +188,23 @@ def fused_backward(value, shapes, start, ref, offsets, logits, grad_out):
     g = ga.reshape(N, Lq, M, L * P)
     g_logits = (a * (g - (a * g).sum(-1, keepdims=True))).reshape(N, Lq, M, L, P)
     return gv, g_off, g_logits
+
+
+def sine_position_embedding(height, width, num_pos_feats=128, temperature=10000.0, scale=2 * np.pi, normalize=True):
+    """numpy restatement of PositionEmbeddingSine.forward for an all-False mask
+    (reference: transformer_decoder/position_encoding.py:29-52), float32 arithmetic in the reference's order.
+    Returns (2 * num_pos_feats, height, width) like the reference's `pos[0]`."""
+    f32 = np.float32
+    y_embed = np.cumsum(np.ones((height, width), dtype=f32), axis=0, dtype=f32)
+    x_embed = np.cumsum(np.ones((height, width), dtype=f32), axis=1, dtype=f32)
+    if normalize:
+        eps = f32(1e-6)
+        y_embed = y_embed / (y_embed[-1:, :] + eps) * f32(scale)
+        x_embed = x_embed / (x_embed[:, -1:] + eps) * f32(scale)
+    dim_t = np.arange(num_pos_feats, dtype=f32)
+    dim_t = np.power(f32(temperature), (2 * np.floor(dim_t / 2) / f32(num_pos_feats)).astype(f32)).astype(f32)
+    pos_x = x_embed[:, :, None] / dim_t
+    pos_y = y_embed[:, :, None] / dim_t
+    pos_x = np.stack((np.sin(pos_x[:, :, 0::2]), np.cos(pos_x[:, :, 1::2])), axis=3).reshape(height, width, -1)
+    pos_y = np.stack((np.sin(pos_y[:, :, 0::2]), np.cos(pos_y[:, :, 1::2])), axis=3).reshape(height, width, -1)
+    return np.concatenate((pos_y, pos_x), axis=2).transpose(2, 0, 1).astype(f32)
