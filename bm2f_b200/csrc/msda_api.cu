@@ -74,6 +74,23 @@ int device_info(int *sms, int *cc_major)
     return BM2F_OK;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) function attribute: remember it per
+// (kernel, device ordinal).  A race only repeats the same idempotent call.
+template <auto Kernel>
+int ensure_dynamic_smem(int bytes, const char *what)
+{
+    static std::atomic<uint64_t> done{0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    if (dev < 0 || dev >= 64) return fail(BM2F_ERR_UNSUPPORTED, "device ordinal %d out of range", dev);
+    if ((done.load(std::memory_order_acquire) >> dev) & 1ull) return BM2F_OK;
+    e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return cuda_fail(e, what);
+    done.fetch_or(1ull << dev, std::memory_order_release);
+    return BM2F_OK;
+}
+
 // ---- TMA tensor maps ------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
@@ -522,12 +539,7 @@ int launch_linear(const LinearParams &p, const float *w_hi, const float *w_lo, c
     CUtensorMap my;
     if ((rc = make_map(&my, p.y, p.M, N, kGemmBlockM, 32, true))) return rc;
     constexpr int smem = linear_smem_bytes<NT, NH>();
-    static bool attr_set = false;   // idempotent; a race only repeats the same call
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(linear_tf32x3_kernel<NT, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(linear smem)");
-        attr_set = true;
-    }
+    if ((rc = ensure_dynamic_smem<&linear_tf32x3_kernel<NT, NH>>(smem, "cudaFuncSetAttribute(linear smem)"))) return rc;
     const int grid = (p.M + kGemmBlockM - 1) / kGemmBlockM;
     linear_tf32x3_kernel<NT, NH><<<grid, kGemmThreads, smem, st>>>(p, mh, ml, my);
     const cudaError_t e = cudaGetLastError();
@@ -544,13 +556,8 @@ int launch_linear_persistent(const LinearParams &p, const float *w_hi, const flo
     if ((rc = make_map(&ml, w_lo, p.N, p.K, NT, kGemmBlockK, true))) return rc;
     if ((rc = make_map(&my, p.y, p.M, p.N, 32, 32, true))) return rc;      // one 32 x 32 box per epilogue warp
     constexpr int smem = linear_persistent_smem_bytes<NT>();
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(linear_tf32x3_persistent_kernel<NT>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(persistent linear smem)");
-        attr_set = true;
-    }
+    if ((rc = ensure_dynamic_smem<&linear_tf32x3_persistent_kernel<NT>>(smem, "cudaFuncSetAttribute(persistent linear smem)")))
+        return rc;
     const int tiles = ((p.M + kGemmBlockM - 1) / kGemmBlockM) * p.slices;
     const int grid = tiles < sms ? tiles : sms;
     linear_tf32x3_persistent_kernel<NT><<<grid, kGemmThreadsPersistent, smem, st>>>(p, mh, ml, my);
@@ -649,6 +656,9 @@ int linear_dw_common(const void *grad_y, const void *x, void *grad_weight, void 
         return fail(BM2F_ERR_UNSUPPORTED, "weight-gradient GEMM needs in_features to be a multiple of 256 (got %d)",
                     in_features);
     if (out_features > 8192 || in_features > 8192) return fail(BM2F_ERR_UNSUPPORTED, "layer too large");
+    // split + 100 * c (A/B knob): cap the rows one CTA reduces at 256 * c, i.e. shorten the TMEM accumulation chain
+    int row_cap = 0;
+    if (split >= 100) { row_cap = (split / 100) * 256; split %= 100; }
     if (split != 1 && split != 3) return fail(BM2F_ERR_INVALID, "split must be 3 (tf32x3) or 1 (single TF32 pass)");
     int sms = 0, cc = 0;
     int rc = device_info(&sms, &cc);
@@ -662,6 +672,7 @@ int linear_dw_common(const void *grad_y, const void *x, void *grad_weight, void 
     const int k_slices = in_features / 256;
     int chunks = sms / (n_tiles * k_slices);
     if (chunks < 1) chunks = 1;
+    if (row_cap > 0 && (rows + chunks - 1) / chunks > row_cap) chunks = (rows + row_cap - 1) / row_cap;
     int rows_per_chunk = ((rows + chunks - 1) / chunks + 31) / 32 * 32;
     chunks = (rows + rows_per_chunk - 1) / rows_per_chunk;
     LinearDwParams p{};
@@ -669,12 +680,7 @@ int linear_dw_common(const void *grad_y, const void *x, void *grad_weight, void 
     p.dw = static_cast<float *>(grad_weight); p.db = static_cast<float *>(grad_bias);
     p.M = rows; p.N = out_features; p.ldx = in_features; p.rows_per_chunk = rows_per_chunk; p.split = split;
     constexpr int smem = linear_dw_smem_bytes();
-    static bool attr_set = false;
-    if (!attr_set) {
-        e = cudaFuncSetAttribute(linear_dw_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dW smem)");
-        attr_set = true;
-    }
+    if ((rc = ensure_dynamic_smem<&linear_dw_tf32x3_kernel>(smem, "cudaFuncSetAttribute(dW smem)"))) return rc;
     linear_dw_tf32x3_kernel<<<dim3(n_tiles, chunks, k_slices), kDwThreads, smem, st>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "launch linear_dw_tf32x3_kernel");

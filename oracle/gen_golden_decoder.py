@@ -17,6 +17,14 @@ activation; get_norm("GN") = GroupNorm(32, C); c2_xavier_fill = kaiming_uniform(
 Parameters are NOT stored: both sides fill the state dict with `fill_state_dict` below (numpy Generator keyed by the
 sorted parameter names), which keeps the fixture small.  The GPU test imports this file for that function only.
 
+Kinks.  The network is piecewise smooth: ReLU (FFN, FPN output conv) and bilinear sampling have one-sided derivatives
+at pre-activation 0 / integer pixel coordinates, and two float32 implementations may legitimately land on different
+sides when a value is within ~1e-5 of a kink — one flipped unit then perturbs every upstream gradient (rank-1).  With
+~10^5 units some always are that close, so `condition()` moves a handful of BIASES (`linear1.bias`,
+`sampling_offsets.bias`, `layer_1.norm.bias`; each shifted by < 0.5) until every ReLU input is >= 2e-4 and every
+sampling coordinate >= 1e-3 px away from its kink in the REFERENCE's forward.  The reference code is untouched; the
+adjusted biases are stored in the fixture (`cond::<name>`) and loaded by both sides after `fill_state_dict`.
+
 Usage (here, where /root/reference exists):  python oracle/gen_golden_decoder.py
 """
 from __future__ import annotations
@@ -97,6 +105,115 @@ GRAD_KEYS = ["transformer.level_embed", "input_proj.0.0.weight", "input_proj.0.0
              "mask_features.weight"]
 
 
+def _best_shift(vals, period, lo, hi, steps=4001):
+    """Shift d in [lo, hi] maximising the distance of every vals + d from the kink set {0} (period None) or the
+    integers (period 1).  vals: (rows,) float64.  Returns (d, margin)."""
+    grid = np.linspace(lo, hi, steps)
+    x = vals[None, :] + grid[:, None]
+    dist = np.abs(x) if period is None else np.abs(x - np.round(x))
+    m = dist.min(1)
+    i = int(np.argmax(m - 1e-9 * np.abs(grid)))          # smallest |shift| among (near-)ties
+    return float(grid[i]), float(m[i])
+
+
+def condition(dec, feats, relu_margin=2e-4, loc_margin=1e-3):
+    """Move biases so that no ReLU input / sampling coordinate of the reference's forward sits next to a kink.
+    Layer by layer in data-flow order, re-running the reference forward after each adjustment."""
+    layers = dec.transformer.encoder.layers
+    report, changed = [], {}
+
+    def run_with_hook(module, fn):
+        box = {}
+        def hook(mod, args, out):            # must return None: a returned value would replace the module's output
+            box["v"] = fn(mod, args, out)
+        h = module.register_forward_hook(hook)
+        with torch.no_grad():
+            dec.forward_features(feats)
+        h.remove()
+        return box["v"]
+
+    for li, layer in enumerate(layers):
+        attn = layer.self_attn
+        # 1. sampling coordinates: pix = ref * (W_l, H_l) - 0.5 + offset  (ops/modules/ms_deform_attn.py:101-109)
+        def grab(mod, args, out):
+            query, ref, _, shapes = args[0], args[1], args[2], args[3]
+            off = mod.sampling_offsets(query)
+            return off.double().numpy(), ref.double().numpy(), shapes.numpy()
+        off, ref, shapes = run_with_hook(attn, grab)
+        N, Lq, _ = off.shape
+        M, L, P = attn.n_heads, attn.n_levels, attn.n_points
+        off = off.reshape(N, Lq, M, L, P, 2)
+        wh = np.stack([shapes[:, 1], shapes[:, 0]], -1).astype(np.float64)            # (L, 2) = (W, H)
+        pix = ref[:, :, None, :, None, :] * wh[None, None, None, :, None, :] - 0.5 + off
+        bias = attn.sampling_offsets.bias.detach().double().numpy().reshape(M, L, P, 2).copy()
+        worst = 1.0
+        for m in range(M):
+            for l in range(L):
+                for pt in range(P):
+                    for c in range(2):
+                        d, mg = _best_shift(pix[:, :, m, l, pt, c].reshape(-1), 1, -0.5, 0.5)
+                        bias[m, l, pt, c] += d
+                        worst = min(worst, mg)
+        assert worst >= loc_margin, worst
+        with torch.no_grad():
+            attn.sampling_offsets.bias.copy_(torch.from_numpy(bias.reshape(-1).astype(np.float32)))
+        report.append((f"layer {li} sampling coordinates", worst))
+        # 2. FFN pre-activations (msdeformattn.py:116)
+        pre = run_with_hook(layer.linear1, lambda mod, args, out: out.double().numpy())
+        pre = pre.reshape(-1, pre.shape[-1])
+        b = layer.linear1.bias.detach().double().numpy().copy()
+        worst = 1.0
+        for u in range(pre.shape[1]):
+            d, mg = _best_shift(pre[:, u], None, -0.3, 0.3)
+            b[u] += d
+            worst = min(worst, mg)
+        assert worst >= relu_margin, worst
+        with torch.no_grad():
+            layer.linear1.bias.copy_(torch.from_numpy(b.astype(np.float32)))
+        report.append((f"layer {li} FFN ReLU inputs", worst))
+    # 3. FPN output conv: conv -> GroupNorm -> ReLU (msdeformattn.py:268-277); the norm's bias is added last
+    for idx in range(dec.num_fpn_levels):
+        conv = getattr(dec, f"layer_{idx + 1}")
+        pre = run_with_hook(conv.norm, lambda mod, args, out: out.double().numpy())
+        b = conv.norm.bias.detach().double().numpy().copy()
+        worst = 1.0
+        for ch in range(pre.shape[1]):
+            d, mg = _best_shift(pre[:, ch].reshape(-1), None, -0.3, 0.3)
+            b[ch] += d
+            worst = min(worst, mg)
+        assert worst >= relu_margin, worst
+        with torch.no_grad():
+            conv.norm.bias.copy_(torch.from_numpy(b.astype(np.float32)))
+        report.append((f"layer_{idx + 1} ReLU inputs", worst))
+    # verify on a final forward (float32 rounding of the stored biases included) and collect what changed
+    final = []
+    for li, layer in enumerate(layers):
+        pre = run_with_hook(layer.linear1, lambda mod, args, out: out.double().numpy())
+        final.append((f"layer {li} FFN", float(np.abs(pre).min())))
+        changed[f"transformer.encoder.layers.{li}.linear1.bias"] = layer.linear1.bias.detach().clone()
+        changed[f"transformer.encoder.layers.{li}.self_attn.sampling_offsets.bias"] = \
+            layer.self_attn.sampling_offsets.bias.detach().clone()
+    for idx in range(dec.num_fpn_levels):
+        conv = getattr(dec, f"layer_{idx + 1}")
+        pre = run_with_hook(conv.norm, lambda mod, args, out: out.double().numpy())
+        final.append((f"layer_{idx + 1}", float(np.abs(pre).min())))
+        changed[f"layer_{idx + 1}.norm.bias"] = conv.norm.bias.detach().clone()
+    for name, mg in report + final:
+        print(f"  kink margin  {name:34s} {mg:.3e}")
+    assert min(m for _, m in final) >= 0.5 * relu_margin
+    return changed
+
+
+def load_conditioned(module, npz):
+    """Apply the fixture's adjusted biases (`cond::<name>`) on top of `fill_state_dict`."""
+    sd = module.state_dict()
+    for k in npz.files:
+        if k.startswith("cond::"):
+            sd[k[6:]] = torch.from_numpy(np.asarray(npz[k], dtype=np.float32)).to(sd[k[6:]].device)
+    module.load_state_dict(sd)
+    return module
+
+
 def install_stubs():
     ShapeSpec = namedtuple("ShapeSpec", ["channels", "height", "width", "stride"], defaults=(None, None, None, None))
 
@@ -171,6 +288,7 @@ def main():
     fill_state_dict(dec, case["seed"])
     dec.train()
     feats = make_features(case)
+    conditioned = condition(dec, feats)
     for v in feats.values():
         v.requires_grad_(True)
     mask_features, out0, multi = dec.forward_features(feats)
@@ -186,6 +304,8 @@ def main():
         blob[f"grad_feature_{k}"] = v.grad
     for k in GRAD_KEYS:
         blob["grad_param::" + k] = params[k].grad
+    for k, v in conditioned.items():
+        blob["cond::" + k] = v
     # the position embedding on its own (reference PositionEmbeddingSine, lowest level and an odd-sized one)
     pe = ref.PositionEmbeddingSine(128, normalize=True)
     blob["pos_2x3"] = pe(torch.zeros(1, 1, 2, 3))[0]

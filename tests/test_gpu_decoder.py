@@ -113,7 +113,8 @@ def _decoder(fused):
     import gen_golden_decoder as G
     from bm2f_b200.pixel_decoder import MSDeformAttnPixelDecoder, ShapeSpec
     shapes = {k: ShapeSpec(channels=c, stride=s) for k, (c, s) in G.CASE["input_shape"].items()}
-    dec = G.fill_state_dict(MSDeformAttnPixelDecoder(shapes, **G.CASE["kwargs"]), G.CASE["seed"]).to(DEV).train()
+    dec = G.fill_state_dict(MSDeformAttnPixelDecoder(shapes, **G.CASE["kwargs"]), G.CASE["seed"])
+    dec = G.load_conditioned(dec, np.load(GOLD)).to(DEV).train()      # biases moved away from ReLU / bilinear kinks
     dec.fused = fused
     for m in dec.modules():
         if hasattr(m, "fused") and m is not dec:
@@ -149,8 +150,10 @@ def fp32_convs():
 def test_pixel_decoder_matches_reference_golden(msda, fp32_convs, fused):
     """Whole decoder (input_proj, position embedding, 2 encoder layers, FPN tail), forward and backward, against the
     reference's own classes run on the CPU in float32.  fused=False runs the reference op sequence around the sm_100a
-    attention op, fused=True the glue / encoder kernels.  Tolerances: forward 1e-4 of the output scale (two fp32
-    implementations of a 2-layer network; the op itself is checked to 1e-5 in test_gpu_parity), gradients 1e-3."""
+    attention op, fused=True the glue / encoder kernels.  The fixture's biases keep every ReLU input and sampling
+    coordinate away from its kink (oracle/gen_golden_decoder.py:condition), so the gradients are comparable entry by
+    entry.  Tolerances: forward 5e-5 of the output scale (two fp32 implementations of the whole network; measured
+    <= 9e-6), gradients 1e-4 relative (north_star; measured <= 2.5e-5)."""
     dec, G = _decoder(fused)
     launches = msda.launch_count()
     got = _run_decoder(dec, G)
@@ -162,8 +165,8 @@ def test_pixel_decoder_matches_reference_golden(msda, fp32_convs, fused):
         worst[k] = rel_err(got[k], z[k])
     fwd = {k: v for k, v in worst.items() if not k.startswith("grad")}
     bwd = {k: v for k, v in worst.items() if k.startswith("grad")}
-    assert max(fwd.values()) <= 1e-4, fwd
-    assert max(bwd.values()) <= 1e-3, bwd
+    assert max(fwd.values()) <= 5e-5, fwd
+    assert max(bwd.values()) <= 1e-4, bwd
 
 
 def test_pixel_decoder_fused_equals_reference_sequence_channels_last(msda, fp32_convs):

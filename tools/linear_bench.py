@@ -42,3 +42,11 @@ for n in (256, 192, 96):
     e = ((MSDA.linear_tf32x3_backward_weight(g, x, 3, True)[0].double() - ref).abs().max() / ref.abs().max()).item()
     e32 = (((g.t() @ x).double() - ref).abs().max() / ref.abs().max()).item()
     print(f"dW N={n:3d} rows={rows}: cuBLAS fp32 (+sum) {t_fp32:.3f} ms (err {e32:.1e}) | tcgen05 tf32x3 {t_dw:.3f} ms (err {e:.1e}, {rows*(256+n)*4/1e9/t_dw*1e3:.0f} GB/s)")
+# ---- weight gradient: accumulation-chain length A/B (rows reduced per CTA capped at 256 * c)
+g = torch.randn(rows, 256, device=dev)
+ref = g.double().t() @ x.double()
+for c in (0, 16, 8, 4, 2):
+    sp = 3 + 100 * c
+    t_dw = t(lambda: MSDA.linear_tf32x3_backward_weight(g, x, sp, True))
+    e = ((MSDA.linear_tf32x3_backward_weight(g, x, sp, True)[0].double() - ref).abs().max() / ref.abs().max()).item()
+    print(f"dW N=256 rows={rows} row cap {256 * c if c else 'none'}: {t_dw:.3f} ms (err {e:.1e})")
