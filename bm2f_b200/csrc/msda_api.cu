@@ -154,7 +154,7 @@ cudaError_t launch_fused(bool bwd, const FastParams &p, const CUtensorMap &ml, c
                          cudaStream_t st)
 {
     constexpr int SW = 32, CPS = 1, G = 1;
-    constexpr int threads = (kNWarp + (TMA ? 1 : 0)) * 32;
+    constexpr int threads = (kNWarp + (TMA ? 2 : 0)) * 32;      // + TMA producer warp + prologue warp
     if (bwd)
         msda_bwd_fast_kernel<T, 4, L_, 4, SW, kNWarp, G, TMA, CPS, false, true><<<grid, threads, 0, st>>>(p, ml, mw);
     else
@@ -473,10 +473,12 @@ int bm2f_msda_fused_forward(const void *value, const int64_t *spatial_shapes, co
     const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
     int rc = check_common(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, d, dtype);
     if (rc) return rc;
-    if (!output || !reference_points) return fail(BM2F_ERR_INVALID, "null output / reference_points pointer");
+    if (!output) return fail(BM2F_ERR_INVALID, "null output pointer");
+    if (!reference_points && num_query != spatial_size)
+        return fail(BM2F_ERR_INVALID, "reference_points == NULL (pixel-centre reference points) needs num_query == spatial_size");
     const bm2f_msda_tuning_t t = resolve_tuning(tuning);
     if (!bm2f_msda_fused_supported(num_heads, channels, num_levels, num_point, dtype) ||
-        !fast_eligible(d, dtype, t, value, output, sampling_offsets, attn_logits) || !aligned16(reference_points) ||
+        !fast_eligible(d, dtype, t, value, output, sampling_offsets, attn_logits) ||
         (reinterpret_cast<uintptr_t>(reference_points) & 7u))
         return fail(BM2F_ERR_UNSUPPORTED,
                     "fused path covers D=32, M=8, P=4, L<=4 (f32) / L=3 (bf16), 16-byte aligned tensors "
@@ -501,8 +503,10 @@ int bm2f_msda_fused_backward(const void *value, const int64_t *spatial_shapes, c
     const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
     int rc = check_common(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, d, dtype);
     if (rc) return rc;
-    if (!grad_output || !grad_value || !grad_sampling_offsets || !grad_attn_logits || !reference_points)
-        return fail(BM2F_ERR_INVALID, "null gradient / reference_points pointer");
+    if (!grad_output || !grad_value || !grad_sampling_offsets || !grad_attn_logits)
+        return fail(BM2F_ERR_INVALID, "null gradient pointer");
+    if (!reference_points && num_query != spatial_size)
+        return fail(BM2F_ERR_INVALID, "reference_points == NULL (pixel-centre reference points) needs num_query == spatial_size");
     const bm2f_msda_tuning_t t = resolve_tuning(tuning);
     if (!bm2f_msda_fused_supported(num_heads, channels, num_levels, num_point, dtype) ||
         !fast_eligible(d, dtype, t, value, grad_value, sampling_offsets, attn_logits) || !aligned16(grad_output) ||

@@ -29,7 +29,8 @@ struct FastParams {
     const int64_t *start;        // (L)   device
     const float *loc;            // (N,Lq,M,L,P,2)        fused mode: raw sampling offsets in pixels
     const float *attn;           // (N,Lq,M,L,P)          fused mode: raw logits
-    const float *ref;            // (N,Lq,L,2) reference points, fused mode only (loc = ref + offset / (W,H))
+    const float *ref;            // (N,Lq,L,2) reference points, fused mode only (loc = ref + offset / (W,H));
+                                 // nullptr: pixel centres of the query's own level, computed in the kernel (Lq == S)
     const void *grad_out;        // (N,Lq,M,32)            bwd only
     void *out;                   // (N,Lq,M,32)            fwd only
     void *grad_value;            // (N,S,M,32) float32      bwd only
@@ -129,9 +130,12 @@ __device__ __forceinline__ void for_each_stage(const Tabs<L_> &t, const FastPara
         const int y_end = min(ql.Hq, (chunk + 1) * p.rows);
         const int x0 = strip * SW;
         const int nq_row = min(SW, ql.Wq - x0);
+        // geometry of the stage for the analytic reference points: level k, pixel row y, first column x0 when this
+        // level is walked as its true H x W grid; y = -1 when it is walked in raster order (or queries are no pyramid)
+        const bool grid = t.nql == L_ && ql.Wq == t.W[k] && ql.qstart == t.start[k];
         for (int y = chunk * p.rows; y < y_end; ++y, ++s) {
             const int q_base = ql.qstart + y * ql.Wq + x0;
-            f(s, b, m, q_base, min(nq_row, ql.qend - q_base));
+            f(s, b, m, q_base, min(nq_row, ql.qend - q_base), k, grid ? y : -1, x0);
         }
     }
 }
@@ -152,12 +156,14 @@ struct Ring {
     alignas(128) unsigned char data[kStages * Lay::kBytes];
     alignas(8) uint64_t full[kStages];
     alignas(8) uint64_t empty[kStages];
+    alignas(8) uint64_t ready[kStages];     // fused mode: prologue warp -> consumers
 
     __device__ __forceinline__ void init()
     {
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], WPG);
+            mbar_init(&ready[i], 1);
         }
         fence_mbar_init();
     }
@@ -169,12 +175,20 @@ struct Ring {
     {
         return reinterpret_cast<const float *>(data + slot * Lay::kBytes + Lay::kLocBytes) + qi * (L_ * P_);
     }
+    __device__ __forceinline__ float2 *loc_rw(int slot, int qi)
+    {
+        return reinterpret_cast<float2 *>(data + slot * Lay::kBytes) + qi * (L_ * P_);
+    }
+    __device__ __forceinline__ float *w_rw(int slot, int qi)
+    {
+        return reinterpret_cast<float *>(data + slot * Lay::kBytes + Lay::kLocBytes) + qi * (L_ * P_);
+    }
     // Producer (one lane): keep the ring full with the CTA's stage sequence.
     __device__ __forceinline__ void produce(const Tabs<L_> &t, const FastParams &p, const CUtensorMap *tm_loc,
                                             const CUtensorMap *tm_w)
     {
         constexpr int LP = L_ * P_;
-        for_each_stage<L_, SW>(t, p, [&](int s, int b, int m, int q_base, int) {
+        for_each_stage<L_, SW>(t, p, [&](int s, int b, int m, int q_base, int, int, int, int) {
             const int slot = s % kStages;
             mbar_wait(&empty[slot], ((s / kStages) & 1) ^ 1);
             mbar_arrive_expect_tx(&full[slot], Lay::kTxBytes);
@@ -191,9 +205,67 @@ struct Ring {
 // registers per (query, head): attention weights = softmax over the L*P logits, sampling locations =
 // reference point + offset / (W_l, H_l).  Each lane holds NIT points (one per level iteration); the LG
 // lane groups hold the other points, so max / sum are folded across groups with xor-shuffles.
-template <int NIT, int LPC, int LG, int L_, int P_>
-__device__ __forceinline__ void fused_prologue(float (&xs)[NIT], float (&ys)[NIT], float (&ws)[NIT],
-                                               const float2 *ref_q, const float (&rW)[L_], const float (&rH)[L_])
+// Reference points (fused mode).  ref_q != nullptr: the caller's (N, Lq, L, 2) tensor — a dependent global load per
+// (query, head) in front of every gather address.  ref_q == nullptr: the encoder's own reference points with valid
+// ratios 1 (msdeformattn.py:141-153): every level gets the query pixel's centre ((x + 0.5) / W_q, (y + 0.5) / H_q),
+// computed here from the query index with the same fp32 division torch does (linspace values i + 0.5 are exact), so
+// the result is bit-identical and no load sits on the critical path.
+template <int L_>
+__device__ __forceinline__ float2 pixel_centre_ref(int q, const int (&st)[L_], const int (&W)[L_], const float (&Wf)[L_],
+                                                   const float (&Hf)[L_])
+{
+    int s0 = st[0], w = W[0];
+    float wf = Wf[0], hf = Hf[0];
+#pragma unroll
+    for (int k = 1; k < L_; ++k)
+        if (q >= st[k]) { s0 = st[k]; w = W[k]; wf = Wf[k]; hf = Hf[k]; }   // level starts ascend
+    const int idx = q - s0;
+    const int y = idx / w;
+    const int x = idx - y * w;
+    return make_float2((static_cast<float>(x) + 0.5f) / wf, (static_cast<float>(y) + 0.5f) / hf);
+}
+
+// Stage-level part of the analytic reference point: row term and the level's width, selected once per stage.
+template <int L_>
+struct StageRef {
+    float wf, ry;      // level width; (y + 0.5) / H   (valid when row >= 0)
+    int row;
+    __device__ __forceinline__ StageRef(int kq, int yq, const float (&Wf)[L_], const float (&Hf)[L_])
+    {
+        float hf = Hf[0];
+        wf = Wf[0];
+#pragma unroll
+        for (int k = 1; k < L_; ++k)
+            if (kq == k) { wf = Wf[k]; hf = Hf[k]; }
+        row = yq;
+        ry = (static_cast<float>(yq) + 0.5f) / hf;
+    }
+    // reference point of query q = q_base + qi, column x0q + qi of the stage's row
+    __device__ __forceinline__ float2 centre(int q, int x, const int (&st)[L_], const int (&W)[L_], const float (&Wf)[L_],
+                                             const float (&Hf)[L_]) const
+    {
+        if (row >= 0) return make_float2((static_cast<float>(x) + 0.5f) / wf, ry);
+        return pixel_centre_ref<L_>(q, st, W, Wf, Hf);
+    }
+};
+
+// Locations: loc = ref + offset / (W_l, H_l).  No cross-lane dependency, so the gather addresses can be formed at once.
+template <int NIT, int LG, int L_, int P_>
+__device__ __forceinline__ void fused_locations(float (&xs)[NIT], float (&ys)[NIT], const float2 *ref_q, const float2 centre,
+                                                const float (&rW)[L_], const float (&rH)[L_])
+{
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int l = (it * LG) / P_;
+        const float2 r = ref_q ? __ldg(ref_q + l) : centre;
+        xs[it] = fmaf(xs[it], rW[l], r.x);
+        ys[it] = fmaf(ys[it], rH[l], r.y);
+    }
+}
+
+// Softmax over the L*P logits of a (query, head): each lane holds NIT of them, the LG lane groups the others.
+template <int NIT, int LPC>
+__device__ __forceinline__ void fused_softmax(float (&ws)[NIT])
 {
     float mx = ws[0];
 #pragma unroll
@@ -208,22 +280,90 @@ __device__ __forceinline__ void fused_prologue(float (&xs)[NIT], float (&ys)[NIT
     }
 #pragma unroll
     for (int o = LPC; o < 32; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float inv = 1.f / sum;
+    const float inv = __frcp_rn(sum);
 #pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-        const int l = (it * LG) / P_;
-        const float2 r = __ldg(ref_q + l);
-        ws[it] *= inv;
-        xs[it] = fmaf(xs[it], rW[l], r.x);
-        ys[it] = fmaf(ys[it], rH[l], r.y);
+    for (int it = 0; it < NIT; ++it) ws[it] *= inv;
+}
+
+template <int NIT, int LPC, int LG, int L_, int P_>
+__device__ __forceinline__ void fused_prologue(float (&xs)[NIT], float (&ys)[NIT], float (&ws)[NIT],
+                                               const float2 *ref_q, const float2 centre, const float (&rW)[L_],
+                                               const float (&rH)[L_])
+{
+    fused_softmax<NIT, LPC>(ws);
+    fused_locations<NIT, LG, L_, P_>(xs, ys, ref_q, centre, rW, rH);
+}
+
+// Prologue warp (fused mode with TMA staging).  The consumer lanes are organised as 4 point groups x 8 channel lanes, so
+// a prologue done by the consumers is computed 8 times over (every lane of a group repeats its point's softmax and
+// location arithmetic: +36 % warp instructions, +50 % forward time, measured).  Here ONE extra warp converts a whole
+// stage in shared memory, lane = query: softmax over the query's L*P logits in registers, loc = ref + offset / (W, H),
+// written back in place; the consumers then run exactly the unfused code on the staged data.  ~150 warp instructions
+// per stage instead of ~2000, off the consumers' critical path (the ring keeps the prologue several stages ahead).
+template <int L_, int P_, int SW, typename RingT>
+__device__ __forceinline__ void prologue_role(RingT &ring, const Tabs<L_> &tabs, const FastParams &p, int lane)
+{
+    constexpr int LP = L_ * P_, kStages = RingT::kStages;
+    static_assert(P_ == 4, "one float4 of logits / two float4 of offsets per level");
+    int W[L_], st[L_];
+    float Hf[L_], Wf[L_], rW[L_], rH[L_];
+#pragma unroll
+    for (int l = 0; l < L_; ++l) {
+        W[l] = tabs.W[l]; st[l] = tabs.start[l];
+        Hf[l] = static_cast<float>(tabs.H[l]); Wf[l] = static_cast<float>(W[l]);
+        rW[l] = 1.f / Wf[l]; rH[l] = 1.f / Hf[l];
     }
+    for_each_stage<L_, SW>(tabs, p, [&](int s, int b, int, int q_base, int nq, int kq, int yq, int x0q) {
+        const int slot = s % kStages;
+        mbar_wait(&ring.full[slot], (s / kStages) & 1);
+        const StageRef<L_> sref(kq, yq, Wf, Hf);
+        for (int qi = lane; qi < nq; qi += 32) {
+            const int q = q_base + qi;
+            float4 *sw = reinterpret_cast<float4 *>(ring.w_rw(slot, qi));
+            float4 w[L_];
+#pragma unroll
+            for (int l = 0; l < L_; ++l) w[l] = sw[l];
+            float mx = fmaxf(fmaxf(w[0].x, w[0].y), fmaxf(w[0].z, w[0].w));
+#pragma unroll
+            for (int l = 1; l < L_; ++l) mx = fmaxf(mx, fmaxf(fmaxf(w[l].x, w[l].y), fmaxf(w[l].z, w[l].w)));
+            float sum = 0.f;
+#pragma unroll
+            for (int l = 0; l < L_; ++l) {
+                w[l].x = __expf(w[l].x - mx); w[l].y = __expf(w[l].y - mx);
+                w[l].z = __expf(w[l].z - mx); w[l].w = __expf(w[l].w - mx);
+                sum += (w[l].x + w[l].y) + (w[l].z + w[l].w);
+            }
+            const float inv = __frcp_rn(sum);
+#pragma unroll
+            for (int l = 0; l < L_; ++l)
+                sw[l] = make_float4(w[l].x * inv, w[l].y * inv, w[l].z * inv, w[l].w * inv);
+            float4 *sl = reinterpret_cast<float4 *>(ring.loc_rw(slot, qi));      // (x, y) pairs: two points per float4
+            const float2 *ref_q = p.ref ? reinterpret_cast<const float2 *>(p.ref) + (static_cast<size_t>(b) * p.Lq + q) * L_
+                                        : nullptr;
+            const float2 centre = p.ref ? make_float2(0.f, 0.f) : sref.centre(q, x0q + qi, st, W, Wf, Hf);
+#pragma unroll
+            for (int l = 0; l < L_; ++l) {
+                const float2 r = ref_q ? __ldg(ref_q + l) : centre;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float4 o = sl[2 * l + h];
+                    o.x = fmaf(o.x, rW[l], r.x); o.y = fmaf(o.y, rH[l], r.y);
+                    o.z = fmaf(o.z, rW[l], r.x); o.w = fmaf(o.w, rH[l], r.y);
+                    sl[2 * l + h] = o;
+                }
+            }
+        }
+        fence_proxy_async_smem();      // the slot is later overwritten by TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ring.ready[slot]);
+    });
 }
 
 // ------------------------------------------------------------------------------------------
 // Forward
 // ------------------------------------------------------------------------------------------
 template <typename T, int VEC, int L_, int P_, int SW, int NWARP, int G, bool TMA, int CPS, bool FUSED = false>
-__global__ void __launch_bounds__((NWARP + (TMA ? 1 : 0)) * 32, CPS)
+__global__ void __launch_bounds__((NWARP + (TMA ? 1 : 0) + (TMA && FUSED ? 1 : 0)) * 32, CPS)
 msda_fwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_loc,
                      const __grid_constant__ CUtensorMap tm_w)
 {
@@ -251,6 +391,11 @@ msda_fwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_
         if (lane == 0) ring.produce(tabs, p, &tm_loc, &tm_w);
         return;
     }
+    constexpr bool PRO = TMA && FUSED;      // prologue done by a dedicated warp on the staged data
+    if (PRO && warp == NWARP + 1) {
+        prologue_role<L_, P_, SW>(ring, tabs, p, lane);
+        return;
+    }
 
     int H[L_], W[L_], st[L_];
     float Hf[L_], Wf[L_];
@@ -269,11 +414,13 @@ msda_fwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_
     const T *value = static_cast<const T *>(p.value);
     T *out = static_cast<T *>(p.out);
 
-    for_each_stage<L_, SW>(tabs, p, [&](int s, int b, int m, int q_base, int nq) {
+    for_each_stage<L_, SW>(tabs, p, [&](int s, int b, int m, int q_base, int nq, int kq, int yq, int x0q) {
         if (G > 1 && (s % G) != g) return;
         const int slot = s % kStages;
-        if (TMA) mbar_wait(&ring.full[slot], (s / kStages) & 1);
+        if (TMA) mbar_wait(PRO ? &ring.ready[slot] : &ring.full[slot], (s / kStages) & 1);
         const T *vlane = value + (static_cast<size_t>(b) * p.S * kHeads + m) * D + sub * VEC;
+        const StageRef<L_> sref(kq, yq, Wf, Hf);
+        (void)sref;
         for (int qi = wi; qi < nq; qi += WPG) {
             const int q = q_base + qi;
             float xs[NIT], ys[NIT], ws[NIT];
@@ -293,9 +440,11 @@ msda_fwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_
                     xs[it] = t.x; ys[it] = t.y; ws[it] = __ldg(p.attn + k0 + it * LG + lg);
                 }
             }
-            if constexpr (FUSED)
-                fused_prologue<NIT, LPC, LG, L_, P_>(
-                    xs, ys, ws, reinterpret_cast<const float2 *>(p.ref) + (static_cast<size_t>(b) * p.Lq + q) * L_, rW, rH);
+            if constexpr (FUSED && !PRO)
+                fused_locations<NIT, LG, L_, P_>(
+                    xs, ys,
+                    p.ref ? reinterpret_cast<const float2 *>(p.ref) + (static_cast<size_t>(b) * p.Lq + q) * L_ : nullptr,
+                    p.ref ? make_float2(0.f, 0.f) : sref.centre(q, x0q + qi, st, W, Wf, Hf), rW, rH);
             float acc[VEC];
 #pragma unroll
             for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
@@ -306,7 +455,6 @@ msda_fwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_
                 const T *row0 = vlane + static_cast<long long>(st[l] + f.y0 * W[l] + f.x0) * MD;
                 const T *row1 = row0 + W[l] * MD;
                 const T *corner[4] = {row0, row0 + MD, row1, row1 + MD};
-                const float wy[2] = {ws[it] * f.hh, ws[it] * f.lh};
                 const float wx[2] = {f.hw, f.lw};
                 float v[4][VEC];
 #pragma unroll
@@ -315,6 +463,11 @@ msda_fwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_
                     for (int c = 0; c < VEC; ++c) v[k][c] = 0.f;
                     if (f.ok[k]) VecIO<T, VEC>::load(corner[k], v[k]);
                 }
+                // fused mode: the softmax (two shuffle rounds, exps, a reciprocal) runs while the first gathers are in
+                // flight instead of in front of every address computation
+                if constexpr (FUSED && !PRO)
+                    if (it == 0) fused_softmax<NIT, LPC>(ws);
+                const float wy[2] = {ws[it] * f.hh, ws[it] * f.lh};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const float cw = wy[k >> 1] * wx[k & 1];   // v == 0 for dropped corners
@@ -384,7 +537,7 @@ msda_fwd_fast256_kernel(const FastParams p, const __grid_constant__ CUtensorMap 
     const float *value = static_cast<const float *>(p.value);
     float *out = static_cast<float *>(p.out);
 
-    for_each_stage<L_, SW>(tabs, p, [&](int s, int b, int m, int q_base, int nq) {
+    for_each_stage<L_, SW>(tabs, p, [&](int s, int b, int m, int q_base, int nq, int kq, int yq, int x0q) {
         if (G > 1 && (s % G) != g) return;
         const int slot = s % kStages;
         if (TMA) mbar_wait(&ring.full[slot], (s / kStages) & 1);
@@ -448,7 +601,7 @@ msda_fwd_fast256_kernel(const FastParams p, const __grid_constant__ CUtensorMap 
 // ------------------------------------------------------------------------------------------
 template <typename T, int VEC, int L_, int P_, int SW, int NWARP, int G, bool TMA, int CPS, bool MERGE,
           bool FUSED = false>
-__global__ void __launch_bounds__((NWARP + (TMA ? 1 : 0)) * 32, CPS)
+__global__ void __launch_bounds__((NWARP + (TMA ? 1 : 0) + (TMA && FUSED ? 1 : 0)) * 32, CPS)
 msda_bwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_loc,
                      const __grid_constant__ CUtensorMap tm_w)
 {
@@ -475,6 +628,11 @@ msda_bwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_
         if (lane == 0) ring.produce(tabs, p, &tm_loc, &tm_w);
         return;
     }
+    constexpr bool PRO = TMA && FUSED;      // prologue done by a dedicated warp on the staged data
+    if (PRO && warp == NWARP + 1) {
+        prologue_role<L_, P_, SW>(ring, tabs, p, lane);
+        return;
+    }
 
     int H[L_], W[L_], st[L_];
     float Hf[L_], Wf[L_];
@@ -494,13 +652,15 @@ msda_bwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_
     const T *grad_out = static_cast<const T *>(p.grad_out);
     float *grad_value = static_cast<float *>(p.grad_value);   // fp32 accumulation for every value dtype
 
-    for_each_stage<L_, SW>(tabs, p, [&](int s, int b, int m, int q_base, int nq) {
+    for_each_stage<L_, SW>(tabs, p, [&](int s, int b, int m, int q_base, int nq, int kq, int yq, int x0q) {
         if (G > 1 && (s % G) != g) return;
         const int slot = s % kStages;
-        if (TMA) mbar_wait(&ring.full[slot], (s / kStages) & 1);
+        if (TMA) mbar_wait(PRO ? &ring.ready[slot] : &ring.full[slot], (s / kStages) & 1);
         const size_t img = (static_cast<size_t>(b) * p.S * kHeads + m) * D + sub * VEC;
         const T *vlane = value + img;
         float *gvlane = grad_value + img;
+        const StageRef<L_> sref(kq, yq, Wf, Hf);
+        (void)sref;
         for (int qi = wi; qi < nq; qi += WPG) {
             const int q = q_base + qi;
             const size_t qm = (static_cast<size_t>(b) * p.Lq + q) * kHeads + m;
@@ -522,9 +682,11 @@ msda_bwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_
                     xs[it] = t.x; ys[it] = t.y; ws[it] = __ldg(p.attn + qm * LP + it * LG + lg);
                 }
             }
-            if constexpr (FUSED)
-                fused_prologue<NIT, LPC, LG, L_, P_>(
-                    xs, ys, ws, reinterpret_cast<const float2 *>(p.ref) + (static_cast<size_t>(b) * p.Lq + q) * L_, rW, rH);
+            if constexpr (FUSED && !PRO)
+                fused_locations<NIT, LG, L_, P_>(
+                    xs, ys,
+                    p.ref ? reinterpret_cast<const float2 *>(p.ref) + (static_cast<size_t>(b) * p.Lq + q) * L_ : nullptr,
+                    p.ref ? make_float2(0.f, 0.f) : sref.centre(q, x0q + qi, st, W, Wf, Hf), rW, rH);
             float ga_keep[NIT], gx_keep[NIT], gy_keep[NIT];   // fused mode: written after the softmax backward
             (void)ga_keep; (void)gx_keep; (void)gy_keep;
 #pragma unroll
@@ -542,6 +704,8 @@ msda_bwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_
                     for (int c = 0; c < VEC; ++c) v[k][c] = 0.f;
                     if (f.ok[k]) VecIO<T, VEC>::load(vlane + eoff[k], v[k]);
                 }
+                if constexpr (FUSED && !PRO)
+                    if (it == 0) fused_softmax<NIT, LPC>(ws);      // overlaps the first gathers (see forward)
                 // scatter grad_value; dot products of grad_out with the four corners
                 float t[4];
                 if constexpr (MERGE && VEC == 4) {

@@ -145,13 +145,13 @@ struct FusedChecked {
     int N, S, M, D, L, Lq, P, dtype;
 };
 
+// reference_points: (N,Lq,L,2) tensor, or None = the encoder's pixel-centre reference points, computed in the kernel
 FusedChecked check_fused(const at::Tensor &value, const at::Tensor &spatial_shapes, const at::Tensor &level_start_index,
-                         const at::Tensor &reference_points, const at::Tensor &sampling_offsets,
+                         const c10::optional<at::Tensor> &reference_points_opt, const at::Tensor &sampling_offsets,
                          const at::Tensor &attn_logits)
 {
     TORCH_CHECK(value.is_cuda(), "Not implemented on the CPU");
-    for (const at::Tensor *t : {&value, &spatial_shapes, &level_start_index, &reference_points, &sampling_offsets,
-                                &attn_logits}) {
+    for (const at::Tensor *t : {&value, &spatial_shapes, &level_start_index, &sampling_offsets, &attn_logits}) {
         TORCH_CHECK(t->is_cuda(), "all tensors must be CUDA tensors");
         TORCH_CHECK(t->is_contiguous(), "all tensors have to be contiguous");
     }
@@ -159,11 +159,8 @@ FusedChecked check_fused(const at::Tensor &value, const at::Tensor &spatial_shap
                 "spatial_shapes / level_start_index must be int64");
     TORCH_CHECK(value.dim() == 4 && sampling_offsets.dim() == 6 && sampling_offsets.size(5) == 2,
                 "value must be (N,S,M,D), sampling_offsets (N,Lq,M,L,P,2)");
-    TORCH_CHECK(reference_points.dim() == 4 && reference_points.size(3) == 2,
-                "fused path takes 2-d reference points (N,Lq,L,2)");
-    TORCH_CHECK(reference_points.scalar_type() == at::kFloat && sampling_offsets.scalar_type() == at::kFloat &&
-                    attn_logits.scalar_type() == at::kFloat,
-                "reference_points / sampling_offsets / attn_logits must be float32");
+    TORCH_CHECK(sampling_offsets.scalar_type() == at::kFloat && attn_logits.scalar_type() == at::kFloat,
+                "sampling_offsets / attn_logits must be float32");
     FusedChecked c;
     c.N = static_cast<int>(value.size(0)); c.S = static_cast<int>(value.size(1));
     c.M = static_cast<int>(value.size(2)); c.D = static_cast<int>(value.size(3));
@@ -173,8 +170,18 @@ FusedChecked check_fused(const at::Tensor &value, const at::Tensor &spatial_shap
                 "sampling_offsets shape does not match value / spatial_shapes");
     TORCH_CHECK(attn_logits.numel() == static_cast<int64_t>(c.N) * c.Lq * c.M * c.L * c.P,
                 "attn_logits must be (N,Lq,M,L*P)");
-    TORCH_CHECK(reference_points.size(0) == c.N && reference_points.size(1) == c.Lq && reference_points.size(2) == c.L,
-                "reference_points must be (N,Lq,L,2)");
+    if (reference_points_opt.has_value()) {
+        const at::Tensor &reference_points = *reference_points_opt;
+        TORCH_CHECK(reference_points.is_cuda() && reference_points.is_contiguous() &&
+                        reference_points.scalar_type() == at::kFloat,
+                    "reference_points must be a contiguous float32 CUDA tensor");
+        TORCH_CHECK(reference_points.dim() == 4 && reference_points.size(3) == 2,
+                    "fused path takes 2-d reference points (N,Lq,L,2)");
+        TORCH_CHECK(reference_points.size(0) == c.N && reference_points.size(1) == c.Lq && reference_points.size(2) == c.L,
+                    "reference_points must be (N,Lq,L,2)");
+    } else {
+        TORCH_CHECK(c.Lq == c.S, "reference_points=None (pixel-centre reference points) needs Lq == S");
+    }
     c.dtype = dtype_code(value);
     return c;
 }
@@ -188,7 +195,8 @@ bool ms_deform_attn_fused_supported(int64_t num_heads, int64_t channels, int64_t
 }
 
 at::Tensor ms_deform_attn_fused_forward(const at::Tensor &value, const at::Tensor &spatial_shapes,
-                                        const at::Tensor &level_start_index, const at::Tensor &reference_points,
+                                        const at::Tensor &level_start_index,
+                                        const c10::optional<at::Tensor> &reference_points,
                                         const at::Tensor &sampling_offsets, const at::Tensor &attn_logits)
 {
     const FusedChecked c = check_fused(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
@@ -196,7 +204,8 @@ at::Tensor ms_deform_attn_fused_forward(const at::Tensor &value, const at::Tenso
     const c10::cuda::CUDAGuard guard(value.device());
     auto output = at::empty({c.N, c.Lq, c.M * c.D}, value.options());
     const int rc = bm2f_msda_fused_forward(value.data_ptr(), spatial_shapes.data_ptr<int64_t>(),
-                                           level_start_index.data_ptr<int64_t>(), reference_points.data_ptr(),
+                                           level_start_index.data_ptr<int64_t>(),
+                                           reference_points.has_value() ? reference_points->data_ptr() : nullptr,
                                            sampling_offsets.data_ptr(), attn_logits.data_ptr(), output.data_ptr(),
                                            c.N, c.S, c.M, c.D, c.L, c.Lq, c.P, c.dtype, nullptr,
                                            at::cuda::getCurrentCUDAStream().stream());
@@ -206,7 +215,7 @@ at::Tensor ms_deform_attn_fused_forward(const at::Tensor &value, const at::Tenso
 
 std::vector<at::Tensor> ms_deform_attn_fused_backward(const at::Tensor &value, const at::Tensor &spatial_shapes,
                                                       const at::Tensor &level_start_index,
-                                                      const at::Tensor &reference_points,
+                                                      const c10::optional<at::Tensor> &reference_points,
                                                       const at::Tensor &sampling_offsets,
                                                       const at::Tensor &attn_logits, const at::Tensor &grad_output)
 {
@@ -219,7 +228,8 @@ std::vector<at::Tensor> ms_deform_attn_fused_backward(const at::Tensor &value, c
     auto grad_off = at::empty_like(sampling_offsets);
     auto grad_logits = at::empty_like(attn_logits);
     const int rc = bm2f_msda_fused_backward(value.data_ptr(), spatial_shapes.data_ptr<int64_t>(),
-                                            level_start_index.data_ptr<int64_t>(), reference_points.data_ptr(),
+                                            level_start_index.data_ptr<int64_t>(),
+                                           reference_points.has_value() ? reference_points->data_ptr() : nullptr,
                                             sampling_offsets.data_ptr(), attn_logits.data_ptr(), grad_output.data_ptr(),
                                             grad_value.data_ptr(), grad_off.data_ptr(), grad_logits.data_ptr(), c.N,
                                             c.S, c.M, c.D, c.L, c.Lq, c.P, c.dtype, nullptr,

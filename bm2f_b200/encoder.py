@@ -109,10 +109,15 @@ class MSDeformAttnTransformerEncoder(nn.Module):
         return reference_points[:, :, None] * valid_ratios[:, None]
 
     def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None,
-                spatial_shapes_list=None):
+                spatial_shapes_list=None, unit_valid_ratios=False):
+        """`unit_valid_ratios=True` (set by `MSDeformAttnTransformerEncoderOnly`, whose masks are all-False by
+        construction, msdeformattn.py:62) marks the reference points as plain pixel centres so the fused sampling
+        kernels can compute them from the query index instead of loading them."""
         output = src
         reference_points = self.get_reference_points(
             spatial_shapes_list if spatial_shapes_list is not None else spatial_shapes, valid_ratios, src.device)
+        if unit_valid_ratios:
+            reference_points.pixel_centres = True
         for layer in self.layers:
             output = layer(output, pos, reference_points, spatial_shapes, level_start_index, padding_mask)
         return output
@@ -164,7 +169,7 @@ class MSDeformAttnTransformerEncoderOnly(nn.Module):
         level_start_index = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
         valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
         memory = self.encoder(src_flatten, spatial_shapes, level_start_index, valid_ratios, lvl_pos_embed_flatten,
-                              mask_flatten, spatial_shapes_list=shapes_list)
+                              mask_flatten, spatial_shapes_list=shapes_list, unit_valid_ratios=True)
         return memory, spatial_shapes, level_start_index
 
     def forward_tokens(self, src_flatten, lvl_pos_embed_flatten, shapes_list):
@@ -177,5 +182,5 @@ class MSDeformAttnTransformerEncoderOnly(nn.Module):
         level_start_index = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
         valid_ratios = torch.ones((n, len(shapes_list), 2), dtype=torch.float32, device=device)
         memory = self.encoder(src_flatten, spatial_shapes, level_start_index, valid_ratios, lvl_pos_embed_flatten,
-                              None, spatial_shapes_list=list(shapes_list))
+                              None, spatial_shapes_list=list(shapes_list), unit_valid_ratios=True)
         return memory, spatial_shapes, level_start_index

@@ -121,9 +121,13 @@ class MSDeformAttn(nn.Module):
         attention_weights = self._proj(self.attention_weights, query).view(
             N, Len_q, self.n_heads, self.n_levels * self.n_points)
         if use_fused and value.dtype == torch.float32 and sampling_offsets.dtype == torch.float32:
+            # The encoder tags reference points it built itself with valid ratios 1 (`pixel_centres`): the kernel then
+            # derives them from the query index (bit-identical) instead of loading them per (query, head).
+            analytic = getattr(reference_points, "pixel_centres", False) and Len_q == Len_in
             output = MSDeformAttnFusedFunction.apply(
-                value, input_spatial_shapes, input_level_start_index, reference_points.contiguous(),
-                sampling_offsets, attention_weights, input_padding_mask)
+                value, input_spatial_shapes, input_level_start_index,
+                None if analytic else reference_points.contiguous(), sampling_offsets, attention_weights,
+                input_padding_mask)
             return self._proj(self.output_proj, output)
         attention_weights = F.softmax(attention_weights, -1).view(
             N, Len_q, self.n_heads, self.n_levels, self.n_points)

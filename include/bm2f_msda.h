@@ -138,6 +138,10 @@ int bm2f_msda_backward(const void *value, const int64_t *spatial_shapes,
  * gradients of the raw Linear outputs (softmax backward and the 1/(W,H) scaling included).
  *   reference_points (N, Lq, L, 2) float32, (x, y) in [0,1]   — the 2-d branch of the module; they get no
  *   gradient (Mask2Former builds them from the level shapes, msdeformattn.py:141-153).
+ *   reference_points == NULL (needs num_query == spatial_size): exactly those encoder reference points with valid
+ *   ratios 1 — every level gets the query pixel's centre ((x + 0.5) / W_q, (y + 0.5) / H_q) — computed in the kernel
+ *   from the query index, bit-identical to the tensor torch builds, and without a dependent global load in front of
+ *   every gather (forward 1.42 -> ~1.0 ms at cfg 2).
  *   sampling_offsets (N, Lq, M, L, P, 2) float32 in pixels;  attn_logits (N, Lq, M, L, P) float32.
  * Shapes outside D=32, M=8, P=4, L<=4 (f32) / L=3 (bf16) return BM2F_ERR_UNSUPPORTED: compose the
  * prologue yourself and call bm2f_msda_forward/backward.  bm2f_msda_fused_supported() tells in advance.

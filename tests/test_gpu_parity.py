@@ -373,3 +373,40 @@ def test_fused_bf16_forward_vs_oracle(built):
     want = O.fused_forward(v.float().cpu().numpy(), base["shapes"].numpy(), base["start"].numpy(), ref.numpy(),
                            offsets.numpy(), logits.numpy())
     assert rel_err(out.float().cpu().numpy(), want) <= 1e-2
+
+
+@pytest.mark.parametrize("levels,batch", [(SMALL_LEVELS, 2), (((1, 1), (3, 2), (25, 38)), 2), (((5, 7), (9, 13)), 1),
+                                          (W.WORKLOADS[1].levels, 1)])
+def test_fused_analytic_reference_points_bit_identical(levels, batch, built):
+    """reference_points == NULL: the kernel derives the encoder's pixel-centre reference points (valid ratios 1,
+    msdeformattn.py:141-153) from the query index.  Same fp32 division as torch, so forward output and the
+    deterministic gradients are bit-identical to passing the tensor torch builds; grad_value (atomic order) to 1e-6."""
+    from bm2f_b200.encoder import MSDeformAttnTransformerEncoder
+    base, _, offsets, logits = _fused_inputs(levels, batch, 950 + len(levels))
+    dev = _dev()
+    L = len(levels)
+    ref = MSDeformAttnTransformerEncoder.get_reference_points(
+        list(levels), torch.ones(batch, L, 2, device=dev), dev).contiguous()             # what the encoder passes
+    assert torch.equal(ref.cpu(), W.reference_points(levels, batch))
+    sh, st = base["shapes"].to(dev), base["start"].to(dev)
+    v, o, lg, go = (t.to(dev).contiguous() for t in (base["value"], offsets, logits, base["grad_out"]))
+    N, S, M, D = v.shape
+    dims = (N, S, M, D, L, S, 4)
+    stream = torch.cuda.current_stream().cuda_stream
+    res = []
+    for r in (ref.data_ptr(), 0):
+        out = torch.full((N, S, M * D), float("nan"), device=dev)
+        gv, goff, glog = torch.full_like(v, float("nan")), torch.full_like(o, float("nan")), torch.full_like(lg, float("nan"))
+        cabi.fused_forward(v.data_ptr(), sh.data_ptr(), st.data_ptr(), r, o.data_ptr(), lg.data_ptr(), out.data_ptr(),
+                           dims, cabi.DTYPE_F32, None, stream)
+        cabi.fused_backward(v.data_ptr(), sh.data_ptr(), st.data_ptr(), r, o.data_ptr(), lg.data_ptr(), go.data_ptr(),
+                            gv.data_ptr(), goff.data_ptr(), glog.data_ptr(), dims, cabi.DTYPE_F32, None, stream)
+        torch.cuda.synchronize()
+        res.append((out, gv, goff, glog))
+    (out_t, gv_t, goff_t, glog_t), (out_a, gv_a, goff_a, glog_a) = res
+    assert torch.equal(out_t, out_a) and torch.equal(goff_t, goff_a) and torch.equal(glog_t, glog_a)
+    assert rel_err(gv_a.cpu().numpy(), gv_t.cpu().numpy()) <= 1e-6
+    # NULL reference points only make sense for self-attention over the same pyramid
+    with pytest.raises(cabi.MSDAError, match="num_query == spatial_size"):
+        cabi.fused_forward(v.data_ptr(), sh.data_ptr(), st.data_ptr(), 0, o.data_ptr(), lg.data_ptr(), out.data_ptr(),
+                           (N, S, M, D, L, S - 1, 4), cabi.DTYPE_F32, None, stream)
