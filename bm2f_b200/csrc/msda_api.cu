@@ -551,22 +551,73 @@ int launch_linear(const LinearParams &p, const float *w_hi, const float *w_lo, c
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return BM2F_OK;
 }
-template <int NT>
+template <int NT, int CL = 1, int PW = kGemmProducerWarps, int XD = 3>
 int launch_linear_persistent(const LinearParams &p, const float *w_hi, const float *w_lo, int sms, cudaStream_t st)
 {
     CUtensorMap mh, ml, my;
     int rc;
-    if ((rc = make_map(&mh, w_hi, p.N, p.K, NT, kGemmBlockK, true))) return rc;
-    if ((rc = make_map(&ml, w_lo, p.N, p.K, NT, kGemmBlockK, true))) return rc;
+    // CL > 1: every CTA of the cluster fetches NT / CL weight rows per k-block and multicasts them
+    if ((rc = make_map(&mh, w_hi, p.N, p.K, NT / CL, kGemmBlockK, true))) return rc;
+    if ((rc = make_map(&ml, w_lo, p.N, p.K, NT / CL, kGemmBlockK, true))) return rc;
     if ((rc = make_map(&my, p.y, p.M, p.N, 32, 32, true))) return rc;      // one 32 x 32 box per epilogue warp
     constexpr int smem = linear_persistent_smem_bytes<NT>();
-    if ((rc = ensure_dynamic_smem<&linear_tf32x3_persistent_kernel<NT>>(smem, "cudaFuncSetAttribute(persistent linear smem)")))
+    if ((rc = ensure_dynamic_smem<&linear_tf32x3_persistent_kernel<NT, CL, PW, XD>>(smem, "cudaFuncSetAttribute(persistent linear smem)")))
         return rc;
-    const int tiles = ((p.M + kGemmBlockM - 1) / kGemmBlockM) * p.slices;
-    const int grid = tiles < sms ? tiles : sms;
-    linear_tf32x3_persistent_kernel<NT><<<grid, kGemmThreadsPersistent, smem, st>>>(p, mh, ml, my);
+    const int row_tiles = (p.M + kGemmBlockM - 1) / kGemmBlockM;
+    const int tiles = ((row_tiles + CL - 1) / CL) * p.slices * CL;          // CTAs that have work
+    int grid = tiles < sms ? tiles : sms;
+    grid -= grid % CL;
+    if (CL == 1) {
+        linear_tf32x3_persistent_kernel<NT, 1, PW, XD><<<grid, gemm_threads_persistent(PW), smem, st>>>(p, mh, ml, my);
+    } else {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(gemm_threads_persistent(PW));
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CL;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const cudaError_t le = cudaLaunchKernelEx(&cfg, linear_tf32x3_persistent_kernel<NT, CL, PW, XD>, p, mh, ml, my);
+        if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(linear_tf32x3_persistent_kernel, cluster)");
+    }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "launch linear_tf32x3_persistent_kernel");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return BM2F_OK;
+}
+template <int NT>
+int launch_linear_pair(const LinearParams &p, const float *w_hi, const float *w_lo, int sms, cudaStream_t st)
+{
+    CUtensorMap mh, ml, my;
+    int rc;
+    if ((rc = make_map(&mh, w_hi, p.N, p.K, NT / 2, kGemmBlockK, true))) return rc;      // each CTA stages half the rows
+    if ((rc = make_map(&ml, w_lo, p.N, p.K, NT / 2, kGemmBlockK, true))) return rc;
+    if ((rc = make_map(&my, p.y, p.M, p.N, 32, 32, true))) return rc;
+    constexpr int smem = linear_pair_smem_bytes<NT>();
+    if ((rc = ensure_dynamic_smem<&linear_tf32x3_pair_kernel<NT>>(smem, "cudaFuncSetAttribute(pair linear smem)"))) return rc;
+    const int row_tiles = (p.M + kGemmBlockM - 1) / kGemmBlockM;
+    const int tiles = ((row_tiles + 1) / 2) * p.slices * 2;
+    int grid = tiles < sms ? tiles : sms;
+    grid -= grid % 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreadsPersistent);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, linear_tf32x3_pair_kernel<NT>, p, mh, ml, my);
+    if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(linear_tf32x3_pair_kernel)");
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return BM2F_OK;
 }
@@ -589,7 +640,14 @@ int linear_common(const void *x, const void *weight, const void *bias, void *y, 
         return fail(BM2F_ERR_UNSUPPORTED, "tcgen05 projection GEMM needs a reduction length that is a multiple of %d "
                     "and <= %d (got %d)", kGemmBlockK, kGemmKMax, k_red);
     // split 3 / 1: persistent kernel (double-buffered TMEM accumulator); +10: one tile per CTA (kept for A/B);
-    // +20: persistent kernel with coalesced-store epilogue instead of the TMA store (A/B)
+    // +20: persistent kernel with coalesced-store epilogue instead of the TMA store (A/B);
+    // +30: persistent kernel in clusters of two CTAs with TMA-multicast weights (A/B)
+    // +40 / +50 / +60: more activation bytes in flight (8 producer warps x 5 k-blocks / 4 x 4 / 8 x 4) (A/B)
+    // +70: CTA pairs issuing tcgen05.mma.cta_group::2 (M = 256 per pair)
+    int xvar = 0;
+    if (split >= 40) { xvar = split / 10 - 3; split -= (xvar + 3) * 10; }
+    const bool cluster2 = split >= 30;
+    if (cluster2) split -= 30;
     const bool stg_epilogue = split >= 20;
     if (stg_epilogue) split -= 20;
     const bool one_tile = split >= 10;
@@ -618,11 +676,20 @@ int linear_common(const void *x, const void *weight, const void *bias, void *y, 
     if (!one_tile) {
         if (n_out % 256 == 0) {      // 256-wide column slices (1024-wide FFN layer = 4 slices sharing the row tile)
             p.slices = n_out / 256;
-            return launch_linear_persistent<256>(p, w_hi, w_lo, sms, st);
+            if (xvar == 4) return launch_linear_pair<256>(p, w_hi, w_lo, sms, st);
+            if (xvar == 1) return launch_linear_persistent<256, 1, 8, 5>(p, w_hi, w_lo, sms, st);
+            if (xvar == 2) return launch_linear_persistent<256, 1, 4, 4>(p, w_hi, w_lo, sms, st);
+            if (xvar == 3) return launch_linear_persistent<256, 1, 8, 4>(p, w_hi, w_lo, sms, st);
+            return cluster2 ? launch_linear_persistent<256, 2>(p, w_hi, w_lo, sms, st)
+                            : launch_linear_persistent<256, 1>(p, w_hi, w_lo, sms, st);
         }
         switch (n_out) {
-        case 192: return launch_linear_persistent<192>(p, w_hi, w_lo, sms, st);
-        case 96: return launch_linear_persistent<96>(p, w_hi, w_lo, sms, st);
+        case 192: if (xvar == 4) return launch_linear_pair<192>(p, w_hi, w_lo, sms, st);
+                  return cluster2 ? launch_linear_persistent<192, 2>(p, w_hi, w_lo, sms, st)
+                                  : launch_linear_persistent<192, 1>(p, w_hi, w_lo, sms, st);
+        case 96: if (xvar == 4) return launch_linear_pair<96>(p, w_hi, w_lo, sms, st);
+                 return cluster2 ? launch_linear_persistent<96, 2>(p, w_hi, w_lo, sms, st)
+                                 : launch_linear_persistent<96, 1>(p, w_hi, w_lo, sms, st);
         default: break;      // 288 = 2 x 144 columns does not fit two accumulators: one-tile kernel
         }
     }

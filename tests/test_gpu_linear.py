@@ -101,3 +101,24 @@ def test_linear_backward_weight_matches_fp64(msda, out_features, rows):
     assert (gb.double() - ref_b).abs().max().item() / ref_b.abs().max().item() <= 1e-5
     gw2, gb2 = msda.linear_tf32x3_backward_weight(g, x, 3, False)
     assert not gb2.defined() if hasattr(gb2, "defined") else gb2 is None or gb2.numel() == 0
+
+
+@pytest.mark.parametrize("variant,name", [(33, "cluster of 2, TMA-multicast weights"), (73, "CTA pair, tcgen05 cta_group::2"),
+                                          (43, "8 producer warps x 5 k-blocks"), (53, "4 x 4"), (23, "coalesced-store epilogue")])
+@pytest.mark.parametrize("in_features,out_features", [(256, 256), (256, 1024), (1024, 256)])
+def test_linear_kernel_variants_match_default(msda, variant, name, in_features, out_features):
+    """The A/B variants of the persistent GEMM kept in the library (split + 20 / 30 / 40 / 50 / 70) compute
+    the same tiles with the same MMA order as the default kernel: results equal to 1e-6, on ragged and odd tile counts
+    (the cluster variants walk row tiles in pairs; an odd count leaves one CTA of the last pair without rows)."""
+    dev = torch.device("cuda:0")
+    for rows in (1, 129, 128 * 5 + 17, 128 * 297 + 5):
+        torch.manual_seed(rows)
+        x = torch.randn(rows, in_features, device=dev)
+        w = torch.randn(out_features, in_features, device=dev) / in_features ** 0.5
+        b = torch.randn(out_features, device=dev)
+        y0 = msda.linear_tf32x3(x, w, b, 3)
+        y1 = msda.linear_tf32x3(x, w, b, variant)
+        ref = x.double() @ w.double().t() + b.double()
+        scale = ref.abs().max().item()
+        assert (y1.double() - ref).abs().max().item() <= 1e-5 * scale, (name, rows)
+        assert (y1 - y0).abs().max().item() <= 2e-6 * scale, (name, rows)
