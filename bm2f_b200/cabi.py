@@ -18,7 +18,7 @@ DTYPE_F32, DTYPE_F64, DTYPE_BF16 = 0, 1, 2
 SYMBOLS = (
     "bm2f_msda_abi_version", "bm2f_msda_build_info", "bm2f_msda_last_error", "bm2f_msda_launch_count",
     "bm2f_msda_set_default_tuning", "bm2f_msda_check_im2col_step", "bm2f_msda_forward",
-    "bm2f_msda_backward", "bm2f_msda_forward_backward_host", "bm2f_msda_fused_supported",
+    "bm2f_msda_backward", "bm2f_msda_forward_backward_host", "bm2f_msda_release_host_workspace", "bm2f_msda_fused_supported",
     "bm2f_msda_fused_forward", "bm2f_msda_fused_backward", "bm2f_linear_workspace_bytes", "bm2f_linear_forward",
     "bm2f_linear_backward_input", "bm2f_linear_backward_weight", "bm2f_linear_relu_forward",
     "bm2f_linear_backward_input_masked", "bm2f_add_layernorm_forward",

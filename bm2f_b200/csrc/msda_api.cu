@@ -999,6 +999,28 @@ struct HostPath {
 size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 }  // namespace
 
+int bm2f_msda_release_host_workspace(void)
+{
+    std::lock_guard<std::mutex> lk(g_host.mu);
+    if (g_host.dev < 0) return BM2F_OK;
+    int cur = 0;
+    cudaError_t e = cudaGetDevice(&cur);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    if ((e = cudaSetDevice(g_host.dev)) != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    for (int i = 0; i < kHostSlots; ++i) {
+        if (g_host.streams[i]) { cudaStreamSynchronize(g_host.streams[i]); cudaStreamDestroy(g_host.streams[i]); }
+        if (g_host.ws[i]) cudaFree(g_host.ws[i]);
+        g_host.streams[i] = nullptr;
+        g_host.ws[i] = nullptr;
+    }
+    if (g_host.tabs) cudaFree(g_host.tabs);
+    g_host.tabs = nullptr;
+    g_host.ws_bytes = 0;
+    g_host.dev = -1;
+    cudaSetDevice(cur);
+    return BM2F_OK;
+}
+
 int bm2f_msda_forward_backward_host(const void *value_host, const int64_t *spatial_shapes_host,
                                     const int64_t *level_start_index_host, const void *sampling_loc_host,
                                     const void *attn_weight_host, const void *grad_output_host, void *output_host,

@@ -252,9 +252,12 @@ int bm2f_sine_position_embedding(void *out, int height, int width, int num_pos_f
  * every pointer is a HOST pointer (pinned memory gives full PCIe rate).  The library copies
  * the inputs to a device workspace it owns for the duration of the call, runs forward and,
  * when grad_output_host != NULL, backward, copies the results back and synchronises.
- * The batch is pipelined image by image over two streams so copies overlap the kernels.
- * Any of the result pointers may be NULL to skip that copy-back.
+ * The batch is pipelined in image chunks over three streams / workspace slots (uploads of a chunk first, then
+ * both kernels, then its downloads), so the H2D engine, the SMs and the D2H engine work on different chunks.
+ * Any of the result pointers may be NULL to skip that copy-back.  The workspace is kept between calls (sized by the
+ * largest call so far); bm2f_msda_release_host_workspace() frees it and the streams.
  */
+int bm2f_msda_release_host_workspace(void);
 int bm2f_msda_forward_backward_host(const void *value_host, const int64_t *spatial_shapes_host,
                                     const int64_t *level_start_index_host,
                                     const void *sampling_loc_host, const void *attn_weight_host,

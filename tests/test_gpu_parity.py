@@ -301,6 +301,14 @@ def test_host_entry_matches_device_entry(built):
     assert rel_err(gv.numpy(), ref["grad_value"]) <= 1e-5
     assert rel_err(gl.numpy(), ref["grad_loc"]) <= 1e-5
     assert rel_err(ga.numpy(), ref["grad_attn"]) <= 1e-5
+    # the workspace survives between calls; releasing it and calling again re-creates it
+    assert cabi.lib().bm2f_msda_release_host_workspace() == 0
+    out2 = torch.empty_like(out)
+    cabi.forward_backward_host(pin["value"].data_ptr(), pin["shapes"].data_ptr(), pin["start"].data_ptr(),
+                               pin["loc"].data_ptr(), pin["attn"].data_ptr(), 0, out2.data_ptr(), 0, 0, 0,
+                               (N, S, M, D, 3, Lq, 4))
+    assert torch.equal(out, out2)
+    assert cabi.lib().bm2f_msda_release_host_workspace() == 0
 
 
 # ----------------------------------------------------------------------------------------------
