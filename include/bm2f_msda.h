@@ -171,7 +171,10 @@ int bm2f_msda_fused_backward(const void *value, const int64_t *spatial_shapes,
  * float32 in / out; output width a multiple of 256 or one of {288, 192, 96}, reduction length a multiple of 32
  * (forward: in_features = 256 = d_model; bm2f_linear_backward_input: grad_x = grad_y * weight, width 256).
  * split = 3: three-term TF32 split with fp32 accumulation (fp32-grade result, what the fp32 reference
- * module needs); split = 1: single TF32 pass.  `workspace` = bm2f_linear_workspace_bytes() of device
+ * module needs); split = 1: single TF32 pass.  Adding a multiple of 10 selects a kernel variant kept for A/B
+ * measurements (same results): +10 one tile per CTA, +20 coalesced-store epilogue, +30 clusters of two
+ * CTAs with TMA-multicast weights, +40 / +50 / +60 more activation k-blocks in flight, +70 CTA pairs issuing
+ * tcgen05.mma.cta_group::2; for bm2f_linear_backward_weight +100*c caps the rows reduced per CTA at 256*c.  `workspace` = bm2f_linear_workspace_bytes() of device
  * memory for the hi/lo halves of the weight (rewritten on every call).  bias may be NULL.
  */
 size_t bm2f_linear_workspace_bytes(int out_features, int in_features);
