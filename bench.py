@@ -304,6 +304,28 @@ def run_ours(args, wl):
         step()
     sync_all()
 
+    graph, graph_launches = None, 0
+    if args.graph:
+        # every launch of a step goes through the C ABI on the current stream: tensor maps are encoded on the host and
+        # passed by value, the zero-fill is a memset node, nothing synchronises -> the whole step is capturable
+        l0 = cabi.launch_count()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step(collective=False)
+        graph_launches = cabi.launch_count() - l0
+        graph.replay()
+        sync_all()
+
+    def timed_step():
+        if graph is None:
+            return step(record=True)
+        graph.replay()
+        if grad_bucket is not None:
+            comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(comm_stream):
+                dist.all_reduce(grad_bucket)
+                grad_bucket.mul_(1.0 / world)
+
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -313,13 +335,18 @@ def run_ours(args, wl):
     sync_all()
     e0.record()
     for _ in range(args.steps):
-        step(record=True)
+        timed_step()
     if comm_stream is not None:
         torch.cuda.current_stream().wait_stream(comm_stream)
     e1.record()
     sync_all()
     elapsed_ms = e0.elapsed_time(e1)
     launches = cabi.launch_count() - launches0
+    if graph is not None:
+        launches = graph_launches * args.steps      # replayed launches do not pass through the launch counter
+        for _ in range(3):                          # per-kernel times for the roofline: separate, un-graphed pass
+            step(record=True, collective=False)
+        torch.cuda.synchronize()
     # keep the GPU busy a little longer so the sampler certainly has samples under load
     if sampler:
         t_end = time.perf_counter() + 0.5
@@ -442,7 +469,7 @@ def run_ours(args, wl):
                    "l2_policy": f"inputs larger than L2: {in_bytes / 1e6:.0f} MB of inputs per layer, 6 distinct "
                                 "layer input sets, no flush needed",
                    "collective": "all-reduce of 4.93 MB projection-gradient bucket per step" if grad_bucket is not None else "none",
-                   "tuning": args.tuning or "default"},
+                   "tuning": args.tuning or "default", "cuda_graph": graph is not None},
         "roofline": roofline, "gather": gather, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
         "clocks": clocks, "reference_cuda": ref_cuda,
     }
@@ -501,6 +528,9 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="override images per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--tuning", default="", help="e.g. vec=4,staging=1,strip_w=16,rows=32,ctas_per_sm=2")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay one step (all layers, fwd+bwd) from a CUDA graph in the timed loop: for launch-bound "
+                         "configs (cfg 1: one 512^2 image, 35 us of launch overhead per layer)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
