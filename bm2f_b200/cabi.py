@@ -21,7 +21,7 @@ SYMBOLS = (
     "bm2f_msda_backward", "bm2f_msda_forward_backward_host", "bm2f_msda_release_host_workspace", "bm2f_msda_fused_supported",
     "bm2f_msda_fused_forward", "bm2f_msda_fused_backward", "bm2f_linear_workspace_bytes", "bm2f_linear_forward",
     "bm2f_linear_backward_input", "bm2f_linear_backward_weight", "bm2f_linear_relu_forward",
-    "bm2f_linear_backward_input_masked", "bm2f_add_layernorm_forward",
+    "bm2f_linear_backward_input_masked", "bm2f_linear_backward_input_accumulate", "bm2f_add_layernorm_forward",
     "bm2f_add_layernorm_backward", "bm2f_zero_masked_rows", "bm2f_transpose_batched",
     "bm2f_groupnorm_tokens_workspace_bytes", "bm2f_groupnorm_tokens_forward", "bm2f_groupnorm_tokens_backward",
     "bm2f_sine_position_embedding",

@@ -38,6 +38,8 @@ struct LinearParams {
     int relu;           // epilogue: y = max(y, 0)
     int store_mode;     // persistent kernel epilogue: 0 = per-warp TMA store, 1 = coalesced 128-bit stores through smem
     const float *out_mask;  // optional (M, N): epilogue zeroes y where out_mask <= 0 (ReLU backward of the previous layer)
+    const float *addend;    // optional (M, N): epilogue adds it (gradient accumulation; may alias y: a tile is read, then
+                            // written, by the one CTA that owns it)
     int split;           // 3 = tf32x3 (fp32-grade), 1 = single TF32 pass
 };
 
@@ -577,6 +579,11 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
                         o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
                     }
                     if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    if (p.addend && grow < p.M) {
+                        const float4 ad = *reinterpret_cast<const float4 *>(      // plain load: addend may alias y
+                            p.addend + static_cast<size_t>(grow) * p.N + ti.sl * NT + c0 + c);
+                        o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
+                    }
                     if (p.out_mask && grow < p.M) {
                         const float4 mk = __ldg(reinterpret_cast<const float4 *>(
                             p.out_mask + static_cast<size_t>(grow) * p.N + ti.sl * NT + c0 + c));
@@ -914,6 +921,11 @@ linear_tf32x3_pair_kernel(const LinearParams p, const __grid_constant__ CUtensor
                         o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
                     }
                     if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    if (p.addend && grow < p.M) {
+                        const float4 ad = *reinterpret_cast<const float4 *>(      // plain load: addend may alias y
+                            p.addend + static_cast<size_t>(grow) * p.N + ti.sl * NT + c0 + c);
+                        o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
+                    }
                     if (p.out_mask && grow < p.M) {
                         const float4 mk = __ldg(reinterpret_cast<const float4 *>(
                             p.out_mask + static_cast<size_t>(grow) * p.N + ti.sl * NT + c0 + c));

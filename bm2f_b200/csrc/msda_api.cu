@@ -632,7 +632,8 @@ size_t bm2f_linear_workspace_bytes(int out_features, int in_features)
 namespace {
 // y[rows, n_out] = x[rows, k_red] * w'[n_out, k_red]^T (+ bias); w' = weight or its transpose
 int linear_common(const void *x, const void *weight, const void *bias, void *y, void *workspace, int rows, int n_out,
-                  int k_red, int transpose_weight, int split, void *stream, int relu = 0, const void *mask = nullptr /* output mask */)
+                  int k_red, int transpose_weight, int split, void *stream, int relu = 0, const void *mask = nullptr /* output mask */,
+                  const void *addend = nullptr)
 {
     if (!x || !weight || !y || !workspace) return fail(BM2F_ERR_INVALID, "null pointer");
     if (rows <= 0) return fail(BM2F_ERR_INVALID, "rows must be positive");
@@ -671,6 +672,8 @@ int linear_common(const void *x, const void *weight, const void *bias, void *y, 
     LinearParams p{};
     p.x = static_cast<const float *>(x); p.bias = static_cast<const float *>(bias); p.y = static_cast<float *>(y);
     p.M = rows; p.N = n_out; p.K = k_red; p.slices = 1; p.relu = relu; p.out_mask = static_cast<const float *>(mask); p.store_mode = stg_epilogue ? 1 : 0;
+    p.addend = static_cast<const float *>(addend);
+    if (addend && !aligned16(addend)) return fail(BM2F_ERR_UNSUPPORTED, "linear: addend must be 16-byte aligned");
     p.split = split;
     if (mask && !aligned16(mask)) return fail(BM2F_ERR_UNSUPPORTED, "linear: mask must be 16-byte aligned");
     if (!one_tile) {
@@ -693,7 +696,8 @@ int linear_common(const void *x, const void *weight, const void *bias, void *y, 
         default: break;      // 288 = 2 x 144 columns does not fit two accumulators: one-tile kernel
         }
     }
-    if (relu || mask) return fail(BM2F_ERR_UNSUPPORTED, "linear: relu / mask need the persistent kernel (width %% 256 == 0, 192 or 96)");
+    if (relu || mask || addend)
+        return fail(BM2F_ERR_UNSUPPORTED, "linear: relu / mask / addend need the persistent kernel (width %% 256 == 0, 192 or 96)");
     switch (n_out) {
     case 256: return launch_linear<256, 1>(p, w_hi, w_lo, st);
     case 288: return launch_linear<144, 2>(p, w_hi, w_lo, st);
@@ -771,6 +775,17 @@ int bm2f_linear_backward_input(const void *grad_y, const void *weight, void *gra
 {
     // grad_x[rows, in] = grad_y[rows, out] * weight[out, in]: a GEMM over k = out with w' = weight^T (in, out)
     return linear_common(grad_y, weight, nullptr, grad_x, workspace, rows, in_features, out_features, 1, split, stream);
+}
+
+int bm2f_linear_backward_input_accumulate(const void *grad_y, const void *weight, const void *addend, void *grad_x,
+                                          void *workspace, int rows, int out_features, int in_features, int split,
+                                          void *stream)
+{
+    // grad_x = grad_y * weight + addend in the GEMM epilogue: gradient branches that meet at one tensor are summed
+    // without a separate element-wise pass.  addend == grad_x accumulates in place.
+    if (!addend) return fail(BM2F_ERR_INVALID, "null addend");
+    return linear_common(grad_y, weight, nullptr, grad_x, workspace, rows, in_features, out_features, 1, split, stream, 0,
+                         nullptr, addend);
 }
 
 int bm2f_linear_backward_input_masked(const void *grad_y, const void *weight, const void *mask, void *grad_x,

@@ -294,6 +294,31 @@ at::Tensor linear_tf32x3_backward_input(const at::Tensor &grad_y, const at::Tens
     return gx;
 }
 
+// grad_x = grad_y @ weight + addend (epilogue accumulation); `out` may be the addend itself (in place) or a new tensor
+at::Tensor linear_tf32x3_backward_input_accumulate(const at::Tensor &grad_y, const at::Tensor &weight,
+                                                   const at::Tensor &addend, bool in_place, int64_t split)
+{
+    TORCH_CHECK(grad_y.is_cuda() && weight.is_cuda() && addend.is_cuda(), "CUDA tensors only");
+    TORCH_CHECK(grad_y.scalar_type() == at::kFloat && weight.scalar_type() == at::kFloat && addend.scalar_type() == at::kFloat,
+                "float32 only");
+    TORCH_CHECK(weight.dim() == 2 && grad_y.size(-1) == weight.size(0) && addend.size(-1) == weight.size(1), "shape mismatch");
+    TORCH_CHECK(linear_tf32x3_supported(weight.size(1), weight.size(0)), "unsupported layer shape");
+    TORCH_CHECK(addend.is_contiguous(), "addend must be contiguous");
+    const c10::cuda::CUDAGuard guard(grad_y.device());
+    auto g = grad_y.contiguous();
+    auto wc = weight.contiguous();
+    const int64_t rows = g.numel() / g.size(-1);
+    TORCH_CHECK(addend.numel() == rows * wc.size(1), "addend must have one row per grad_y row");
+    auto out = in_place ? addend : at::empty_like(addend);
+    auto ws = at::empty({static_cast<int64_t>(bm2f_linear_workspace_bytes(wc.size(0), wc.size(1)) / 4)}, g.options());
+    const int rc = bm2f_linear_backward_input_accumulate(g.data_ptr(), wc.data_ptr(), addend.data_ptr(), out.data_ptr(),
+                                                         ws.data_ptr(), static_cast<int>(rows), static_cast<int>(wc.size(0)),
+                                                         static_cast<int>(wc.size(1)), static_cast<int>(split),
+                                                         at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == BM2F_OK, "linear_tf32x3_backward_input_accumulate: ", bm2f_msda_last_error());
+    return out;
+}
+
 at::Tensor linear_tf32x3(const at::Tensor &x, const at::Tensor &weight, const c10::optional<at::Tensor> &bias,
                          int64_t split)
 {
@@ -528,6 +553,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("linear_tf32x3_supported", &linear_tf32x3_supported);
     m.def("linear_tf32x3_backward_weight", &linear_tf32x3_backward_weight, "grad_W = grad_y^T x, grad_b = sum grad_y (tcgen05)");
     m.def("linear_tf32x3_backward_input", &linear_tf32x3_backward_input, "grad_x = grad_y @ weight (tcgen05)");
+    m.def("linear_tf32x3_backward_input_accumulate", &linear_tf32x3_backward_input_accumulate,
+          "grad_x = grad_y @ weight + addend, summed in the GEMM epilogue");
     m.def("linear_relu_tf32x3", &linear_relu_tf32x3, "y = relu(x W^T + b) on tcgen05");
     m.def("ffn_tf32x3_backward", &ffn_tf32x3_backward, "backward of linear2(relu(linear1(x)))");
     m.def("zero_masked_rows_", &zero_masked_rows_, "in-place masked_fill(mask[..., None], 0) touching only masked rows");

@@ -7,8 +7,8 @@ checkpoints load.  Detectron2 is not needed for this part; the decoder around it
 embedding, FPN tail) is mirrored in `bm2f_b200.pixel_decoder`, which enters through `forward_tokens`.
 
 On CUDA float32 with dropout 0 (every config that selects this decoder sets DROPOUT 0.0) the layer runs:
-    q = src + pos                         torch add
-    src2 = MSDeformAttn(q, ref, src)      fused prologue + tcgen05 projections + sm_100a sampling kernels
+    src2 = MSDeformAttn(src + pos, ref, src)   value / offset / logit projections as ONE autograd node (tcgen05 GEMMs,
+                                          gradient branches summed in GEMM epilogues), fused-prologue sampling kernels
     src = LayerNorm(src + src2)           one fused kernel (csrc/ln_kernels.cuh)
     src2 = linear2(relu(linear1(src)))    two tcgen05 GEMMs (ReLU in the epilogue); backward = five tcgen05 GEMMs,
                                           the ReLU mask applied in the epilogue of the grad_h GEMM
@@ -57,6 +57,7 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
         self.dropout3 = nn.Dropout(dropout)
         self.norm2 = nn.LayerNorm(d_model)
         self.fused = True          # False: always the reference op sequence in torch
+        self.fuse_projections = True   # value / offset / logit projections of self-attention as one autograd node
 
     @staticmethod
     def with_pos_embed(tensor, pos):
@@ -77,8 +78,14 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
         return self.norm2(src)
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
-        src2 = self.self_attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes, level_start_index,
-                              padding_mask)
+        if (self.fuse_projections and self._fast_ok(src)
+                and self.self_attn.self_attention_supported(src, pos, reference_points)):
+            # query = src + pos, input = src: the three input projections run as one autograd node
+            src2 = self.self_attn.forward_self_attention(src, pos, reference_points, spatial_shapes, level_start_index,
+                                                         padding_mask)
+        else:
+            src2 = self.self_attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes,
+                                  level_start_index, padding_mask)
         if self._fast_ok(src):
             src = encoder_func.add_layernorm(src, src2, self.norm1)
         else:

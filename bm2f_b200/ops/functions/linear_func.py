@@ -61,3 +61,55 @@ def linear_tf32x3(x, weight, bias=None, split=3, row_mask=None):
 def supported(layer: torch.nn.Linear, x: torch.Tensor) -> bool:
     return (x.is_cuda and x.dtype == torch.float32 and layer.weight.dtype == torch.float32
             and MSDA.linear_tf32x3_supported(layer.in_features, layer.out_features))
+
+
+class SelfAttnProjectionsFunction(Function):
+    """The three input projections of MSDeformAttn in encoder self-attention, where query = src + pos and
+    input_flatten = src (reference: msdeformattn.py:123 calling ops/modules/ms_deform_attn.py:98-104):
+
+        value   = value_proj(src)   [masked rows zeroed]
+        offsets = sampling_offsets(src + pos)
+        logits  = attention_weights(src + pos)
+
+    as ONE autograd node, so the gradient branches that meet at `src + pos` and at `src` are summed in GEMM epilogues
+    (`linear_tf32x3_backward_input_accumulate`) instead of by two element-wise passes of the autograd engine:
+        g_q   = g_off W_o  (+)= g_logits W_a        g_src = g_value W_v + g_q        g_pos = g_q (summed over the batch
+    when pos is the shared (1, S, C) table)."""
+
+    @staticmethod
+    def forward(ctx, src, pos, wv, bv, wo, bo, wa, ba, split, row_mask):
+        q = src + pos
+        value = MSDA.linear_tf32x3(src, wv, bv, split)
+        if row_mask is not None:
+            MSDA.zero_masked_rows_(value, row_mask)          # consumer zeroes the masked rows of grad_value
+        offsets = MSDA.linear_tf32x3(q, wo, bo, split)
+        logits = MSDA.linear_tf32x3(q, wa, ba, split)
+        ctx.save_for_backward(src, q, wv, wo, wa)
+        ctx.split = split
+        ctx.pos_shape = pos.shape
+        return value, offsets, logits
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_value, g_off, g_logits):
+        src, q, wv, wo, wa = ctx.saved_tensors
+        sp = ctx.split
+        rows = src.numel() // src.shape[-1]
+        gv2 = g_value.reshape(rows, -1).contiguous()
+        go2 = g_off.reshape(rows, -1).contiguous()
+        gl2 = g_logits.reshape(rows, -1).contiguous()
+        g_src = g_pos = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            g_q = MSDA.linear_tf32x3_backward_input(go2, wo, sp)
+            MSDA.linear_tf32x3_backward_input_accumulate(gl2, wa, g_q, True, sp)            # g_q += g_logits W_a
+            if ctx.needs_input_grad[0]:
+                g_src = MSDA.linear_tf32x3_backward_input_accumulate(gv2, wv, g_q, False, sp).view_as(src)
+            if ctx.needs_input_grad[1]:
+                g_pos = g_q.view_as(src)
+                if tuple(ctx.pos_shape) != tuple(src.shape):
+                    g_pos = g_pos.sum_to_size(ctx.pos_shape)
+        x2, q2 = src.reshape(rows, -1), q.reshape(rows, -1)
+        gwv, gbv = MSDA.linear_tf32x3_backward_weight(gv2, x2, sp, True)
+        gwo, gbo = MSDA.linear_tf32x3_backward_weight(go2, q2, sp, True)
+        gwa, gba = MSDA.linear_tf32x3_backward_weight(gl2, q2, sp, True)
+        return g_src, g_pos, gwv, gbv, gwo, gbo, gwa, gba, None, None

@@ -86,6 +86,34 @@ class MSDeformAttn(nn.Module):
         y = layer(x)
         return y if row_mask is None else y.masked_fill(row_mask[..., None], float(0))
 
+    def self_attention_supported(self, src, pos, reference_points):
+        """True when `forward_self_attention` can take the call (fused prologue + tcgen05 projections, 2-d reference
+        points, float32 CUDA tensors)."""
+        return (self.fuse_prologue and self.tcgen05_linear and src.is_cuda and src.dtype == torch.float32
+                and pos is not None and pos.dtype == torch.float32 and reference_points.shape[-1] == 2
+                and reference_points.dtype == torch.float32
+                and all(linear_func.supported(l, src) for l in (self.value_proj, self.sampling_offsets, self.attention_weights))
+                and bool(MSDA.ms_deform_attn_fused_supported(self.n_heads, self.d_model // self.n_heads, self.n_levels,
+                                                             self.n_points, False)))
+
+    def forward_self_attention(self, src, pos, reference_points, input_spatial_shapes, input_level_start_index,
+                               input_padding_mask=None):
+        """Encoder self-attention: `forward(src + pos, reference_points, src, ...)` (msdeformattn.py:123) with the three
+        input projections as one autograd node (`SelfAttnProjectionsFunction`): the gradients of `src + pos` and `src`
+        are accumulated in GEMM epilogues instead of element-wise passes.  Same result as `forward`."""
+        N, Len, _ = src.shape
+        value, offsets, logits = linear_func.SelfAttnProjectionsFunction.apply(
+            src, pos, self.value_proj.weight, self.value_proj.bias, self.sampling_offsets.weight,
+            self.sampling_offsets.bias, self.attention_weights.weight, self.attention_weights.bias, 3, input_padding_mask)
+        value = value.view(N, Len, self.n_heads, self.d_model // self.n_heads)
+        offsets = offsets.view(N, Len, self.n_heads, self.n_levels, self.n_points, 2)
+        logits = logits.view(N, Len, self.n_heads, self.n_levels * self.n_points)
+        analytic = getattr(reference_points, "pixel_centres", False)
+        output = MSDeformAttnFusedFunction.apply(
+            value, input_spatial_shapes, input_level_start_index, None if analytic else reference_points.contiguous(),
+            offsets, logits, input_padding_mask)
+        return self._proj(self.output_proj, output)
+
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
                 input_padding_mask=None):
         """

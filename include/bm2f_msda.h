@@ -199,6 +199,11 @@ int bm2f_linear_relu_forward(const void *x, const void *weight, const void *bias
 int bm2f_linear_backward_input_masked(const void *grad_y, const void *weight, const void *mask, void *grad_x,
                                       void *workspace, int rows, int out_features, int in_features, int split,
                                       void *stream);
+/* grad_x = grad_y * weight + addend, the sum done in the GEMM epilogue (gradient branches meeting at one tensor:
+ * q = src + pos feeds two projections, src feeds a third).  addend (rows, in_features) may alias grad_x. */
+int bm2f_linear_backward_input_accumulate(const void *grad_y, const void *weight, const void *addend, void *grad_x,
+                                          void *workspace, int rows, int out_features, int in_features, int split,
+                                          void *stream);
 
 /*
  * Fused residual-add + LayerNorm of the encoder layer (reference: msdeformattn.py:115-131,

@@ -122,3 +122,37 @@ def test_encoder_only_end_to_end(msda):
             m.tcgen05_linear = False
     mem2, _, _ = enc(srcs, poss)
     assert (mem - mem2).abs().max().item() <= 1e-4 * max(1.0, mem2.abs().max().item())
+
+
+def test_self_attention_entry_equals_module_forward(msda):
+    """`MSDeformAttn.forward_self_attention(src, pos, ...)` (one autograd node for the three input projections, gradient
+    branches summed in GEMM epilogues) against `forward(src + pos, ref, src, ...)` of the same module: outputs and all
+    gradients, with a shared (1, S, C) position table and with a per-image one, and with a padding mask."""
+    from bm2f_b200.encoder import MSDeformAttnTransformerEncoder
+    from bm2f_b200.ops.modules import MSDeformAttn
+    torch.manual_seed(3)
+    levels = ((6, 9), (12, 18), (24, 36))
+    n, S = 2, sum(h * w for h, w in levels)
+    attn = MSDeformAttn(256, 3, 8, 4).to(DEV)
+    with torch.no_grad():
+        attn.sampling_offsets.weight.normal_(0, 0.02); attn.attention_weights.weight.normal_(0, 0.05)
+    shapes = torch.as_tensor(levels, dtype=torch.long, device=DEV)
+    start = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    ref = MSDeformAttnTransformerEncoder.get_reference_points(list(levels), torch.ones(n, 3, 2, device=DEV), DEV)
+    mask = torch.zeros(n, S, dtype=torch.bool, device=DEV); mask[1, -40:] = True
+    go = torch.randn(n, S, 256, device=DEV)
+    for pos_batch, pad in ((1, None), (n, None), (1, mask)):
+        src = torch.randn(n, S, 256, device=DEV, requires_grad=True)
+        pos = torch.randn(pos_batch, S, 256, device=DEV, requires_grad=True)
+        assert attn.self_attention_supported(src, pos, ref)
+        res = []
+        for fast in (True, False):
+            for t in [src, pos] + list(attn.parameters()):
+                t.grad = None
+            out = attn.forward_self_attention(src, pos, ref, shapes, start, pad) if fast \
+                else attn(src + pos, ref, src, shapes, start, pad)
+            out.backward(go)
+            res.append([out.detach()] + [t.grad.clone() for t in [src, pos] + list(attn.parameters())])
+        for a, b in zip(*res):
+            assert a.shape == b.shape
+            assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 2e-5

@@ -122,3 +122,23 @@ def test_linear_kernel_variants_match_default(msda, variant, name, in_features, 
         scale = ref.abs().max().item()
         assert (y1.double() - ref).abs().max().item() <= 1e-5 * scale, (name, rows)
         assert (y1 - y0).abs().max().item() <= 2e-6 * scale, (name, rows)
+
+
+@pytest.mark.parametrize("rows", [77, 128 * 5 + 17, 128 * 300])
+@pytest.mark.parametrize("out_features", [256, 192, 96])
+def test_backward_input_accumulate_matches_fp64(msda, rows, out_features):
+    """grad_x = grad_y W + addend with the sum in the GEMM epilogue, out of place and in place (addend aliases grad_x)."""
+    torch.manual_seed(rows + out_features)
+    dev = torch.device("cuda:0")
+    g = torch.randn(rows, out_features, device=dev)
+    w = torch.randn(out_features, 256, device=dev) / 16
+    add = torch.randn(rows, 256, device=dev)
+    ref = g.double() @ w.double() + add.double()
+    scale = ref.abs().max().item()
+    out = msda.linear_tf32x3_backward_input_accumulate(g, w, add, False, 3)
+    assert out.data_ptr() != add.data_ptr()
+    assert (out.double() - ref).abs().max().item() <= 5e-6 * scale
+    acc = add.clone()
+    same = msda.linear_tf32x3_backward_input_accumulate(g, w, acc, True, 3)
+    assert same.data_ptr() == acc.data_ptr()
+    assert torch.equal(acc, out)

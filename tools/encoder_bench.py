@@ -24,14 +24,17 @@ def run():
     mem, _, _ = enc(srcs, poss); mem.backward(gout); return mem
 
 res = {}
-for name, fused in (("fused_sm100a", True), ("reference_sequence_torch", False)):
+for name, fused in (("fused_sm100a", True), ("fused_sm100a, separate projection nodes", True), ("fused_sm100a", True),
+                    ("reference_sequence_torch", False)):
     set_mode(fused)
+    for m in enc.modules():
+        if hasattr(m, "fuse_projections"): m.fuse_projections = "separate" not in name
     run(); run(); torch.cuda.synchronize()
     best = 1e9
     for _ in range(args.reps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); out = run(); b.record(); torch.cuda.synchronize(); best = min(best, a.elapsed_time(b))
     res[name] = best
-    print(f"{name:28s} {best:9.2f} ms / encoder fwd+bwd (6 layers, batch {args.batch}) -> {args.batch / (best * 1e-3):8.1f} images/s, "
+    print(f"{name:42s} {best:9.2f} ms / encoder fwd+bwd (6 layers, batch {args.batch}) -> {args.batch / (best * 1e-3):8.1f} images/s, "
           f"peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB", flush=True)
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", f"encoder_bench_cfg{args.cfg}.json"), "w"))
