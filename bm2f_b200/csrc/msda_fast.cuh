@@ -16,6 +16,7 @@
 // When the queries are not the pixels of the levels (Lq != sum H*W) the same kernels walk the
 // queries in plain 1-D order.
 #pragma once
+#include <type_traits>
 
 #include "msda_common.cuh"
 
@@ -487,6 +488,246 @@ msda_fwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_
             __syncwarp();
             if (lane == 0) mbar_arrive(&ring.empty[slot]);
         }
+    });
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Forward with geometry warps.  In msda_fwd_fast_kernel the 8 channel lanes of a point group all repeat the point's
+// scalar geometry — pixel coordinates, floor, bilinear weights, range tests, corner addresses: ~45 of the ~65
+// instructions of an iteration — before they can issue their gathers.  Here NGEO extra warps do that once per point
+// (lane = (query, point) of the TMA-staged stage) and leave a 32-byte record per point in a second shared-memory ring:
+// four element offsets (-1 = corner dropped) and the four combined weights attn * bilinear.  A consumer iteration is
+// then two 128-bit shared loads, four address adds, four gathers and sixteen FMAs, in the same order and with the same
+// operands as the fast kernel, so the output is bit-identical.
+//   TMA warp -> raw ring (loc, attn) -> geometry warps -> record ring -> 16 consumer warps
+// ------------------------------------------------------------------------------------------
+template <int L_, int P_, int SW, int RSTAGES>
+struct GeoRing {
+    static constexpr int kPoints = SW * L_ * P_;
+    static constexpr int kStageBytes = kPoints * 32;
+    static constexpr int kBytes = RSTAGES * kStageBytes;
+    __device__ static __forceinline__ int4 *offs(unsigned char *base, int rslot)
+    {
+        return reinterpret_cast<int4 *>(base + rslot * kStageBytes);
+    }
+    __device__ static __forceinline__ float4 *cws(unsigned char *base, int rslot)
+    {
+        return reinterpret_cast<float4 *>(base + rslot * kStageBytes + kPoints * 16);
+    }
+};
+
+// WIDE (fp32): the consumers gather with 256-bit loads — 4 lanes x 32 B per corner, 8 corners (two points) per warp
+// instruction, the access shape with the 1.6x higher measured L1 line rate (profiles/r01_microbench.txt).  The partial
+// sums are partitioned differently across lanes, so the result equals the default kernel to rounding, not bitwise.
+template <typename T, int L_, int P_, int SW, int NWARP, int NGEO, int RSTAGES, bool FUSED = false, bool WIDE = false>
+__global__ void __launch_bounds__((NWARP + 1 + NGEO) * 32, 1)
+msda_fwd_geo_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_loc, const __grid_constant__ CUtensorMap tm_w)
+{
+    constexpr int D = 32, VEC = 4, LP = L_ * P_, LPC = D / VEC, LG = 32 / LPC, NIT = LP / LG;
+    static_assert(P_ % LG == 0, "a lane-group iteration must stay inside one level");
+    __shared__ Tabs<L_> tabs;
+    using RingT = Ring<L_, P_, SW, NGEO>;          // raw ring: released by the geometry warps
+    using Geo = GeoRing<L_, P_, SW, RSTAGES>;
+    constexpr int kStages = RingT::kStages;
+    __shared__ RingT ring;
+    __shared__ alignas(8) uint64_t rec_full[RSTAGES], rec_empty[RSTAGES];
+    extern __shared__ __align__(128) unsigned char geo_smem[];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        build_tabs<L_, SW>(tabs, p);
+        ring.init();
+        for (int i = 0; i < RSTAGES; ++i) {
+            mbar_init(&rec_full[i], NGEO);
+            mbar_init(&rec_empty[i], NWARP);
+        }
+        fence_mbar_init();
+        tma_prefetch_desc(&tm_loc);
+        tma_prefetch_desc(&tm_w);
+    }
+    __syncthreads();
+
+    if (warp == NWARP) {                                   // ---- TMA producer ----
+        if (lane == 0) ring.produce(tabs, p, &tm_loc, &tm_w);
+        return;
+    }
+    int H[L_], W[L_], st[L_];
+    float Hf[L_], Wf[L_];
+#pragma unroll
+    for (int l = 0; l < L_; ++l) {
+        H[l] = tabs.H[l]; W[l] = tabs.W[l]; st[l] = tabs.start[l];
+        Hf[l] = static_cast<float>(H[l]); Wf[l] = static_cast<float>(W[l]);
+    }
+    constexpr int MD = kHeads * D;
+
+    if (warp > NWARP) {                                    // ---- geometry warps ----
+        const int gw = warp - NWARP - 1;
+        float rW[L_], rH[L_];
+#pragma unroll
+        for (int l = 0; l < L_; ++l) { rW[l] = 1.f / Wf[l]; rH[l] = 1.f / Hf[l]; }
+        (void)rW; (void)rH;
+        for_each_stage<L_, SW>(tabs, p, [&](int s, int b, int, int q_base, int nq, int kq, int yq, int x0q) {
+            const int slot = s % kStages, rslot = s % RSTAGES;
+            mbar_wait(&ring.full[slot], (s / kStages) & 1);
+            if constexpr (FUSED) {
+                // softmax over each query's logits, lane = query (this warp's share of the stage's queries)
+                for (int qi = gw * 32 + lane; qi < nq; qi += NGEO * 32) {
+                    float4 *sw = reinterpret_cast<float4 *>(ring.w_rw(slot, qi));
+                    float4 w[L_];
+#pragma unroll
+                    for (int l = 0; l < L_; ++l) w[l] = sw[l];
+                    float mx = fmaxf(fmaxf(w[0].x, w[0].y), fmaxf(w[0].z, w[0].w));
+#pragma unroll
+                    for (int l = 1; l < L_; ++l) mx = fmaxf(mx, fmaxf(fmaxf(w[l].x, w[l].y), fmaxf(w[l].z, w[l].w)));
+                    float sum = 0.f;
+#pragma unroll
+                    for (int l = 0; l < L_; ++l) {
+                        w[l].x = __expf(w[l].x - mx); w[l].y = __expf(w[l].y - mx);
+                        w[l].z = __expf(w[l].z - mx); w[l].w = __expf(w[l].w - mx);
+                        sum += (w[l].x + w[l].y) + (w[l].z + w[l].w);
+                    }
+                    const float inv = __frcp_rn(sum);
+#pragma unroll
+                    for (int l = 0; l < L_; ++l)
+                        sw[l] = make_float4(w[l].x * inv, w[l].y * inv, w[l].z * inv, w[l].w * inv);
+                }
+                // every geometry warp normalises the queries it reads below only if the split matches; with NGEO > 1 the
+                // point loop crosses queries of the other warp, so all geometry warps meet here first
+                if (NGEO > 1) asm volatile("bar.sync 2, %0;" ::"n"(NGEO * 32) : "memory");
+                else __syncwarp();
+            }
+            mbar_wait(&rec_empty[rslot], ((s / RSTAGES) & 1) ^ 1);
+            int4 *ro = Geo::offs(geo_smem, rslot);
+            float4 *rc = Geo::cws(geo_smem, rslot);
+            const StageRef<L_> sref(kq, yq, Wf, Hf);
+            (void)sref;
+            const int npts = nq * LP;
+            for (int idx = gw * 32 + lane; idx < npts; idx += NGEO * 32) {
+                const int qi = idx / LP, j = idx - qi * LP;
+                const float2 xy = ring.loc(slot, qi)[j];
+                const float a = ring.w(slot, qi)[j];
+                int l = 0;
+#pragma unroll
+                for (int k = 1; k < L_; ++k) l = (j >= k * P_) ? k : l;
+                int Hl = H[0], Wl = W[0], stl = st[0];
+                float Hfl = Hf[0], Wfl = Wf[0], rWl = rW[0], rHl = rH[0];
+#pragma unroll
+                for (int k = 1; k < L_; ++k)
+                    if (l == k) { Hl = H[k]; Wl = W[k]; stl = st[k]; Hfl = Hf[k]; Wfl = Wf[k]; rWl = rW[k]; rHl = rH[k]; }
+                (void)rWl; (void)rHl;
+                float x = xy.x, y = xy.y;
+                if constexpr (FUSED) {
+                    const int q = q_base + qi;
+                    float2 r;
+                    if (p.ref) r = __ldg(reinterpret_cast<const float2 *>(p.ref) + (static_cast<size_t>(b) * p.Lq + q) * L_ + l);
+                    else r = sref.centre(q, x0q + qi, st, W, Wf, Hf);
+                    x = fmaf(x, rWl, r.x);
+                    y = fmaf(y, rHl, r.y);
+                }
+                const Footprint f = make_footprint(x, y, Hl, Wl, Hfl, Wfl);
+                const int e00 = (stl + f.y0 * Wl + f.x0) * MD;
+                ro[idx] = make_int4(f.ok[0] ? e00 : -1, f.ok[1] ? e00 + MD : -1, f.ok[2] ? e00 + Wl * MD : -1,
+                                    f.ok[3] ? e00 + Wl * MD + MD : -1);
+                const float wy0 = a * f.hh, wy1 = a * f.lh;
+                rc[idx] = make_float4(wy0 * f.hw, wy0 * f.lw, wy1 * f.hw, wy1 * f.lw);
+            }
+            if constexpr (FUSED) fence_proxy_async_smem();   // the raw slot (softmax written in place) goes back to TMA
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&ring.empty[slot]);
+                mbar_arrive(&rec_full[rslot]);
+            }
+        });
+        return;
+    }
+
+    // ---- consumers ----
+    const int wi = warp;
+    const int lg = lane / LPC, sub = lane % LPC;
+    const T *value = static_cast<const T *>(p.value);
+    T *out = static_cast<T *>(p.out);
+    if constexpr (WIDE) {
+        static_assert(std::is_same<T, float>::value && LP % 2 == 0, "256-bit gathers: fp32, points in pairs");
+        const int s8 = lane >> 2, sub8 = lane & 3;     // corner slot of the instruction, 8-channel group
+        const int kk = s8 & 3, pp = s8 >> 2;           // corner of the point, point of the pair
+        for_each_stage<L_, SW>(tabs, p, [&](int s, int b, int m, int q_base, int nq, int, int, int) {
+            const int rslot = s % RSTAGES;
+            mbar_wait(&rec_full[rslot], (s / RSTAGES) & 1);
+            const int *ro = reinterpret_cast<const int *>(Geo::offs(geo_smem, rslot));
+            const float *rc = reinterpret_cast<const float *>(Geo::cws(geo_smem, rslot));
+            const float *vlane = static_cast<const float *>(p.value) + (static_cast<size_t>(b) * p.S * kHeads + m) * D + sub8 * 8;
+            for (int qi = wi; qi < nq; qi += NWARP) {
+                const int q = q_base + qi;
+                float acc[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+#pragma unroll
+                for (int it = 0; it < LP / 2; ++it) {
+                    const int e = (qi * LP + it * 2 + pp) * 4 + kk;
+                    const int off = ro[e];
+                    const float cw = rc[e];
+                    float v[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) v[c] = 0.f;
+                    ldg256_pred(vlane + off, off >= 0, v);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc[c] = fmaf(cw, v[c], acc[c]);
+                }
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+                if (s8 == 0) {
+                    float4 *dst = reinterpret_cast<float4 *>(static_cast<float *>(p.out) +
+                                                             ((static_cast<size_t>(b) * p.Lq + q) * kHeads + m) * D + sub8 * 8);
+                    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&rec_empty[rslot]);
+        });
+        return;
+    }
+    for_each_stage<L_, SW>(tabs, p, [&](int s, int b, int m, int q_base, int nq, int, int, int) {
+        const int rslot = s % RSTAGES;
+        mbar_wait(&rec_full[rslot], (s / RSTAGES) & 1);
+        const int4 *ro = Geo::offs(geo_smem, rslot);
+        const float4 *rc = Geo::cws(geo_smem, rslot);
+        const T *vlane = value + (static_cast<size_t>(b) * p.S * kHeads + m) * D + sub * VEC;
+        for (int qi = wi; qi < nq; qi += NWARP) {
+            const int q = q_base + qi;
+            float acc[VEC];
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int4 o = ro[qi * LP + it * LG + lg];
+                const float4 cw4 = rc[qi * LP + it * LG + lg];
+                const int off[4] = {o.x, o.y, o.z, o.w};
+                const float cw[4] = {cw4.x, cw4.y, cw4.z, cw4.w};
+                float v[4][VEC];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                    for (int c = 0; c < VEC; ++c) v[k][c] = 0.f;
+                    if (off[k] >= 0) VecIO<T, VEC>::load(vlane + off[k], v[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int c = 0; c < VEC; ++c) acc[c] = fmaf(cw[k], v[k][c], acc[c]);
+            }
+#pragma unroll
+            for (int o = LPC; o < 32; o <<= 1)
+#pragma unroll
+                for (int c = 0; c < VEC; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+            if (lg == 0)
+                VecIO<T, VEC>::store(out + ((static_cast<size_t>(b) * p.Lq + q) * kHeads + m) * D + sub * VEC, acc);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&rec_empty[rslot]);
     });
 }
 

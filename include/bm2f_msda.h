@@ -82,7 +82,9 @@ typedef struct {
     int order;      /* 0 = default; 1 = 1-D query order (ignore level geometry)                  */
     int merge;      /* backward: 1 = merge equal-pixel corners in-warp before the REDs; 0/2 = off
                        (default: measured slower on B200)                          */
-    int reserved[8];
+    int geo;        /* forward: 1 = geometry warps (per-point footprints computed once, records in shared
+                       memory), 2 = off; 0 = default                                  */
+    int reserved[7];
 } bm2f_msda_tuning_t;
 
 /* Library / ABI identification. */

@@ -418,3 +418,42 @@ def test_fused_analytic_reference_points_bit_identical(levels, batch, built):
     with pytest.raises(cabi.MSDAError, match="num_query == spatial_size"):
         cabi.fused_forward(v.data_ptr(), sh.data_ptr(), st.data_ptr(), 0, o.data_ptr(), lg.data_ptr(), out.data_ptr(),
                            (N, S, M, D, L, S - 1, 4), cabi.DTYPE_F32, None, stream)
+
+
+@pytest.mark.parametrize("levels,batch", [(SMALL_LEVELS, 3), (((1, 1), (3, 2), (25, 38)), 2), (((5, 7), (9, 13)), 1),
+                                          (W.WORKLOADS[1].levels, 1), (((32, 32), (64, 64), (16, 16), (8, 8)), 2)])
+def test_geometry_warp_forward_bit_identical(levels, batch, built):
+    """tuning.geo = 1: per-point footprints / weights / corner offsets computed once by geometry warps and handed to the
+    consumers through shared-memory records.  Same operands and FMA order as the default forward, so the output is
+    bit-identical — plain and fused entry points, strip-walked and raster-walked levels, a 1 x 1 level, L = 2, 3, 4."""
+    base, _, offsets, logits = _fused_inputs(levels, batch, 970 + len(levels))
+    dev = _dev()
+    L = len(levels)
+    sh, st = base["shapes"].to(dev), base["start"].to(dev)
+    v, lc, at, o, lg = (t.to(dev).contiguous() for t in (base["value"], base["loc"], base["attn"], offsets, logits))
+    N, S, M, D = v.shape
+    dims = (N, S, M, D, L, S, 4)
+    stream = torch.cuda.current_stream().cuda_stream
+    geo = cabi.make_tuning(geo=1)
+    res = {}
+    for name, tun in (("default", None), ("geo", geo)):
+        out_p = torch.full((N, S, M * D), float("nan"), device=dev)
+        out_f = torch.full((N, S, M * D), float("nan"), device=dev)
+        cabi.forward(v.data_ptr(), sh.data_ptr(), st.data_ptr(), lc.data_ptr(), at.data_ptr(), out_p.data_ptr(), dims,
+                     cabi.DTYPE_F32, tun, stream)
+        cabi.fused_forward(v.data_ptr(), sh.data_ptr(), st.data_ptr(), 0, o.data_ptr(), lg.data_ptr(), out_f.data_ptr(),
+                           dims, cabi.DTYPE_F32, tun, stream)
+        torch.cuda.synchronize()
+        res[name] = (out_p, out_f)
+    assert not torch.isnan(res["geo"][0]).any() and not torch.isnan(res["geo"][1]).any()
+    assert torch.equal(res["default"][0], res["geo"][0])
+    assert torch.equal(res["default"][1], res["geo"][1])
+    if L == 3:
+        # geo = 3: the same records consumed with 256-bit gathers (8 corners per warp instruction); the partial sums
+        # are split differently across lanes, so equality is to rounding
+        out_w = torch.full((N, S, M * D), float("nan"), device=dev)
+        cabi.forward(v.data_ptr(), sh.data_ptr(), st.data_ptr(), lc.data_ptr(), at.data_ptr(), out_w.data_ptr(), dims,
+                     cabi.DTYPE_F32, cabi.make_tuning(geo=3), stream)
+        torch.cuda.synchronize()
+        scale = res["default"][0].abs().max().item()
+        assert (out_w - res["default"][0]).abs().max().item() <= 2e-6 * max(scale, 1.0)

@@ -1,0 +1,46 @@
+"""A/B of the forward kernels at cfg 2: default fast kernel vs geometry-warp kernel (tuning.geo = 1), plain and fused
+entry points; outputs must be bit-identical.   python tools/geo_ab.py [batch] [reps]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from bm2f_b200 import cabi
+from bm2f_b200 import workloads as W
+
+batch = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+dev = torch.device("cuda:0"); torch.manual_seed(0)
+wl = W.WORKLOADS[2]; levels = list(wl.levels); L, M, D, P = len(levels), 8, 32, 4
+S = sum(h * w for h, w in levels)
+shapes, start = W.level_tensors(levels); shapes, start = shapes.to(dev), start.to(dev)
+value = torch.randn(batch, S, M, D, device=dev)
+ref = W.reference_points(levels, batch).to(dev).contiguous()
+offsets = (W.compass_offset_bias(M, L, P)[None, None].to(dev) + torch.randn(batch, S, M, L, P, 2, device=dev)).contiguous()
+logits = torch.randn(batch, S, M, L * P, device=dev)
+norm = torch.stack((shapes[:, 1], shapes[:, 0]), -1).float()
+loc = (ref[:, :, None, :, None, :] + offsets / norm[None, None, None, :, None, :]).contiguous()
+attn = torch.softmax(logits, -1).view(batch, S, M, L, P).contiguous()
+outs = {k: torch.empty(batch, S, M * D, device=dev) for k in ("plain", "plain_geo", "plain_geo_wide", "fused", "fused_geo")}
+dims = (batch, S, M, D, L, S, P); st = torch.cuda.current_stream().cuda_stream
+geo = cabi.make_tuning(geo=1); geow = cabi.make_tuning(geo=3)
+P_ = lambda t: t.data_ptr()
+fns = {
+    "plain": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["plain"]), dims, 0, None, st),
+    "plain_geo": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["plain_geo"]), dims, 0, geo, st),
+    "plain_geo_wide": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["plain_geo_wide"]), dims, 0, geow, st),
+    "fused": lambda: cabi.fused_forward(P_(value), P_(shapes), P_(start), 0, P_(offsets), P_(logits), P_(outs["fused"]), dims, 0, None, st),
+    "fused_geo": lambda: cabi.fused_forward(P_(value), P_(shapes), P_(start), 0, P_(offsets), P_(logits), P_(outs["fused_geo"]), dims, 0, geo, st),
+}
+def t(fn):
+    fn(); fn(); torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize(); best = min(best, a.elapsed_time(b))
+    return best
+for k, fn in fns.items():
+    print(f"{k:10s} {t(fn):7.3f} ms", flush=True)
+print("plain_geo == plain:", bool(torch.equal(outs["plain"], outs["plain_geo"])),
+      " fused_geo == fused:", bool(torch.equal(outs["fused"], outs["fused_geo"])),
+      " max |wide - plain|", float((outs["plain_geo_wide"] - outs["plain"]).abs().max()),
+      " max |fused - plain|", float((outs["fused"] - outs["plain"]).abs().max()))
