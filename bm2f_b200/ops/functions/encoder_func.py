@@ -51,8 +51,10 @@ class AddLayerNormFunction(Function):
         return dz, dz, dgamma, dbeta, None
 
 
-def ffn(x, linear1: torch.nn.Linear, linear2: torch.nn.Linear, split=3):
-    return FFNFunction.apply(x, linear1.weight, linear1.bias, linear2.weight, linear2.bias, split)
+def ffn(x, linear1: torch.nn.Linear, linear2: torch.nn.Linear, split=None):
+    from .linear_func import matmul_split
+    return FFNFunction.apply(x, linear1.weight, linear1.bias, linear2.weight, linear2.bias,
+                             matmul_split() if split is None else split)
 
 
 def add_layernorm(x, residual, norm: torch.nn.LayerNorm):

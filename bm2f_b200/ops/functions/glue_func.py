@@ -85,7 +85,7 @@ class InputProjFlattenFunction(Function):
         return (None, None, None, *gxs, *gparams)
 
 
-def input_proj_flatten(xs, input_proj, split=3):
+def input_proj_flatten(xs, input_proj, split=None):
     """xs: list of (N, C_l, H_l, W_l) CUDA float32 features, lowest resolution first (msdeformattn.py:319-321);
     input_proj: ModuleList of Sequential(Conv2d(C_l, 256, 1), GroupNorm(32, 256)).  Returns (N, S, 256)."""
     params = []
@@ -93,6 +93,9 @@ def input_proj_flatten(xs, input_proj, split=3):
         conv, gn = seq[0], seq[1]
         params += [conv.weight, conv.bias, gn.weight, gn.bias]
     eps = input_proj[0][1].eps
+    if split is None:
+        from .linear_func import conv_split
+        split = conv_split()          # follows torch.backends.cudnn.allow_tf32 like the reference's nn.Conv2d
     return InputProjFlattenFunction.apply(len(xs), eps, split, *xs, *params)
 
 

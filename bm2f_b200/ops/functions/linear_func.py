@@ -18,6 +18,20 @@ MSDA = load_extension()
 USE_TCGEN05_DW = True
 
 
+def matmul_split() -> int:
+    """TF32 terms of the tcgen05 GEMMs that replace nn.Linear: 3 (fp32-grade, tf32x3) unless the user has allowed TF32
+    matmuls (`torch.backends.cuda.matmul.allow_tf32` / `set_float32_matmul_precision("high")`), in which case nn.Linear in
+    the reference would run single-pass TF32 too and one term is used.  Mask2Former leaves the flag at its default
+    (off), so the default is 3."""
+    return 1 if torch.backends.cuda.matmul.allow_tf32 else 3
+
+
+def conv_split() -> int:
+    """Same for the 1x1 `input_proj` convolutions: torch's convolutions follow `torch.backends.cudnn.allow_tf32`, which
+    defaults to True, so by default the reference runs them in single-pass TF32 and so do we."""
+    return 1 if torch.backends.cudnn.allow_tf32 else 3
+
+
 class LinearTF32x3Function(Function):
     @staticmethod
     def forward(ctx, x, weight, bias, split, row_mask=None):
@@ -52,10 +66,10 @@ class LinearTF32x3Function(Function):
         return gx, gw, gb, None, None
 
 
-def linear_tf32x3(x, weight, bias=None, split=3, row_mask=None):
+def linear_tf32x3(x, weight, bias=None, split=None, row_mask=None):
     """Drop-in for F.linear(x, weight, bias) on CUDA float32 tensors (in_features a multiple of 256, output width a
-    multiple of 256 or 288 / 192 / 96)."""
-    return LinearTF32x3Function.apply(x, weight, bias, split, row_mask)
+    multiple of 256 or 288 / 192 / 96).  split=None: follow torch's matmul precision flag (`matmul_split`)."""
+    return LinearTF32x3Function.apply(x, weight, bias, matmul_split() if split is None else split, row_mask)
 
 
 def supported(layer: torch.nn.Linear, x: torch.Tensor) -> bool:

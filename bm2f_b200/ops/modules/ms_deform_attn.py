@@ -104,7 +104,8 @@ class MSDeformAttn(nn.Module):
         N, Len, _ = src.shape
         value, offsets, logits = linear_func.SelfAttnProjectionsFunction.apply(
             src, pos, self.value_proj.weight, self.value_proj.bias, self.sampling_offsets.weight,
-            self.sampling_offsets.bias, self.attention_weights.weight, self.attention_weights.bias, 3, input_padding_mask)
+            self.sampling_offsets.bias, self.attention_weights.weight, self.attention_weights.bias,
+            linear_func.matmul_split(), input_padding_mask)
         value = value.view(N, Len, self.n_heads, self.d_model // self.n_heads)
         offsets = offsets.view(N, Len, self.n_heads, self.n_levels, self.n_points, 2)
         logits = logits.view(N, Len, self.n_heads, self.n_levels * self.n_points)

@@ -25,6 +25,17 @@ def msda(built):
     return bm2f_b200.load_extension()
 
 
+@pytest.fixture
+def fp32_convs():
+    """torch's convolutions default to TF32 on this GPU (`torch.backends.cudnn.allow_tf32 = True`), for the reference as
+    for this repo: the FPN tail runs on the library convolutions and the 1x1 `input_proj` GEMMs follow the same flag
+    (one TF32 pass instead of three).  The golden vectors / float64 references need float32-grade arithmetic."""
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32 = old
+
+
 @pytest.mark.parametrize("shape", [(1, 1, 1), (2, 320, 6), (3, 33, 65), (2, 512, 4096), (1, 7, 1000)])
 def test_transpose_batched(msda, shape):
     torch.manual_seed(0)
@@ -81,7 +92,7 @@ def _input_proj(chans, seed):
 
 
 @pytest.mark.parametrize("channels_last", [False, True])
-def test_input_proj_flatten_vs_torch_fp64(msda, channels_last):
+def test_input_proj_flatten_vs_torch_fp64(msda, fp32_convs, channels_last):
     """conv1x1 + GroupNorm + flatten + cat in one function vs the reference op sequence (msdeformattn.py:66-82, 321) in
     fp64; 512 / 256 channels run on the tcgen05 GEMMs, 320 on the library GEMM, all on the token GroupNorm kernels."""
     from bm2f_b200.ops.functions import glue_func
@@ -136,16 +147,6 @@ def _run_decoder(dec, G):
     return {k: v.detach().cpu().numpy() for k, v in res.items()}
 
 
-@pytest.fixture
-def fp32_convs():
-    """The FPN tail runs on torch's library convolutions, which default to TF32 on this GPU (as they do for the
-    reference); the golden vectors are CPU float32, so the comparison pins them to float32."""
-    old = torch.backends.cudnn.allow_tf32
-    torch.backends.cudnn.allow_tf32 = False
-    yield
-    torch.backends.cudnn.allow_tf32 = old
-
-
 @pytest.mark.parametrize("fused", [True, False])
 def test_pixel_decoder_matches_reference_golden(msda, fp32_convs, fused):
     """Whole decoder (input_proj, position embedding, 2 encoder layers, FPN tail), forward and backward, against the
@@ -179,3 +180,25 @@ def test_pixel_decoder_fused_equals_reference_sequence_channels_last(msda, fp32_
         b = dec.forward_features(feats)
     for x, y in zip([a[0], a[1]] + list(a[2]), [b[0], b[1]] + list(b[2])):
         assert rel_err(x.cpu().numpy(), y.cpu().numpy()) <= 5e-5
+
+
+def test_input_proj_follows_the_conv_tf32_flag(msda):
+    """`torch.backends.cudnn.allow_tf32` (default True) selects one TF32 pass for the 1x1 input_proj GEMMs, as it does
+    for the reference's nn.Conv2d; switched off, the GEMMs use the three-term split (fp32-grade)."""
+    from bm2f_b200.ops.functions import glue_func
+    chans, sizes, n = [512, 256], [(6, 10), (12, 20)], 2
+    proj = _input_proj(chans, 2)
+    xs = [torch.randn(n, c, h, w, device=DEV) for c, (h, w) in zip(chans, sizes)]
+    proj64 = _input_proj(chans, 2).double()
+    ref = torch.cat([proj64[i](x.double()).flatten(2).transpose(1, 2) for i, x in enumerate(xs)], 1)
+    old = torch.backends.cudnn.allow_tf32
+    try:
+        errs = {}
+        for flag in (True, False):
+            torch.backends.cudnn.allow_tf32 = flag
+            with torch.no_grad():
+                errs[flag] = rel_err(glue_func.input_proj_flatten(xs, proj).cpu().numpy(), ref.cpu().numpy())
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert errs[False] <= 1e-5
+    assert 2e-5 <= errs[True] <= 5e-3, errs

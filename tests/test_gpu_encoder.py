@@ -156,3 +156,37 @@ def test_self_attention_entry_equals_module_forward(msda):
         for a, b in zip(*res):
             assert a.shape == b.shape
             assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 2e-5
+
+
+def test_module_gemms_follow_the_matmul_tf32_flag(msda):
+    """`torch.backends.cuda.matmul.allow_tf32` (default False; Mask2Former leaves it off) selects one TF32 pass for the
+    projections / FFN exactly where the reference's nn.Linear would run TF32; off = three-term split, fp32-grade."""
+    from bm2f_b200.encoder import MSDeformAttnTransformerEncoderLayer, MSDeformAttnTransformerEncoder
+    torch.manual_seed(11)
+    levels = ((8, 8), (16, 16), (32, 32))
+    n, S = 2, sum(h * w for h, w in levels)
+    layer = MSDeformAttnTransformerEncoderLayer(256, 1024, 0.0, "relu", 3, 8, 4).to(DEV)
+    shapes = torch.as_tensor(levels, dtype=torch.long, device=DEV)
+    start = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    ref_pts = MSDeformAttnTransformerEncoder.get_reference_points(list(levels), torch.ones(n, 3, 2, device=DEV), DEV)
+    src, pos = torch.randn(n, S, 256, device=DEV), torch.randn(1, S, 256, device=DEV) * 0.1
+    old = torch.backends.cuda.matmul.allow_tf32
+    try:
+        with torch.no_grad():
+            torch.backends.cuda.matmul.allow_tf32 = False
+            exact = layer(src, pos, ref_pts, shapes, start)
+            layer.fused = False
+            for m in layer.modules():
+                if hasattr(m, "tcgen05_linear"): m.tcgen05_linear = False; m.fuse_prologue = False
+            want = layer(src, pos, ref_pts, shapes, start)          # cuBLAS fp32 + torch ops around the sampling op
+            layer.fused = True
+            for m in layer.modules():
+                if hasattr(m, "tcgen05_linear"): m.tcgen05_linear = True; m.fuse_prologue = True
+            torch.backends.cuda.matmul.allow_tf32 = True
+            fast = layer(src, pos, ref_pts, shapes, start)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    e_exact = rel_err(exact.cpu().numpy(), want.cpu().numpy())
+    e_fast = rel_err(fast.cpu().numpy(), want.cpu().numpy())
+    assert e_exact <= 2e-5, e_exact
+    assert 2e-5 < e_fast <= 1e-2, e_fast

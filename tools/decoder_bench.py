@@ -12,7 +12,7 @@ from bm2f_b200.ops.functions import glue_func
 
 ap = argparse.ArgumentParser(); ap.add_argument("--cfg", type=int, default=2); ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--reps", type=int, default=3); ap.add_argument("--layers", type=int, default=6)
-ap.add_argument("--channels-last", action="store_true"); ap.add_argument("--split", type=int, default=3)
+ap.add_argument("--channels-last", action="store_true"); ap.add_argument("--split", type=int, default=None, help="TF32 terms of the input_proj GEMMs; default: follow torch.backends.cudnn.allow_tf32")
 ap.add_argument("--profile", action="store_true"); args = ap.parse_args()
 wl = W.WORKLOADS[args.cfg]; dev = torch.device("cuda:0"); torch.manual_seed(0)
 levels = list(wl.levels)                       # lowest resolution first: res5, res4, res3
