@@ -180,6 +180,36 @@ float time_ms(F launch, int reps)
     return best;
 }
 
+
+// Shared-memory integer reductions in the backward's access shape (fixed-point accumulation of the 32 x 32
+// level on chip): the accumulator of one (image, head) is 1024 pixels x 32 int32 words = 128 KB.  A warp instruction
+// = 4 point groups x 8 lanes; a group adds one corner line (32 words) at a pseudo-random pixel with 4 x
+// red.shared.add.u32 per lane (there is no vector form).  SWZ rotates a pixel's channel groups by 8 words per
+// (pixel & 3) so that the 4 groups of an instruction do not land on the same banks by construction.
+template <int SWZ>
+__global__ void __launch_bounds__(512) smem_red_kernel(int iters, uint32_t *sink)
+{
+    extern __shared__ uint32_t acc[];
+    for (int i = threadIdx.x; i < 1024 * 32; i += blockDim.x) acc[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, grp = lane >> 3, l8 = lane & 7;
+    uint32_t seed = (blockIdx.x * blockDim.x + threadIdx.x) / 8 * 4 + grp + 12345u;
+    for (int it = 0; it < iters; ++it) {
+        seed = mix(seed + it);
+        const uint32_t pix = seed & 1023u;
+        const uint32_t rot = SWZ ? (pix & 3u) * 8u : 0u;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t w = pix * 32u + ((l8 * 4u + c + rot) & 31u);
+            asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(acc + w))),
+                         "r"(seed >> 8)
+                         : "memory");
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) sink[blockIdx.x] = acc[blockIdx.x & 1023];
+}
+
 int main()
 {
     cudaDeviceProp prop;
@@ -316,6 +346,26 @@ int main()
             const float ms = time_ms(launch, 3);
             printf("hybrid_red_v4+tma512  ctas %4d  %9.1f GB/s\n", g, (double)(g * threads / 32) * it * 8 * 128.0 / ms * 1e-6);
         }
+    }
+    // shared-memory integer reductions, backward access shape (one 128-KB accumulator per CTA)
+    {
+        const int it = 4000, threads = 512;
+        CK(cudaFuncSetAttribute(smem_red_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        CK(cudaFuncSetAttribute(smem_red_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        uint32_t *isink;
+        CK(cudaMalloc(&isink, 4096));
+        for (int swz = 0; swz < 2; ++swz) {
+            auto launch = [&] {
+                if (swz) smem_red_kernel<1><<<sms, threads, 128 * 1024>>>(it, isink);
+                else smem_red_kernel<0><<<sms, threads, 128 * 1024>>>(it, isink);
+                CK(cudaGetLastError());
+            };
+            const float ms = time_ms(launch, 3);
+            const double lines = (double)sms * (threads / 8) * it;      // corner lines (32 words = 128 B) added
+            printf("smem_red_u32 %s  %9.1f GB/s of 128-B corner lines = %.2f cycles per line per SM at 1.9 GHz\n",
+                   swz ? "swizzled" : "plain   ", lines * 128.0 / ms * 1e-6, 1.9e9 * ms * 1e-3 * sms / lines);
+        }
+        CK(cudaFree(isink));
     }
     // plain streaming copy for reference (same denominator as MEASURED_PEAKS.json hbm_gbs)
     {
