@@ -164,16 +164,16 @@ cudaError_t launch_fused(bool bwd, const FastParams &p, const CUtensorMap &ml, c
 
 // Forward with geometry warps (msda_fwd_geo_kernel): 16 consumer warps + TMA warp + kGeoWarps geometry warps.
 constexpr int kGeoWarps = 2, kGeoStages = 4;
-template <typename T, int L_, bool FUSED, bool WIDE = false>
+template <typename T, int L_, bool FUSED, bool WIDE = false, int CPS = 1>
 int launch_geo(const FastParams &p, const CUtensorMap &ml, const CUtensorMap &mw, int grid, cudaStream_t st)
 {
     constexpr int SW = 32;
     constexpr int threads = (kNWarp + 1 + kGeoWarps) * 32;
     constexpr int smem = GeoRing<L_, 4, SW, kGeoStages>::kBytes;
-    int rc = ensure_dynamic_smem<&msda_fwd_geo_kernel<T, L_, 4, SW, kNWarp, kGeoWarps, kGeoStages, FUSED, WIDE>>(
+    int rc = ensure_dynamic_smem<&msda_fwd_geo_kernel<T, L_, 4, SW, kNWarp, kGeoWarps, kGeoStages, FUSED, WIDE, CPS>>(
         smem, "cudaFuncSetAttribute(geometry-warp forward smem)");
     if (rc) return rc;
-    msda_fwd_geo_kernel<T, L_, 4, SW, kNWarp, kGeoWarps, kGeoStages, FUSED, WIDE><<<grid, threads, smem, st>>>(p, ml, mw);
+    msda_fwd_geo_kernel<T, L_, 4, SW, kNWarp, kGeoWarps, kGeoStages, FUSED, WIDE, CPS><<<grid, threads, smem, st>>>(p, ml, mw);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "launch msda_fwd_geo_kernel");
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -317,6 +317,8 @@ int run_fast(bool bwd, FastParams p, const Dims &d, int dtype, const bm2f_msda_t
     }
 
     // geometry-warp forward (float32, TMA staging, strip 32): opt-in through tuning.geo = 1
+    if (!bwd && t.geo == 1 && c.tma && c.sw == 32 && c.cps == 2 && dtype == BM2F_DTYPE_F32 && d.L == 3 && !fused)
+        return launch_geo<float, 3, false, false, 2>(p, ml, mw, grid, st);  // two CTAs per SM (cfg shape only)
     if (!bwd && t.geo == 3 && c.tma && c.sw == 32 && c.cps == 1 && dtype == BM2F_DTYPE_F32 && d.L == 3 && !fused)
         return launch_geo<float, 3, false, true>(p, ml, mw, grid, st);      // + 256-bit gathers (cfg shape only)
     if (!bwd && t.geo == 1 && c.tma && c.sw == 32 && c.cps == 1 && !c.wide && dtype == BM2F_DTYPE_F32) {

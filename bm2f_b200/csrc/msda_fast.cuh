@@ -520,8 +520,9 @@ struct GeoRing {
 // WIDE (fp32): the consumers gather with 256-bit loads — 4 lanes x 32 B per corner, 8 corners (two points) per warp
 // instruction, the access shape with the 1.6x higher measured L1 line rate (profiles/r01_microbench.txt).  The partial
 // sums are partitioned differently across lanes, so the result equals the default kernel to rounding, not bitwise.
-template <typename T, int L_, int P_, int SW, int NWARP, int NGEO, int RSTAGES, bool FUSED = false, bool WIDE = false>
-__global__ void __launch_bounds__((NWARP + 1 + NGEO) * 32, 1)
+template <typename T, int L_, int P_, int SW, int NWARP, int NGEO, int RSTAGES, bool FUSED = false, bool WIDE = false,
+          int CPS = 1>
+__global__ void __launch_bounds__((NWARP + 1 + NGEO) * 32, CPS)
 msda_fwd_geo_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_loc, const __grid_constant__ CUtensorMap tm_w)
 {
     constexpr int D = 32, VEC = 4, LP = L_ * P_, LPC = D / VEC, LG = 32 / LPC, NIT = LP / LG;

@@ -457,3 +457,9 @@ def test_geometry_warp_forward_bit_identical(levels, batch, built):
         torch.cuda.synchronize()
         scale = res["default"][0].abs().max().item()
         assert (out_w - res["default"][0]).abs().max().item() <= 2e-6 * max(scale, 1.0)
+        # geo = 1 with two CTAs per SM (47 registers per thread): bit-identical again
+        out_2 = torch.full((N, S, M * D), float("nan"), device=dev)
+        cabi.forward(v.data_ptr(), sh.data_ptr(), st.data_ptr(), lc.data_ptr(), at.data_ptr(), out_2.data_ptr(), dims,
+                     cabi.DTYPE_F32, cabi.make_tuning(geo=1, ctas_per_sm=2), stream)
+        torch.cuda.synchronize()
+        assert torch.equal(out_2, res["default"][0])

@@ -20,13 +20,14 @@ logits = torch.randn(batch, S, M, L * P, device=dev)
 norm = torch.stack((shapes[:, 1], shapes[:, 0]), -1).float()
 loc = (ref[:, :, None, :, None, :] + offsets / norm[None, None, None, :, None, :]).contiguous()
 attn = torch.softmax(logits, -1).view(batch, S, M, L, P).contiguous()
-outs = {k: torch.empty(batch, S, M * D, device=dev) for k in ("plain", "plain_geo", "plain_geo_wide", "fused", "fused_geo")}
+outs = {k: torch.empty(batch, S, M * D, device=dev) for k in ("plain", "plain_geo", "plain_geo_2cta", "plain_geo_wide", "fused", "fused_geo")}
 dims = (batch, S, M, D, L, S, P); st = torch.cuda.current_stream().cuda_stream
-geo = cabi.make_tuning(geo=1); geow = cabi.make_tuning(geo=3)
+geo = cabi.make_tuning(geo=1); geow = cabi.make_tuning(geo=3); geo2 = cabi.make_tuning(geo=1, ctas_per_sm=2)
 P_ = lambda t: t.data_ptr()
 fns = {
     "plain": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["plain"]), dims, 0, None, st),
     "plain_geo": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["plain_geo"]), dims, 0, geo, st),
+    "plain_geo_2cta": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["plain_geo_2cta"]), dims, 0, geo2, st),
     "plain_geo_wide": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["plain_geo_wide"]), dims, 0, geow, st),
     "fused": lambda: cabi.fused_forward(P_(value), P_(shapes), P_(start), 0, P_(offsets), P_(logits), P_(outs["fused"]), dims, 0, None, st),
     "fused_geo": lambda: cabi.fused_forward(P_(value), P_(shapes), P_(start), 0, P_(offsets), P_(logits), P_(outs["fused_geo"]), dims, 0, geo, st),
@@ -40,6 +41,7 @@ def t(fn):
     return best
 for k, fn in fns.items():
     print(f"{k:10s} {t(fn):7.3f} ms", flush=True)
+print("plain_geo_2cta == plain:", bool(torch.equal(outs["plain"], outs["plain_geo_2cta"])))
 print("plain_geo == plain:", bool(torch.equal(outs["plain"], outs["plain_geo"])),
       " fused_geo == fused:", bool(torch.equal(outs["fused"], outs["fused_geo"])),
       " max |wide - plain|", float((outs["plain_geo_wide"] - outs["plain"]).abs().max()),
