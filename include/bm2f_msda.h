@@ -82,8 +82,9 @@ typedef struct {
     int order;      /* 0 = default; 1 = 1-D query order (ignore level geometry)                  */
     int merge;      /* backward: 1 = merge equal-pixel corners in-warp before the REDs; 0/2 = off
                        (default: measured slower on B200)                          */
-    int geo;        /* forward: 1 = geometry warps (per-point footprints computed once, records in shared
-                       memory), 2 = off; 0 = default                                  */
+    int geo;        /* forward A/B variants (same results): 1 = geometry warps (per-point footprints
+                       computed once, 32-byte records in shared memory; with ctas_per_sm = 2: two CTAs per SM),
+                       3 = geometry warps + 256-bit gathers (L = 3); 0 / 2 = default kernel                   */
     int reserved[7];
 } bm2f_msda_tuning_t;
 
