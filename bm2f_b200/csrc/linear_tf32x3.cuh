@@ -361,274 +361,6 @@ constexpr int kGemmProducerWarps = 4;   // activation producers (8 measured slow
 constexpr int kGemmThreadsPersistent = (2 + kGemmProducerWarps + 4) * 32;
 constexpr int gemm_threads_persistent(int producer_warps) { return (2 + producer_warps + 4) * 32; }
 
-// CL = 2: thread-block cluster of two CTAs working on neighbouring row tiles in lockstep.  Each CTA fetches HALF of every
-// weight k-block and TMA-multicasts it to both, so the weight stream out of L2 (the contended resource of this kernel:
-// 512 KB per 128-row tile) is halved; a stage is released to both TMA producers by multicast tcgen05.commit arrivals.
-// PW activation-producer warps keep XD k-blocks of X in flight in registers: (XD - 1) * 16 KB outstanding per SM.
-template <int NT, int CL = 1, int PW = kGemmProducerWarps, int XD = 3>
-__global__ void __launch_bounds__(gemm_threads_persistent(PW), 1)
-linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CUtensorMap tm_whi,
-                                const __grid_constant__ CUtensorMap tm_wlo, const __grid_constant__ CUtensorMap tm_y)
-{
-    constexpr int N = NT;
-    constexpr int kXBytes = kGemmBlockM * kGemmBlockK * 4;
-    constexpr int kWBytes = N * kGemmBlockK * 4;
-    constexpr int kStageBytes = 2 * kXBytes + 2 * kWBytes;
-    constexpr uint32_t kTmemCols = (2 * N <= 64) ? 64 : (2 * N <= 128) ? 128 : (2 * N <= 256) ? 256 : 512;
-    static_assert(NT % 16 == 0 && NT <= 256, "UMMA N for M = 128, two accumulators in 512 TMEM columns");
-
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    unsigned char *staging = smem + kGemmStages * kStageBytes;            // 2 x 16 KB epilogue tiles
-    __shared__ uint64_t full_bar[kGemmStages], empty_bar[kGemmStages], acc_full[2], acc_empty[2];
-    __shared__ uint32_t tmem_base_slot;
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kKBlocks = p.K / kGemmBlockK;
-    const int slices = p.slices;
-    // the cluster (CL CTAs) walks virtual tiles = (group of CL row tiles, slice); CTA `crank` owns row tile group * CL + crank
-    const int crank = CL > 1 ? static_cast<int>(blockIdx.x) % CL : 0;
-    const int cid = static_cast<int>(blockIdx.x) / CL, ncl = static_cast<int>(gridDim.x) / CL;
-    const int row_tiles = (p.M + kGemmBlockM - 1) / kGemmBlockM;
-    const int num_tiles = ((row_tiles + CL - 1) / CL) * slices;   // tile = row_tile_group * slices + slice
-    // (row tile, slice) of a tile index advance incrementally: an integer division per tile / k-block in the
-    // single-threaded TMA and MMA roles costs ~200 cycles of latency each and made this kernel 1.7x slower (measured)
-    const int step_rt = ncl / slices, step_sl = ncl % slices;
-    struct TileIter {
-        int tile, rt, sl;
-    };
-    auto first_tile = [&]() { return TileIter{cid, cid / slices, cid % slices}; };
-    auto next_tile = [&](TileIter &t) {
-        t.tile += ncl;
-        t.rt += step_rt;
-        t.sl += step_sl;
-        if (t.sl >= slices) { t.sl -= slices; ++t.rt; }
-    };
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kGemmStages; ++s) {
-            mbar_init(&full_bar[s], PW * 32 + 1);
-            mbar_init(&empty_bar[s], CL);      // one tcgen05.commit arrival from every CTA of the cluster
-        }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(&acc_full[b], 1);        // tcgen05.commit after the last k-block of a tile
-            mbar_init(&acc_empty[b], 128);     // every epilogue thread, after its last TMEM read of the tile
-        }
-        fence_mbar_init();
-        tma_prefetch_desc(&tm_whi);
-        tma_prefetch_desc(&tm_wlo);
-        tma_prefetch_desc(&tm_y);
-    }
-    if (warp == 0) tmem_alloc(&tmem_base_slot, kTmemCols);
-    tc_fence_before();
-    __syncthreads();
-    if (CL > 1) cluster_sync_all();        // peers' barriers are initialised before anything is multicast to them
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_base_slot;
-    auto stage_ptr = [&](int s) { return smem + s * kStageBytes; };
-
-    if (warp == 0) {
-        if (lane == 0) {                                   // ---- TMA producer (W_hi, W_lo) ----
-            int g = 0;
-            for (TileIter ti = first_tile(); ti.tile < num_tiles; next_tile(ti)) {
-                const int wrow = ti.sl * NT;
-                for (int kb = 0; kb < kKBlocks; ++kb, ++g) {
-                    const int s = g % kGemmStages;
-                    mbar_wait_bounded(&empty_bar[s], ((g / kGemmStages) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[s], p.split == 3 ? 2 * kWBytes : kWBytes);
-                    unsigned char *w_hi = stage_ptr(s) + 2 * kXBytes;
-                    if (CL == 1) {
-                        tma_load_2d(w_hi, &tm_whi, kb * kGemmBlockK, wrow, &full_bar[s]);
-                        if (p.split == 3) tma_load_2d(w_hi + kWBytes, &tm_wlo, kb * kGemmBlockK, wrow, &full_bar[s]);
-                    } else {
-                        // this CTA's share of the weight rows, delivered to every CTA of the cluster
-                        constexpr int kShare = NT / CL;
-                        constexpr uint16_t kMask = (1u << CL) - 1;
-                        unsigned char *dst = w_hi + crank * kShare * 128;
-                        tma_load_2d_multicast(dst, &tm_whi, kb * kGemmBlockK, wrow + crank * kShare, &full_bar[s], kMask);
-                        if (p.split == 3)
-                            tma_load_2d_multicast(dst + kWBytes, &tm_wlo, kb * kGemmBlockK, wrow + crank * kShare,
-                                                  &full_bar[s], kMask);
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {                                   // ---- MMA issuer ----
-            constexpr uint32_t idesc = umma_idesc_tf32(kGemmBlockM, NT);
-            int g = 0, i = 0;
-            for (int tile = cid; tile < num_tiles; tile += ncl, ++i) {
-                const int b = i & 1;
-                mbar_wait_bounded(&acc_empty[b], ((i >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
-                tc_fence_after();
-                const uint32_t d = tmem_base + b * NT;
-                for (int kb = 0; kb < kKBlocks; ++kb, ++g) {
-                    const int s = g % kGemmStages;
-                    mbar_wait_bounded(&full_bar[s], (g / kGemmStages) & 1);
-                    tc_fence_after();
-                    const uint32_t x_hi = smem_u32(stage_ptr(s));
-                    const uint32_t x_lo = x_hi + kXBytes;
-                    const uint32_t w_hi = x_hi + 2 * kXBytes;
-                    const uint32_t w_lo = w_hi + kWBytes;
-#pragma unroll
-                    for (int k = 0; k < kGemmBlockK / 8; ++k) {
-                        const uint32_t koff = k * 32;
-                        const uint64_t a_hi = umma_desc_k128(x_hi + koff);
-                        const uint64_t b_hi = umma_desc_k128(w_hi + koff);
-                        umma_tf32(d, a_hi, b_hi, idesc, (kb | k) ? 1u : 0u);
-                        if (p.split == 3) {
-                            umma_tf32(d, umma_desc_k128(x_lo + koff), b_hi, idesc, 1u);
-                            umma_tf32(d, a_hi, umma_desc_k128(w_lo + koff), idesc, 1u);
-                        }
-                    }
-                    if (CL == 1) umma_commit(&empty_bar[s]);
-                    else umma_commit_multicast(&empty_bar[s], (1u << CL) - 1);
-                }
-                umma_commit(&acc_full[b]);
-            }
-        }
-    } else if (warp < 2 + PW) {
-        // ---- X producers: global -> registers -> hi/lo -> swizzled shared memory ----
-        constexpr int kRowsPerPass = PW * 4;          // 8 threads per 128-byte row segment
-        constexpr int kPasses = kGemmBlockM / kRowsPerPass;
-        const int t = threadIdx.x - 64;
-        const int c16 = t & 7, rsub = t >> 3;
-        auto load_x = [&](int rt, int kb, float4 (&v)[kPasses]) {
-            const int rbase = rt * kGemmBlockM + rsub;
-            const size_t cbase = static_cast<size_t>(kb) * kGemmBlockK;
-#pragma unroll
-            for (int j = 0; j < kPasses; ++j) {
-                const int gr = rbase + kRowsPerPass * j;
-                v[j] = gr < p.M ? __ldg(reinterpret_cast<const float4 *>(p.x + static_cast<size_t>(gr) * p.K + cbase) + c16)
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        };
-        // kXDepth k-blocks of X are in flight per thread (registers): with one block in flight the kernel is bound by
-        // global-load latency (16 KB per SM outstanding), measured 2x slower on the 1024-wide FFN shapes
-        constexpr int kXDepth = XD;
-        float4 buf[kXDepth][kPasses];
-        TileIter lt = first_tile(), ct = first_tile();   // load iterator (kXDepth - 1 k-blocks ahead), convert iterator
-        int lkb = 0, kb = 0, g = 0;
-        auto advance = [&](TileIter &tl, int &k) {
-            if (++k == kKBlocks) { k = 0; next_tile(tl); }
-        };
-#pragma unroll
-        for (int d = 0; d < kXDepth - 1; ++d) {
-            if (lt.tile < num_tiles) load_x(lt.rt * CL + crank, lkb, buf[d]);
-            advance(lt, lkb);
-        }
-        while (ct.tile < num_tiles) {
-#pragma unroll
-            for (int u = 0; u < kXDepth; ++u) {
-                if (ct.tile >= num_tiles) break;
-                if (lt.tile < num_tiles) load_x(lt.rt * CL + crank, lkb, buf[(u + kXDepth - 1) % kXDepth]);
-                advance(lt, lkb);
-                const int s = g % kGemmStages;
-                mbar_wait_bounded(&empty_bar[s], ((g / kGemmStages) & 1) ^ 1);
-                unsigned char *x_hi = stage_ptr(s);
-                unsigned char *x_lo = x_hi + kXBytes;
-#pragma unroll
-                for (int j = 0; j < kPasses; ++j) {
-                    const int r = rsub + kRowsPerPass * j;
-                    const uint32_t off = r * 128 + ((c16 ^ (r & 7)) << 4);
-                    const float4 v = buf[u][j];
-                    float4 hi, lo;
-                    hi.x = tf32_hi(v.x); lo.x = v.x - hi.x;
-                    hi.y = tf32_hi(v.y); lo.y = v.y - hi.y;
-                    hi.z = tf32_hi(v.z); lo.z = v.z - hi.z;
-                    hi.w = tf32_hi(v.w); lo.w = v.w - hi.w;
-                    *reinterpret_cast<float4 *>(x_hi + off) = hi;
-                    *reinterpret_cast<float4 *>(x_lo + off) = lo;
-                }
-                fence_async_smem();
-                mbar_arrive(&full_bar[s]);
-                advance(ct, kb);
-                ++g;
-            }
-        }
-    } else {
-        // ---- epilogue (last 4 warps; warp % 4 selects the TMEM lane quarter) ----
-        const int q = warp & 3;
-        int i = 0, chunk = 0;
-        for (TileIter ti = first_tile(); ti.tile < num_tiles; next_tile(ti), ++i) {
-            const int b = i & 1;
-            const int rt_own = ti.rt * CL + crank;              // this CTA's row tile of the group
-            mbar_wait_bounded(&acc_full[b], (i >> 1) & 1);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c0 = 0; c0 < N; c0 += 32, ++chunk) {
-                float acc[32];
-                tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * NT + c0, acc);
-                if (c0 + 32 >= N) {                      // last TMEM read of this tile: hand the accumulator back
-                    tc_fence_before();
-                    mbar_arrive(&acc_empty[b]);
-                }
-                // every epilogue warp owns a private pair of 32-row x 128-byte staging tiles and issues its own
-                // TMA store (box 32 x 32): no CTA-level barrier in the epilogue, four independent store pipelines
-                unsigned char *stg = staging + q * (2 * 4096) + (chunk & 1) * 4096;
-                const int grow = rt_own * kGemmBlockM + q * 32 + lane;     // this thread's output row
-                if (chunk >= 2 && p.store_mode == 0) {
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    __syncwarp();
-                }
-#pragma unroll
-                for (int c = 0; c < 32; c += 4) {
-                    float4 o = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
-                    if (p.bias) {
-                        const float4 bb = __ldg(reinterpret_cast<const float4 *>(p.bias + ti.sl * NT + c0 + c));
-                        o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-                    }
-                    if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                    if (p.addend && grow < p.M) {
-                        const float4 ad = *reinterpret_cast<const float4 *>(      // plain load: addend may alias y
-                            p.addend + static_cast<size_t>(grow) * p.N + ti.sl * NT + c0 + c);
-                        o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
-                    }
-                    if (p.out_mask && grow < p.M) {
-                        const float4 mk = __ldg(reinterpret_cast<const float4 *>(
-                            p.out_mask + static_cast<size_t>(grow) * p.N + ti.sl * NT + c0 + c));
-                        o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f;
-                        o.z = mk.z > 0.f ? o.z : 0.f; o.w = mk.w > 0.f ? o.w : 0.f;
-                    }
-                    *reinterpret_cast<float4 *>(stg + lane * 128 + ((((c >> 2) ^ (lane & 7))) << 4)) = o;
-                }
-                if (p.store_mode == 0) {
-                    fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                                         reinterpret_cast<uint64_t>(&tm_y)),
-                                     "r"(smem_u32(stg)), "r"(ti.sl * NT + c0), "r"(rt_own * kGemmBlockM + q * 32)
-                                     : "memory");
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
-                } else {
-                    // transposed read-back: 8 lanes cover one row's 128 bytes, every store instruction writes 4 full lines
-                    __syncwarp();
-                    const int ch = lane & 7;
-                    float *ybase = p.y + static_cast<size_t>(rt_own * kGemmBlockM + q * 32) * p.N + ti.sl * NT + c0 + ch * 4;
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int row = it * 4 + (lane >> 3);
-                        const float4 v = *reinterpret_cast<const float4 *>(stg + row * 128 + ((ch ^ (row & 7)) << 4));
-                        if (rt_own * kGemmBlockM + q * 32 + row < p.M)
-                            *reinterpret_cast<float4 *>(ybase + static_cast<size_t>(row) * p.N) = v;
-                    }
-                    __syncwarp();
-                }
-            }
-        }
-        if (lane == 0 && p.store_mode == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (CL > 1) cluster_sync_all();        // no CTA leaves while a peer may still signal its barriers
-    if (warp == 0) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
-    }
-}
-
 // ------------------------------------------------------------------------------------------------------
 // CTA-pair variant (tcgen05 cta_group::2).  With both operands in shared memory a single-CTA TF32 MMA (M = 128, N = 256,
 // K = 8: 128 cycles) reads A 4 KB + B 8 KB = 96 B/cycle of the SM's 128 B/cycle shared-memory bandwidth; together with the
@@ -702,33 +434,39 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t *bar, uint16_t cta_mas
 
 constexpr int kPairStages = 3;
 
-template <int NT>
-__global__ void __launch_bounds__(kGemmThreadsPersistent, 1)
-linear_tf32x3_pair_kernel(const LinearParams p, const __grid_constant__ CUtensorMap tm_whi,
+// CL = 2: thread-block cluster of two CTAs working on neighbouring row tiles in lockstep.  Each CTA fetches HALF of every
+// weight k-block and TMA-multicasts it to both, so the weight stream out of L2 (the contended resource of this kernel:
+// 512 KB per 128-row tile) is halved; a stage is released to both TMA producers by multicast tcgen05.commit arrivals.
+// PW activation-producer warps keep XD k-blocks of X in flight in registers: (XD - 1) * 16 KB outstanding per SM.
+template <int NT, int CL = 1, int PW = kGemmProducerWarps, int XD = 3, bool PAIR = false>
+__global__ void __launch_bounds__(gemm_threads_persistent(PW), 1)
+linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CUtensorMap tm_whi,
                                 const __grid_constant__ CUtensorMap tm_wlo, const __grid_constant__ CUtensorMap tm_y)
 {
     constexpr int N = NT;
     constexpr int kXBytes = kGemmBlockM * kGemmBlockK * 4;
-    constexpr int kWBytes = (N / 2) * kGemmBlockK * 4;          // this CTA's half of the weight k-block
+    static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
+    constexpr int kStages = PAIR ? kPairStages : kGemmStages;
+    constexpr int kWBytes = (PAIR ? N / 2 : N) * kGemmBlockK * 4;   // PAIR: this CTA's half of the weight k-block
     constexpr int kStageBytes = 2 * kXBytes + 2 * kWBytes;
     constexpr uint32_t kTmemCols = (2 * N <= 64) ? 64 : (2 * N <= 128) ? 128 : (2 * N <= 256) ? 256 : 512;
     static_assert(NT % 16 == 0 && NT <= 256, "UMMA N for M = 128, two accumulators in 512 TMEM columns");
 
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    unsigned char *staging = smem + kPairStages * kStageBytes;            // 2 x 16 KB epilogue tiles
-    __shared__ uint64_t full_bar[kPairStages], empty_bar[kPairStages], acc_full[2], acc_empty[2];
-    __shared__ uint64_t peer_full[kPairStages], peer_acc_empty[2];      // leader only: arrivals from the peer CTA
+    unsigned char *staging = smem + kStages * kStageBytes;            // 2 x 16 KB epilogue tiles
+    __shared__ uint64_t full_bar[kStages], empty_bar[kStages], acc_full[2], acc_empty[2];
+    __shared__ uint64_t peer_full[kStages], peer_acc_empty[2];      // PAIR, leader only: arrivals from the peer CTA
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kKBlocks = p.K / kGemmBlockK;
     const int slices = p.slices;
-    // the cluster (2 CTAs) walks virtual tiles = (group of 2 row tiles, slice); CTA `crank` owns row tile group * 2 + crank
-    const int crank = static_cast<int>(blockIdx.x) % 2;         // rank in the (2, 1, 1) cluster
-    const int cid = static_cast<int>(blockIdx.x) / 2, ncl = static_cast<int>(gridDim.x) / 2;
+    // the cluster (CL CTAs) walks virtual tiles = (group of CL row tiles, slice); CTA `crank` owns row tile group * CL + crank
+    const int crank = CL > 1 ? static_cast<int>(blockIdx.x) % CL : 0;
+    const int cid = static_cast<int>(blockIdx.x) / CL, ncl = static_cast<int>(gridDim.x) / CL;
     const int row_tiles = (p.M + kGemmBlockM - 1) / kGemmBlockM;
-    const int num_tiles = ((row_tiles + 2 - 1) / 2) * slices;   // tile = row_tile_group * slices + slice
+    const int num_tiles = ((row_tiles + CL - 1) / CL) * slices;   // tile = row_tile_group * slices + slice
     // (row tile, slice) of a tile index advance incrementally: an integer division per tile / k-block in the
     // single-threaded TMA and MMA roles costs ~200 cycles of latency each and made this kernel 1.7x slower (measured)
     const int step_rt = ncl / slices, step_sl = ncl % slices;
@@ -744,25 +482,28 @@ linear_tf32x3_pair_kernel(const LinearParams p, const __grid_constant__ CUtensor
     };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kPairStages; ++s) {
-            mbar_init(&full_bar[s], kGemmProducerWarps * 32 + 1);
-            mbar_init(&empty_bar[s], 1);      // the leader's multicast tcgen05.commit
-            mbar_init(&peer_full[s], 1);      // relay thread of the peer CTA
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], PW * 32 + 1);
+            mbar_init(&empty_bar[s], PAIR ? 1 : CL);   // a commit from every CTA of the cluster / the leader's multicast commit
+            if (PAIR) mbar_init(&peer_full[s], 1);     // relay thread of the peer CTA
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);        // tcgen05.commit after the last k-block of a tile
             mbar_init(&acc_empty[b], 128);     // every epilogue thread, after its last TMEM read of the tile
-            mbar_init(&peer_acc_empty[b], 128);   // the peer's epilogue threads (remote arrives)
+            if (PAIR) mbar_init(&peer_acc_empty[b], 128);   // the peer's epilogue threads (remote arrives)
         }
         fence_mbar_init();
         tma_prefetch_desc(&tm_whi);
         tma_prefetch_desc(&tm_wlo);
         tma_prefetch_desc(&tm_y);
     }
-    if (warp == 0) tmem_alloc_pair(&tmem_base_slot, kTmemCols);
+    if (warp == 0) {
+        if (PAIR) tmem_alloc_pair(&tmem_base_slot, kTmemCols);
+        else tmem_alloc(&tmem_base_slot, kTmemCols);
+    }
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();                  // the peer's barriers and TMEM are set up before anything is signalled to it
+    if (CL > 1) cluster_sync_all();        // peers' barriers are initialised before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
     auto stage_ptr = [&](int s) { return smem + s * kStageBytes; };
@@ -773,31 +514,89 @@ linear_tf32x3_pair_kernel(const LinearParams p, const __grid_constant__ CUtensor
             for (TileIter ti = first_tile(); ti.tile < num_tiles; next_tile(ti)) {
                 const int wrow = ti.sl * NT;
                 for (int kb = 0; kb < kKBlocks; ++kb, ++g) {
-                    const int s = g % kPairStages;
-                    mbar_wait_bounded(&empty_bar[s], ((g / kPairStages) & 1) ^ 1);
+                    const int s = g % kStages;
+                    mbar_wait_bounded(&empty_bar[s], ((g / kStages) & 1) ^ 1);
                     mbar_arrive_expect_tx(&full_bar[s], p.split == 3 ? 2 * kWBytes : kWBytes);
                     unsigned char *w_hi = stage_ptr(s) + 2 * kXBytes;
-                    // this CTA's half of the weight rows, into its own shared memory only
-                    constexpr int kShare = NT / 2;
-                    tma_load_2d(w_hi, &tm_whi, kb * kGemmBlockK, wrow + crank * kShare, &full_bar[s]);
-                    if (p.split == 3) tma_load_2d(w_hi + kWBytes, &tm_wlo, kb * kGemmBlockK, wrow + crank * kShare, &full_bar[s]);
+                    if (CL == 1) {
+                        tma_load_2d(w_hi, &tm_whi, kb * kGemmBlockK, wrow, &full_bar[s]);
+                        if (p.split == 3) tma_load_2d(w_hi + kWBytes, &tm_wlo, kb * kGemmBlockK, wrow, &full_bar[s]);
+                    } else if (PAIR) {
+                        // this CTA's half of the weight rows, into its own shared memory only
+                        constexpr int kShare = NT / 2;
+                        tma_load_2d(w_hi, &tm_whi, kb * kGemmBlockK, wrow + crank * kShare, &full_bar[s]);
+                        if (p.split == 3)
+                            tma_load_2d(w_hi + kWBytes, &tm_wlo, kb * kGemmBlockK, wrow + crank * kShare, &full_bar[s]);
+                    } else {
+                        // this CTA's share of the weight rows, delivered to every CTA of the cluster
+                        constexpr int kShare = NT / CL;
+                        constexpr uint16_t kMask = (1u << CL) - 1;
+                        unsigned char *dst = w_hi + crank * kShare * 128;
+                        tma_load_2d_multicast(dst, &tm_whi, kb * kGemmBlockK, wrow + crank * kShare, &full_bar[s], kMask);
+                        if (p.split == 3)
+                            tma_load_2d_multicast(dst + kWBytes, &tm_wlo, kb * kGemmBlockK, wrow + crank * kShare,
+                                                  &full_bar[s], kMask);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && crank == 0) {                     // ---- MMA issuer (leader CTA, for the pair) ----
-            constexpr uint32_t idesc = umma_idesc_tf32(2 * kGemmBlockM, NT);
+        if constexpr (PAIR) {
+            if (lane == 0 && crank == 0) {                     // ---- MMA issuer (leader CTA, for the pair) ----
+                constexpr uint32_t idesc = umma_idesc_tf32(2 * kGemmBlockM, NT);
+                int g = 0, i = 0;
+                for (int tile = cid; tile < num_tiles; tile += ncl, ++i) {
+                    const int b = i & 1;
+                    mbar_wait_bounded(&acc_empty[b], ((i >> 1) & 1) ^ 1);               // own epilogue has drained it
+                    mbar_wait_cluster_bounded(&peer_acc_empty[b], ((i >> 1) & 1) ^ 1);  // and the peer's
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + b * NT;
+                    for (int kb = 0; kb < kKBlocks; ++kb, ++g) {
+                        const int s = g % kStages;
+                        mbar_wait_bounded(&full_bar[s], (g / kStages) & 1);
+                        mbar_wait_cluster_bounded(&peer_full[s], (g / kStages) & 1);
+                        tc_fence_after();
+                        const uint32_t x_hi = smem_u32(stage_ptr(s));
+                        const uint32_t x_lo = x_hi + kXBytes;
+                        const uint32_t w_hi = x_hi + 2 * kXBytes;
+                        const uint32_t w_lo = w_hi + kWBytes;
+    #pragma unroll
+                        for (int k = 0; k < kGemmBlockK / 8; ++k) {
+                            const uint32_t koff = k * 32;
+                            const uint64_t a_hi = umma_desc_k128(x_hi + koff);
+                            const uint64_t b_hi = umma_desc_k128(w_hi + koff);
+                            umma_tf32_pair(d, a_hi, b_hi, idesc, (kb | k) ? 1u : 0u);
+                            if (p.split == 3) {
+                                umma_tf32_pair(d, umma_desc_k128(x_lo + koff), b_hi, idesc, 1u);
+                                umma_tf32_pair(d, a_hi, umma_desc_k128(w_lo + koff), idesc, 1u);
+                            }
+                        }
+                        umma_commit_pair(&empty_bar[s], 3);     // stage s is free again in both CTAs
+                    }
+                    umma_commit_pair(&acc_full[b], 3);           // both halves of the accumulator are complete
+                }
+            } else if (lane == 0) {                              // ---- peer CTA: relay "my stage is full" to the leader ----
+                int g = 0;
+                for (int tile = cid; tile < num_tiles; tile += ncl) {
+                    for (int kb = 0; kb < kKBlocks; ++kb, ++g) {
+                        const int s = g % kStages;
+                        mbar_wait_bounded(&full_bar[s], (g / kStages) & 1);
+                        mbar_arrive_remote(cluster_map_shared(smem_u32(&peer_full[s]), 0));
+                    }
+                }
+            }
+        } else
+        if (lane == 0) {                                   // ---- MMA issuer ----
+            constexpr uint32_t idesc = umma_idesc_tf32(kGemmBlockM, NT);
             int g = 0, i = 0;
             for (int tile = cid; tile < num_tiles; tile += ncl, ++i) {
                 const int b = i & 1;
-                mbar_wait_bounded(&acc_empty[b], ((i >> 1) & 1) ^ 1);               // own epilogue has drained it
-                mbar_wait_cluster_bounded(&peer_acc_empty[b], ((i >> 1) & 1) ^ 1);  // and the peer's
+                mbar_wait_bounded(&acc_empty[b], ((i >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d = tmem_base + b * NT;
                 for (int kb = 0; kb < kKBlocks; ++kb, ++g) {
-                    const int s = g % kPairStages;
-                    mbar_wait_bounded(&full_bar[s], (g / kPairStages) & 1);
-                    mbar_wait_cluster_bounded(&peer_full[s], (g / kPairStages) & 1);
+                    const int s = g % kStages;
+                    mbar_wait_bounded(&full_bar[s], (g / kStages) & 1);
                     tc_fence_after();
                     const uint32_t x_hi = smem_u32(stage_ptr(s));
                     const uint32_t x_lo = x_hi + kXBytes;
@@ -808,29 +607,21 @@ linear_tf32x3_pair_kernel(const LinearParams p, const __grid_constant__ CUtensor
                         const uint32_t koff = k * 32;
                         const uint64_t a_hi = umma_desc_k128(x_hi + koff);
                         const uint64_t b_hi = umma_desc_k128(w_hi + koff);
-                        umma_tf32_pair(d, a_hi, b_hi, idesc, (kb | k) ? 1u : 0u);
+                        umma_tf32(d, a_hi, b_hi, idesc, (kb | k) ? 1u : 0u);
                         if (p.split == 3) {
-                            umma_tf32_pair(d, umma_desc_k128(x_lo + koff), b_hi, idesc, 1u);
-                            umma_tf32_pair(d, a_hi, umma_desc_k128(w_lo + koff), idesc, 1u);
+                            umma_tf32(d, umma_desc_k128(x_lo + koff), b_hi, idesc, 1u);
+                            umma_tf32(d, a_hi, umma_desc_k128(w_lo + koff), idesc, 1u);
                         }
                     }
-                    umma_commit_pair(&empty_bar[s], 3);     // stage s is free again in both CTAs
+                    if (CL == 1) umma_commit(&empty_bar[s]);
+                    else umma_commit_multicast(&empty_bar[s], (1u << CL) - 1);
                 }
-                umma_commit_pair(&acc_full[b], 3);           // both halves of the accumulator are complete
-            }
-        } else if (lane == 0) {                              // ---- peer CTA: relay "my stage is full" to the leader ----
-            int g = 0;
-            for (int tile = cid; tile < num_tiles; tile += ncl) {
-                for (int kb = 0; kb < kKBlocks; ++kb, ++g) {
-                    const int s = g % kPairStages;
-                    mbar_wait_bounded(&full_bar[s], (g / kPairStages) & 1);
-                    mbar_arrive_remote(cluster_map_shared(smem_u32(&peer_full[s]), 0));
-                }
+                umma_commit(&acc_full[b]);
             }
         }
-    } else if (warp < 2 + kGemmProducerWarps) {
+    } else if (warp < 2 + PW) {
         // ---- X producers: global -> registers -> hi/lo -> swizzled shared memory ----
-        constexpr int kRowsPerPass = kGemmProducerWarps * 4;          // 8 threads per 128-byte row segment
+        constexpr int kRowsPerPass = PW * 4;          // 8 threads per 128-byte row segment
         constexpr int kPasses = kGemmBlockM / kRowsPerPass;
         const int t = threadIdx.x - 64;
         const int c16 = t & 7, rsub = t >> 3;
@@ -846,7 +637,7 @@ linear_tf32x3_pair_kernel(const LinearParams p, const __grid_constant__ CUtensor
         };
         // kXDepth k-blocks of X are in flight per thread (registers): with one block in flight the kernel is bound by
         // global-load latency (16 KB per SM outstanding), measured 2x slower on the 1024-wide FFN shapes
-        constexpr int kXDepth = 3;
+        constexpr int kXDepth = XD;
         float4 buf[kXDepth][kPasses];
         TileIter lt = first_tile(), ct = first_tile();   // load iterator (kXDepth - 1 k-blocks ahead), convert iterator
         int lkb = 0, kb = 0, g = 0;
@@ -855,17 +646,17 @@ linear_tf32x3_pair_kernel(const LinearParams p, const __grid_constant__ CUtensor
         };
 #pragma unroll
         for (int d = 0; d < kXDepth - 1; ++d) {
-            if (lt.tile < num_tiles) load_x(lt.rt * 2 + crank, lkb, buf[d]);
+            if (lt.tile < num_tiles) load_x(lt.rt * CL + crank, lkb, buf[d]);
             advance(lt, lkb);
         }
         while (ct.tile < num_tiles) {
 #pragma unroll
             for (int u = 0; u < kXDepth; ++u) {
                 if (ct.tile >= num_tiles) break;
-                if (lt.tile < num_tiles) load_x(lt.rt * 2 + crank, lkb, buf[(u + kXDepth - 1) % kXDepth]);
+                if (lt.tile < num_tiles) load_x(lt.rt * CL + crank, lkb, buf[(u + kXDepth - 1) % kXDepth]);
                 advance(lt, lkb);
-                const int s = g % kPairStages;
-                mbar_wait_bounded(&empty_bar[s], ((g / kPairStages) & 1) ^ 1);
+                const int s = g % kStages;
+                mbar_wait_bounded(&empty_bar[s], ((g / kStages) & 1) ^ 1);
                 unsigned char *x_hi = stage_ptr(s);
                 unsigned char *x_lo = x_hi + kXBytes;
 #pragma unroll
@@ -893,7 +684,7 @@ linear_tf32x3_pair_kernel(const LinearParams p, const __grid_constant__ CUtensor
         int i = 0, chunk = 0;
         for (TileIter ti = first_tile(); ti.tile < num_tiles; next_tile(ti), ++i) {
             const int b = i & 1;
-            const int rt_own = ti.rt * 2 + crank;              // this CTA's row tile of the group
+            const int rt_own = ti.rt * CL + crank;              // this CTA's row tile of the group
             mbar_wait_bounded(&acc_full[b], (i >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
@@ -902,7 +693,7 @@ linear_tf32x3_pair_kernel(const LinearParams p, const __grid_constant__ CUtensor
                 tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * NT + c0, acc);
                 if (c0 + 32 >= N) {                      // last TMEM read of this tile: hand the accumulator back
                     tc_fence_before();
-                    if (crank == 0) mbar_arrive(&acc_empty[b]);
+                    if (!PAIR || crank == 0) mbar_arrive(&acc_empty[b]);
                     else mbar_arrive_remote(cluster_map_shared(smem_u32(&peer_acc_empty[b]), 0));
                 }
                 // every epilogue warp owns a private pair of 32-row x 128-byte staging tiles and issues its own
@@ -964,13 +755,13 @@ linear_tf32x3_pair_kernel(const LinearParams p, const __grid_constant__ CUtensor
     }
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();                  // no CTA leaves while the peer may still signal its barriers / use its TMEM
+    if (CL > 1) cluster_sync_all();        // no CTA leaves while a peer may still signal its barriers
     if (warp == 0) {
         tc_fence_after();
-        tmem_dealloc_pair(tmem_base, kTmemCols);
+        if (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
-
 
 template <int NT>
 constexpr int linear_pair_smem_bytes()

@@ -631,7 +631,7 @@ int launch_linear_pair(const LinearParams &p, const float *w_hi, const float *w_
     if ((rc = make_map(&ml, w_lo, p.N, p.K, NT / 2, kGemmBlockK, true))) return rc;
     if ((rc = make_map(&my, p.y, p.M, p.N, 32, 32, true))) return rc;
     constexpr int smem = linear_pair_smem_bytes<NT>();
-    if ((rc = ensure_dynamic_smem<&linear_tf32x3_pair_kernel<NT>>(smem, "cudaFuncSetAttribute(pair linear smem)"))) return rc;
+    if ((rc = ensure_dynamic_smem<&linear_tf32x3_persistent_kernel<NT, 2, kGemmProducerWarps, 3, true>>(smem, "cudaFuncSetAttribute(pair linear smem)"))) return rc;
     const int row_tiles = (p.M + kGemmBlockM - 1) / kGemmBlockM;
     const int tiles = ((row_tiles + 1) / 2) * p.slices * 2;
     int grid = tiles < sms ? tiles : sms;
@@ -648,8 +648,8 @@ int launch_linear_pair(const LinearParams &p, const float *w_hi, const float *w_
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    const cudaError_t le = cudaLaunchKernelEx(&cfg, linear_tf32x3_pair_kernel<NT>, p, mh, ml, my);
-    if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(linear_tf32x3_pair_kernel)");
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, linear_tf32x3_persistent_kernel<NT, 2, kGemmProducerWarps, 3, true>, p, mh, ml, my);
+    if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(linear_tf32x3_persistent_kernel, CTA pair)");
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return BM2F_OK;
 }
