@@ -7,8 +7,9 @@ checkpoints load.  Detectron2 is not needed for this part; the decoder around it
 embedding, FPN tail) is mirrored in `bm2f_b200.pixel_decoder`, which enters through `forward_tokens`.
 
 On CUDA float32 with dropout 0 (every config that selects this decoder sets DROPOUT 0.0) the layer runs:
-    src2 = MSDeformAttn(src + pos, ref, src)   value / offset / logit projections as ONE autograd node (tcgen05 GEMMs,
-                                          gradient branches summed in GEMM epilogues), fused-prologue sampling kernels
+    q = src + pos                         torch add
+    src2 = MSDeformAttn(q, ref, src)      fused-prologue sampling kernels + tcgen05 projections (`fuse_projections`:
+                                          the three input projections as one autograd node, off by default)
     src = LayerNorm(src + src2)           one fused kernel (csrc/ln_kernels.cuh)
     src2 = linear2(relu(linear1(src)))    two tcgen05 GEMMs (ReLU in the epilogue); backward = five tcgen05 GEMMs,
                                           the ReLU mask applied in the epilogue of the grad_h GEMM
@@ -57,7 +58,11 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
         self.dropout3 = nn.Dropout(dropout)
         self.norm2 = nn.LayerNorm(d_model)
         self.fused = True          # False: always the reference op sequence in torch
-        self.fuse_projections = True   # value / offset / logit projections of self-attention as one autograd node
+        # value / offset / logit projections of self-attention as ONE autograd node with the gradient sums in GEMM
+        # epilogues (MSDeformAttn.forward_self_attention).  Measured neutral (92.5 vs 92.7 ms per encoder pass) to
+        # slightly slower with TF32 allowed (85.4 vs 84.1 ms): the epilogue's per-row addend loads are no better than the
+        # autograd engine's coalesced adds.  Off by default; kept selectable and tested.
+        self.fuse_projections = False
 
     @staticmethod
     def with_pos_embed(tensor, pos):

@@ -8,7 +8,10 @@ from bm2f_b200 import workloads as W
 from bm2f_b200.encoder import MSDeformAttnTransformerEncoderOnly
 
 ap = argparse.ArgumentParser(); ap.add_argument("--cfg", type=int, default=2); ap.add_argument("--batch", type=int, default=16)
-ap.add_argument("--reps", type=int, default=3); args = ap.parse_args()
+ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--tf32", action="store_true", help="torch.backends.cuda.matmul.allow_tf32 = True for both arms")
+args = ap.parse_args()
+torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
 wl = W.WORKLOADS[args.cfg]; dev = torch.device("cuda:0"); torch.manual_seed(0)
 enc = MSDeformAttnTransformerEncoderOnly(256, 8, 6, 1024, 0.0, "relu", wl.L, 4).to(dev)
 srcs = [torch.randn(args.batch, 256, h, w, device=dev, requires_grad=True) for h, w in wl.levels]
