@@ -69,6 +69,12 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// 128-bit store to a shared-memory address (state space known: STS.128 instead of a generic ST.E.128)
+__device__ __forceinline__ void sts128(uint32_t smem_addr, const float4 &v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(smem_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // D[tmem] (+)= A[smem desc] * B[smem desc], TF32 inputs, fp32 accumulate
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate)
@@ -657,8 +663,8 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
                 advance(lt, lkb);
                 const int s = g % kStages;
                 mbar_wait_bounded(&empty_bar[s], ((g / kStages) & 1) ^ 1);
-                unsigned char *x_hi = stage_ptr(s);
-                unsigned char *x_lo = x_hi + kXBytes;
+                const uint32_t x_hi_s = smem_u32(stage_ptr(s));
+                const uint32_t x_lo_s = x_hi_s + kXBytes;
 #pragma unroll
                 for (int j = 0; j < kPasses; ++j) {
                     const int r = rsub + kRowsPerPass * j;
@@ -669,8 +675,8 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
                     hi.y = tf32_hi(v.y); lo.y = v.y - hi.y;
                     hi.z = tf32_hi(v.z); lo.z = v.z - hi.z;
                     hi.w = tf32_hi(v.w); lo.w = v.w - hi.w;
-                    *reinterpret_cast<float4 *>(x_hi + off) = hi;
-                    *reinterpret_cast<float4 *>(x_lo + off) = lo;
+                    sts128(x_hi_s + off, hi);
+                    sts128(x_lo_s + off, lo);
                 }
                 fence_async_smem();
                 mbar_arrive(&full_bar[s]);
@@ -699,6 +705,7 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
                 // every epilogue warp owns a private pair of 32-row x 128-byte staging tiles and issues its own
                 // TMA store (box 32 x 32): no CTA-level barrier in the epilogue, four independent store pipelines
                 unsigned char *stg = staging + q * (2 * 4096) + (chunk & 1) * 4096;
+                const uint32_t stg_s = smem_u32(stg);
                 const int grow = rt_own * kGemmBlockM + q * 32 + lane;     // this thread's output row
                 if (chunk >= 2 && p.store_mode == 0) {
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -723,7 +730,7 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
                         o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f;
                         o.z = mk.z > 0.f ? o.z : 0.f; o.w = mk.w > 0.f ? o.w : 0.f;
                     }
-                    *reinterpret_cast<float4 *>(stg + lane * 128 + ((((c >> 2) ^ (lane & 7))) << 4)) = o;
+                    sts128(stg_s + lane * 128 + ((((c >> 2) ^ (lane & 7))) << 4), o);
                 }
                 if (p.store_mode == 0) {
                     fence_async_smem();
