@@ -75,6 +75,13 @@ __device__ __forceinline__ void sts128(uint32_t smem_addr, const float4 &v)
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(smem_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+__device__ __forceinline__ float4 lds128(uint32_t smem_addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_addr) : "memory");
+    return v;
+}
+
 // D[tmem] (+)= A[smem desc] * B[smem desc], TF32 inputs, fp32 accumulate
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate)
@@ -439,22 +446,29 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t *bar, uint16_t cta_mas
 }
 
 constexpr int kPairStages = 3;
+constexpr int kXtmaStages = 4;
 
 // CL = 2: thread-block cluster of two CTAs working on neighbouring row tiles in lockstep.  Each CTA fetches HALF of every
 // weight k-block and TMA-multicasts it to both, so the weight stream out of L2 (the contended resource of this kernel:
 // 512 KB per 128-row tile) is halved; a stage is released to both TMA producers by multicast tcgen05.commit arrivals.
 // PW activation-producer warps keep XD k-blocks of X in flight in registers: (XD - 1) * 16 KB outstanding per SM.
-template <int NT, int CL = 1, int PW = kGemmProducerWarps, int XD = 3, bool PAIR = false>
+// XTMA (single TF32 pass only): the activation tile needs no hi/lo split, so it is TMA-loaded straight into the MMA
+// stage like the weights (the tensor core ignores the low 13 mantissa bits); the producer warps idle and the freed
+// shared memory holds four stages.
+template <int NT, int CL = 1, int PW = kGemmProducerWarps, int XD = 3, bool PAIR = false, bool XTMA = false>
 __global__ void __launch_bounds__(gemm_threads_persistent(PW), 1)
 linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CUtensorMap tm_whi,
-                                const __grid_constant__ CUtensorMap tm_wlo, const __grid_constant__ CUtensorMap tm_y)
+                                const __grid_constant__ CUtensorMap tm_wlo, const __grid_constant__ CUtensorMap tm_y,
+                                const __grid_constant__ CUtensorMap tm_x)
 {
     constexpr int N = NT;
     constexpr int kXBytes = kGemmBlockM * kGemmBlockK * 4;
     static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
-    constexpr int kStages = PAIR ? kPairStages : kGemmStages;
+    static_assert(!XTMA || (CL == 1 && !PAIR), "XTMA: single CTAs");
+    constexpr int kStages = XTMA ? kXtmaStages : PAIR ? kPairStages : kGemmStages;
     constexpr int kWBytes = (PAIR ? N / 2 : N) * kGemmBlockK * 4;   // PAIR: this CTA's half of the weight k-block
-    constexpr int kStageBytes = 2 * kXBytes + 2 * kWBytes;
+    constexpr int kSlots = XTMA ? 1 : 2;                            // hi (+ lo) tiles per operand and stage
+    constexpr int kStageBytes = kSlots * kXBytes + kSlots * kWBytes;
     constexpr uint32_t kTmemCols = (2 * N <= 64) ? 64 : (2 * N <= 128) ? 128 : (2 * N <= 256) ? 256 : 512;
     static_assert(NT % 16 == 0 && NT <= 256, "UMMA N for M = 128, two accumulators in 512 TMEM columns");
 
@@ -489,7 +503,7 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(&full_bar[s], PW * 32 + 1);
+            mbar_init(&full_bar[s], XTMA ? 1 : PW * 32 + 1);
             mbar_init(&empty_bar[s], PAIR ? 1 : CL);   // a commit from every CTA of the cluster / the leader's multicast commit
             if (PAIR) mbar_init(&peer_full[s], 1);     // relay thread of the peer CTA
         }
@@ -502,6 +516,7 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
         tma_prefetch_desc(&tm_whi);
         tma_prefetch_desc(&tm_wlo);
         tma_prefetch_desc(&tm_y);
+        if (XTMA) tma_prefetch_desc(&tm_x);
     }
     if (warp == 0) {
         if (PAIR) tmem_alloc_pair(&tmem_base_slot, kTmemCols);
@@ -522,26 +537,29 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
                 for (int kb = 0; kb < kKBlocks; ++kb, ++g) {
                     const int s = g % kStages;
                     mbar_wait_bounded(&empty_bar[s], ((g / kStages) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[s], p.split == 3 ? 2 * kWBytes : kWBytes);
-                    unsigned char *w_hi = stage_ptr(s) + 2 * kXBytes;
+                    uint64_t *tbar = &full_bar[s];
+                    mbar_arrive_expect_tx(tbar, XTMA ? kWBytes + kXBytes : p.split == 3 ? 2 * kWBytes : kWBytes);
+                    if (XTMA)      // rows past M are zero-filled by the TMA unit
+                        tma_load_2d(stage_ptr(s), &tm_x, kb * kGemmBlockK, (ti.rt * CL + crank) * kGemmBlockM, tbar);
+                    unsigned char *w_hi = stage_ptr(s) + kSlots * kXBytes;
                     if (CL == 1) {
-                        tma_load_2d(w_hi, &tm_whi, kb * kGemmBlockK, wrow, &full_bar[s]);
-                        if (p.split == 3) tma_load_2d(w_hi + kWBytes, &tm_wlo, kb * kGemmBlockK, wrow, &full_bar[s]);
+                        tma_load_2d(w_hi, &tm_whi, kb * kGemmBlockK, wrow, tbar);
+                        if (p.split == 3) tma_load_2d(w_hi + kWBytes, &tm_wlo, kb * kGemmBlockK, wrow, tbar);
                     } else if (PAIR) {
                         // this CTA's half of the weight rows, into its own shared memory only
                         constexpr int kShare = NT / 2;
-                        tma_load_2d(w_hi, &tm_whi, kb * kGemmBlockK, wrow + crank * kShare, &full_bar[s]);
+                        tma_load_2d(w_hi, &tm_whi, kb * kGemmBlockK, wrow + crank * kShare, tbar);
                         if (p.split == 3)
-                            tma_load_2d(w_hi + kWBytes, &tm_wlo, kb * kGemmBlockK, wrow + crank * kShare, &full_bar[s]);
+                            tma_load_2d(w_hi + kWBytes, &tm_wlo, kb * kGemmBlockK, wrow + crank * kShare, tbar);
                     } else {
                         // this CTA's share of the weight rows, delivered to every CTA of the cluster
                         constexpr int kShare = NT / CL;
                         constexpr uint16_t kMask = (1u << CL) - 1;
                         unsigned char *dst = w_hi + crank * kShare * 128;
-                        tma_load_2d_multicast(dst, &tm_whi, kb * kGemmBlockK, wrow + crank * kShare, &full_bar[s], kMask);
+                        tma_load_2d_multicast(dst, &tm_whi, kb * kGemmBlockK, wrow + crank * kShare, tbar, kMask);
                         if (p.split == 3)
                             tma_load_2d_multicast(dst + kWBytes, &tm_wlo, kb * kGemmBlockK, wrow + crank * kShare,
-                                                  &full_bar[s], kMask);
+                                                  tbar, kMask);
                     }
                 }
             }
@@ -564,7 +582,7 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
                         tc_fence_after();
                         const uint32_t x_hi = smem_u32(stage_ptr(s));
                         const uint32_t x_lo = x_hi + kXBytes;
-                        const uint32_t w_hi = x_hi + 2 * kXBytes;
+                        const uint32_t w_hi = x_hi + kSlots * kXBytes;
                         const uint32_t w_lo = w_hi + kWBytes;
     #pragma unroll
                         for (int k = 0; k < kGemmBlockK / 8; ++k) {
@@ -606,7 +624,7 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
                     tc_fence_after();
                     const uint32_t x_hi = smem_u32(stage_ptr(s));
                     const uint32_t x_lo = x_hi + kXBytes;
-                    const uint32_t w_hi = x_hi + 2 * kXBytes;
+                    const uint32_t w_hi = x_hi + kSlots * kXBytes;
                     const uint32_t w_lo = w_hi + kWBytes;
 #pragma unroll
                     for (int k = 0; k < kGemmBlockK / 8; ++k) {
@@ -626,6 +644,7 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
             }
         }
     } else if (warp < 2 + PW) {
+        if constexpr (!XTMA) {
         // ---- X producers: global -> registers -> hi/lo -> swizzled shared memory ----
         constexpr int kRowsPerPass = PW * 4;          // 8 threads per 128-byte row segment
         constexpr int kPasses = kGemmBlockM / kRowsPerPass;
@@ -683,6 +702,7 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
                 advance(ct, kb);
                 ++g;
             }
+        }
         }
     } else {
         // ---- epilogue (last 4 warps; warp % 4 selects the TMEM lane quarter) ----
@@ -774,6 +794,12 @@ template <int NT>
 constexpr int linear_pair_smem_bytes()
 {
     return kPairStages * (2 * kGemmBlockM * kGemmBlockK * 4 + 2 * (NT / 2) * kGemmBlockK * 4) + 2 * kGemmBlockM * kGemmBlockK * 4 + 1024;
+}
+
+template <int NT>
+constexpr int linear_xtma_smem_bytes()
+{
+    return kXtmaStages * (kGemmBlockM * kGemmBlockK * 4 + NT * kGemmBlockK * 4) + 2 * kGemmBlockM * kGemmBlockK * 4 + 1024;
 }
 
 template <int NT>

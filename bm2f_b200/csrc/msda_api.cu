@@ -600,7 +600,7 @@ int launch_linear_persistent(const LinearParams &p, const float *w_hi, const flo
     int grid = tiles < sms ? tiles : sms;
     grid -= grid % CL;
     if (CL == 1) {
-        linear_tf32x3_persistent_kernel<NT, 1, PW, XD><<<grid, gemm_threads_persistent(PW), smem, st>>>(p, mh, ml, my);
+        linear_tf32x3_persistent_kernel<NT, 1, PW, XD><<<grid, gemm_threads_persistent(PW), smem, st>>>(p, mh, ml, my, my);
     } else {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(grid);
@@ -614,7 +614,7 @@ int launch_linear_persistent(const LinearParams &p, const float *w_hi, const flo
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        const cudaError_t le = cudaLaunchKernelEx(&cfg, linear_tf32x3_persistent_kernel<NT, CL, PW, XD>, p, mh, ml, my);
+        const cudaError_t le = cudaLaunchKernelEx(&cfg, linear_tf32x3_persistent_kernel<NT, CL, PW, XD>, p, mh, ml, my, my);
         if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(linear_tf32x3_persistent_kernel, cluster)");
     }
     const cudaError_t e = cudaGetLastError();
@@ -622,6 +622,29 @@ int launch_linear_persistent(const LinearParams &p, const float *w_hi, const flo
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return BM2F_OK;
 }
+// single TF32 pass with the activation tile TMA-loaded into the MMA stage (no producer warps, four stages)
+template <int NT>
+int launch_linear_xtma(const LinearParams &p, const float *w_hi, int sms, cudaStream_t st)
+{
+    CUtensorMap mh, my, mx;
+    int rc;
+    if ((rc = make_map(&mh, w_hi, p.N, p.K, NT, kGemmBlockK, true))) return rc;
+    if ((rc = make_map(&my, p.y, p.M, p.N, 32, 32, true))) return rc;
+    if ((rc = make_map(&mx, p.x, p.M, p.K, kGemmBlockM, kGemmBlockK, true))) return rc;
+    constexpr int smem = linear_xtma_smem_bytes<NT>();
+    if ((rc = ensure_dynamic_smem<&linear_tf32x3_persistent_kernel<NT, 1, kGemmProducerWarps, 3, false, true>>(
+             smem, "cudaFuncSetAttribute(xtma linear smem)")))
+        return rc;
+    const int tiles = ((p.M + kGemmBlockM - 1) / kGemmBlockM) * p.slices;
+    const int grid = tiles < sms ? tiles : sms;
+    linear_tf32x3_persistent_kernel<NT, 1, kGemmProducerWarps, 3, false, true>
+        <<<grid, kGemmThreadsPersistent, smem, st>>>(p, mh, mh, my, mx);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "launch linear_tf32x3_persistent_kernel (TMA activations)");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return BM2F_OK;
+}
+
 template <int NT>
 int launch_linear_pair(const LinearParams &p, const float *w_hi, const float *w_lo, int sms, cudaStream_t st)
 {
@@ -648,7 +671,7 @@ int launch_linear_pair(const LinearParams &p, const float *w_hi, const float *w_
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    const cudaError_t le = cudaLaunchKernelEx(&cfg, linear_tf32x3_persistent_kernel<NT, 2, kGemmProducerWarps, 3, true>, p, mh, ml, my);
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, linear_tf32x3_persistent_kernel<NT, 2, kGemmProducerWarps, 3, true>, p, mh, ml, my, my);
     if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(linear_tf32x3_persistent_kernel, CTA pair)");
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return BM2F_OK;
@@ -677,6 +700,8 @@ int linear_common(const void *x, const void *weight, const void *bias, void *y, 
     // +30: persistent kernel in clusters of two CTAs with TMA-multicast weights (A/B)
     // +40 / +50 / +60: more activation bytes in flight (8 producer warps x 5 k-blocks / 4 x 4 / 8 x 4) (A/B)
     // +70: CTA pairs issuing tcgen05.mma.cta_group::2 (M = 256 per pair)
+    // split 1 (single TF32 pass) loads the activation tile by TMA straight into the MMA stage by default (= 1 + 80);
+    // 1 + 50 selects the register-staged activation path of the three-term kernel for comparison
     int xvar = 0;
     if (split >= 40) { xvar = split / 10 - 3; split -= (xvar + 3) * 10; }
     const bool cluster2 = split >= 30;
@@ -708,9 +733,12 @@ int linear_common(const void *x, const void *weight, const void *bias, void *y, 
     if (addend && !aligned16(addend)) return fail(BM2F_ERR_UNSUPPORTED, "linear: addend must be 16-byte aligned");
     p.split = split;
     if (mask && !aligned16(mask)) return fail(BM2F_ERR_UNSUPPORTED, "linear: mask must be 16-byte aligned");
+    // single TF32 pass: the activation tile goes through TMA like the weights (no split to compute): default for split = 1
+    const bool xtma = split == 1 && !one_tile && !stg_epilogue && !cluster2 && (xvar == 0 || xvar == 5);
     if (!one_tile) {
         if (n_out % 256 == 0) {      // 256-wide column slices (1024-wide FFN layer = 4 slices sharing the row tile)
             p.slices = n_out / 256;
+            if (xtma) return launch_linear_xtma<256>(p, w_hi, sms, st);
             if (xvar == 4) return launch_linear_pair<256>(p, w_hi, w_lo, sms, st);
             if (xvar == 1) return launch_linear_persistent<256, 1, 8, 5>(p, w_hi, w_lo, sms, st);
             if (xvar == 2) return launch_linear_persistent<256, 1, 4, 4>(p, w_hi, w_lo, sms, st);
@@ -719,10 +747,12 @@ int linear_common(const void *x, const void *weight, const void *bias, void *y, 
                             : launch_linear_persistent<256, 1>(p, w_hi, w_lo, sms, st);
         }
         switch (n_out) {
-        case 192: if (xvar == 4) return launch_linear_pair<192>(p, w_hi, w_lo, sms, st);
+        case 192: if (xtma) return launch_linear_xtma<192>(p, w_hi, sms, st);
+                  if (xvar == 4) return launch_linear_pair<192>(p, w_hi, w_lo, sms, st);
                   return cluster2 ? launch_linear_persistent<192, 2>(p, w_hi, w_lo, sms, st)
                                   : launch_linear_persistent<192, 1>(p, w_hi, w_lo, sms, st);
-        case 96: if (xvar == 4) return launch_linear_pair<96>(p, w_hi, w_lo, sms, st);
+        case 96: if (xtma) return launch_linear_xtma<96>(p, w_hi, sms, st);
+                 if (xvar == 4) return launch_linear_pair<96>(p, w_hi, w_lo, sms, st);
                  return cluster2 ? launch_linear_persistent<96, 2>(p, w_hi, w_lo, sms, st)
                                  : launch_linear_persistent<96, 1>(p, w_hi, w_lo, sms, st);
         default: break;      // 288 = 2 x 144 columns does not fit two accumulators: one-tile kernel

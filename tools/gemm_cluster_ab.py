@@ -60,3 +60,22 @@ for k, n in ((256, 256), (256, 192), (256, 96), (256, 1024), (1024, 256)):
     x = torch.randn(rows, k, device=dev); w = torch.randn(n, k, device=dev) / k ** 0.5; b = torch.randn(n, device=dev)
     t1 = t(lambda: MSDA.linear_tf32x3(x, w, b, 3)); t2 = t(lambda: MSDA.linear_tf32x3(x, w, b, 73))
     print(f"{k:4d} -> {n:4d}: single {t1:.3f} ms | CTA pair {t2:.3f} ms", flush=True)
+
+print("single TF32 pass: register-staged activations (split 51) vs TMA-loaded activations (split 1, default)", flush=True)
+for rws in (1, 129, 128 * 5 + 17, 128 * 297 + 5):
+    for k, n in ((256, 256), (256, 192), (256, 96), (256, 1024), (1024, 256)):
+        x = torch.randn(rws, k, device=dev); w = torch.randn(n, k, device=dev) / k ** 0.5; b = torch.randn(n, device=dev)
+        ref = x.double() @ w.double().t() + b.double()
+        e51 = err(MSDA.linear_tf32x3(x, w, b, 51), ref) if n % 256 == 0 else float("nan")
+        e1 = err(MSDA.linear_tf32x3(x, w, b, 1), ref)
+        torch.cuda.synchronize()
+        assert e1 < 3e-3, (rws, k, n, e51, e1)
+print("   errors vs float64 (last shape): register-staged %.2e, TMA %.2e" % (e51, e1), flush=True)
+for k, n in ((256, 256), (256, 192), (256, 96), (256, 1024), (1024, 256)):
+    x = torch.randn(rows, k, device=dev); w = torch.randn(n, k, device=dev) / k ** 0.5; b = torch.randn(n, device=dev)
+    t3 = t(lambda: MSDA.linear_tf32x3(x, w, b, 3)); t1 = t(lambda: MSDA.linear_tf32x3(x, w, b, 1))
+    t51 = t(lambda: MSDA.linear_tf32x3(x, w, b, 51)) if n % 256 == 0 else float("nan")
+    torch.backends.cuda.matmul.allow_tf32 = True
+    tc = t(lambda: torch.nn.functional.linear(x, w, b))
+    torch.backends.cuda.matmul.allow_tf32 = False
+    print(f"{k:4d} -> {n:4d}: tf32x3 {t3:.3f} ms | tf32x1 register-staged {t51:.3f} ms | tf32x1 TMA activations {t1:.3f} ms | cuBLAS TF32 {tc:.3f} ms", flush=True)
