@@ -7,13 +7,14 @@ import torch
 import bm2f_b200
 MSDA = bm2f_b200.load_extension()
 dev = torch.device("cuda:0"); torch.manual_seed(0)
+split = int(os.environ.get("BM2F_SPLIT", "3"))
 rows = 16 * 21504
 xs = {k: torch.randn(rows, k, device=dev) for k in (256, 1024)}
 ws = {k: torch.randn(256, k, device=dev) / k ** 0.5 for k in (256, 1024)}
 b = torch.randn(256, device=dev)
 for _ in range(3):
     for k in (256, 1024):
-        y = MSDA.linear_tf32x3(xs[k], ws[k], b, 3)
+        y = MSDA.linear_tf32x3(xs[k], ws[k], b, split)
 torch.cuda.synchronize()
 print("ok", float(y.abs().mean()))
 if len(sys.argv) > 1 and sys.argv[1] == "clocks":
