@@ -79,3 +79,4 @@ for k, n in ((256, 256), (256, 192), (256, 96), (256, 1024), (1024, 256)):
     tc = t(lambda: torch.nn.functional.linear(x, w, b))
     torch.backends.cuda.matmul.allow_tf32 = False
     print(f"{k:4d} -> {n:4d}: tf32x3 {t3:.3f} ms | tf32x1 register-staged {t51:.3f} ms | tf32x1 TMA activations {t1:.3f} ms | cuBLAS TF32 {tc:.3f} ms", flush=True)
+
