@@ -45,24 +45,56 @@ def _stale(target: str, sources) -> bool:
     return any(os.path.getmtime(s) > t for s in sources)
 
 
-def _run(cmd, log=None):
+def _run(cmd):
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if log:
-        with open(log, "w") as f:
-            f.write(r.stdout)
     if r.returncode != 0:
         sys.stderr.write(r.stdout[-8000:])
         raise RuntimeError("build command failed: " + " ".join(cmd))
     return r.stdout
 
 
+# translation units of libbm2f_msda.so (compiled in parallel, then linked)
+LIB_UNITS = ("api_common.cu", "msda_api.cu", "msda_bwd_sorted.cu", "linear_api.cu", "glue_api.cu", "host_api.cu")
+OBJ_DIR = os.path.join(PKG, "_obj")
+
+
 def build_lib(force=False, ptxas_log=None) -> str:
+    """nvcc -c every unit whose sources changed (headers are shared: any .cuh change rebuilds all), then link.
+    BM2F_SWEEP=1 in the environment adds the sweep-only kernel instantiations (tools/sweep.py)."""
     import glob
-    srcs = glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(CSRC, "msda_api.cu")]   # every header the unit includes
-    srcs.append(os.path.join(ROOT, "include", "bm2f_msda.h"))
-    if force or _stale(LIB, srcs):
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-shared", "-Xptxas", "-v", "-o", LIB, os.path.join(CSRC, "msda_api.cu")]
-        _run(cmd, log=ptxas_log or os.path.join(PKG, "ptxas_v.log"))
+    from concurrent.futures import ThreadPoolExecutor
+    headers = glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(ROOT, "include", "bm2f_msda.h")]
+    flags = list(NVCC_FLAGS)
+    sweep = os.environ.get("BM2F_SWEEP", "0") not in ("", "0")
+    if sweep:
+        flags.append("-DBM2F_SWEEP")
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    stamp = os.path.join(OBJ_DIR, "flags.txt")
+    if not os.path.exists(stamp) or open(stamp).read() != " ".join(flags):
+        force = True
+    units = [u for u in LIB_UNITS if os.path.exists(os.path.join(CSRC, u))]
+    todo = []
+    for u in units:
+        obj = os.path.join(OBJ_DIR, u[:-3] + ".o")
+        if force or _stale(obj, headers + [os.path.join(CSRC, u)]):
+            todo.append((u, obj))
+
+    def compile_unit(job):
+        u, obj = job
+        return u, _run([_nvcc()] + flags + ["-Xptxas", "-v", "-c", "-o", obj, os.path.join(CSRC, u)])
+
+    if todo:
+        with ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 4)) as ex:
+            logs = list(ex.map(compile_unit, todo))
+        log_path = ptxas_log or os.path.join(OBJ_DIR, "ptxas_v.log")      # build artefact, git-ignored
+        with open(log_path, "a" if len(todo) < len(units) else "w") as f:
+            for u, out in logs:
+                f.write(f"==== {u}\n{out}\n")
+        with open(stamp, "w") as f:
+            f.write(" ".join(flags))
+    objs = [os.path.join(OBJ_DIR, u[:-3] + ".o") for u in units]
+    if todo or _stale(LIB, objs):
+        _run([_nvcc()] + NVCC_FLAGS + ["-shared", "-o", LIB] + objs)
     return LIB
 
 

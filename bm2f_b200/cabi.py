@@ -32,7 +32,8 @@ class Tuning(ctypes.Structure):
     _fields_ = [("vec", ctypes.c_int), ("staging", ctypes.c_int), ("strip_w", ctypes.c_int),
                 ("rows", ctypes.c_int), ("ctas_per_sm", ctypes.c_int), ("force_generic", ctypes.c_int),
                 ("order", ctypes.c_int), ("merge", ctypes.c_int), ("geo", ctypes.c_int),
-                ("reserved", ctypes.c_int * 7)]
+                ("bwd", ctypes.c_int), ("bwd_margin", ctypes.c_int), ("bwd_lanes", ctypes.c_int),
+                ("reserved", ctypes.c_int * 4)]
 
 
 class MSDAError(RuntimeError):

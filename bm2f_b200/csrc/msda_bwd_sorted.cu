@@ -1,0 +1,82 @@
+// Launcher of the anchor-sorted backward (msda_bwd_sorted.cuh).  Called from bm2f_msda_backward /
+// bm2f_msda_fused_backward (msda_api.cu) when the problem qualifies: float32, D = 32, M = 8, P = 4, L <= 4 and the
+// queries are the pixels of the levels (Lq == S, encoder self-attention).
+#include "api_common.cuh"
+#include "msda_bwd_sorted.cuh"
+
+namespace bm2f {
+namespace host {
+
+namespace {
+constexpr int kCells = 8192;      // 16-bit anchor cells per chunk (16 KB)
+
+template <int L_, int RMAX, int NWARP, int LPP, bool FUSED, int CPS>
+int launch(const FastParams &p, int marg, const CUtensorMap &ml, const CUtensorMap &mw, const CUtensorMap &mg, int sms,
+           long long est_jobs, cudaStream_t st)
+{
+    constexpr int smem = SortedSmem<L_, RMAX, kCells>::kBytes;
+    auto kern = msda_bwd_sorted_kernel<L_, RMAX, NWARP, LPP, FUSED, kCells, CPS>;
+    int rc = ensure_dynamic_smem<&msda_bwd_sorted_kernel<L_, RMAX, NWARP, LPP, FUSED, kCells, CPS>>(
+        smem, "cudaFuncSetAttribute(sorted backward smem)");
+    if (rc) return rc;
+    const long long grid_max = static_cast<long long>(sms) * CPS;
+    const int grid = static_cast<int>(est_jobs < grid_max ? est_jobs : grid_max);
+    kern<<<grid, NWARP * 32, smem, st>>>(p, marg, ml, mw, mg);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "launch msda_bwd_sorted_kernel");
+    count_launch(1);
+    return BM2F_OK;
+}
+
+template <int L_, int RMAX, bool FUSED>
+int pick(const FastParams &p, int marg, int lanes, const CUtensorMap &ml, const CUtensorMap &mw, const CUtensorMap &mg,
+         int sms, long long est_jobs, cudaStream_t st)
+{
+    // two CTAs of 8 warps per SM: while one sits in the short single-threaded / barrier phases the other computes
+    if (lanes == 4) return launch<L_, RMAX, 8, 4, FUSED, 2>(p, marg, ml, mw, mg, sms, est_jobs, st);
+    return launch<L_, RMAX, 8, 8, FUSED, 2>(p, marg, ml, mw, mg, sms, est_jobs, st);
+}
+}  // namespace
+
+bool bwd_sorted_eligible(const Dims &d, int dtype, const bm2f_msda_tuning_t &t)
+{
+    return dtype == BM2F_DTYPE_F32 && d.D == 32 && d.M == kHeads && d.P == 4 && d.L >= 1 && d.L <= 4 && d.Lq == d.S &&
+           t.order == 0 && !t.force_generic;
+}
+
+int run_bwd_sorted(FastParams p, const Dims &d, const bm2f_msda_tuning_t &t, bool fused, cudaStream_t st)
+{
+    int sms = 0, cc = 0;
+    int rc = device_info(&sms, &cc);
+    if (rc) return rc;
+    if (cc < 10) return fail(BM2F_ERR_CUDA, "this library contains sm_100a code only; device has cc %d.x", cc);
+    const int marg = t.bwd_margin > 0 ? t.bwd_margin : 6;
+    if (marg > 64) return fail(BM2F_ERR_INVALID, "bwd_margin %d out of range (1..64)", marg);
+    const int lanes = t.bwd_lanes == 4 ? 4 : 8;
+    p.order = t.order;
+    p.rows = 0;
+    const int LP = d.L * d.P;
+    const uint64_t rows_total = static_cast<uint64_t>(d.N) * d.Lq;
+    CUtensorMap ml, mw, mg;
+    if ((rc = make_map(&ml, p.loc, rows_total, static_cast<uint64_t>(d.M) * LP * 2, 32, LP * 2))) return rc;
+    if ((rc = make_map(&mw, p.attn, rows_total, static_cast<uint64_t>(d.M) * LP, 32, LP))) return rc;
+    if ((rc = make_map(&mg, static_cast<const float *>(p.grad_out), rows_total, static_cast<uint64_t>(d.M) * d.D, 32, d.D)))
+        return rc;
+    // lower bound on the chunk count (tiles hold at most 32 x RMAX queries); the kernel enumerates the exact tiles
+    // from the device-resident shape table
+    const long long est_jobs = static_cast<long long>(d.N) * d.M * ((d.Lq + 32 * 6 - 1) / (32 * 6));
+#define BM2F_SORTED(L_, RMAX)                                                                                         \
+    return fused ? pick<L_, RMAX, true>(p, marg, lanes, ml, mw, mg, sms, est_jobs, st)                                \
+                 : pick<L_, RMAX, false>(p, marg, lanes, ml, mw, mg, sms, est_jobs, st)
+    switch (d.L) {
+    case 1: BM2F_SORTED(1, 6);
+    case 2: BM2F_SORTED(2, 6);
+    case 3: BM2F_SORTED(3, 6);
+    case 4: BM2F_SORTED(4, 4);
+    }
+#undef BM2F_SORTED
+    return fail(BM2F_ERR_UNSUPPORTED, "sorted backward: L = %d", d.L);
+}
+
+}  // namespace host
+}  // namespace bm2f
