@@ -17,7 +17,7 @@ DTYPE_F32, DTYPE_F64, DTYPE_BF16 = 0, 1, 2
 # every symbol include/bm2f_msda.h declares (tests/test_cabi_symbols.py checks the export list)
 SYMBOLS = (
     "bm2f_msda_abi_version", "bm2f_msda_build_info", "bm2f_msda_last_error", "bm2f_msda_launch_count",
-    "bm2f_msda_set_default_tuning", "bm2f_msda_check_im2col_step", "bm2f_msda_forward",
+    "bm2f_msda_set_default_tuning", "bm2f_msda_debug_phase_profile", "bm2f_msda_check_im2col_step", "bm2f_msda_forward",
     "bm2f_msda_backward", "bm2f_msda_forward_backward_host", "bm2f_msda_release_host_workspace", "bm2f_msda_fused_supported",
     "bm2f_msda_fused_forward", "bm2f_msda_fused_backward", "bm2f_linear_workspace_bytes", "bm2f_linear_forward",
     "bm2f_linear_backward_input", "bm2f_linear_backward_weight", "bm2f_linear_relu_forward",
@@ -57,6 +57,8 @@ def lib():
         L.bm2f_msda_launch_count.restype = ctypes.c_uint64
         L.bm2f_msda_set_default_tuning.argtypes = [tp]
         L.bm2f_msda_set_default_tuning.restype = None
+        L.bm2f_msda_debug_phase_profile.argtypes = [vp]
+        L.bm2f_msda_debug_phase_profile.restype = None
         L.bm2f_msda_check_im2col_step.argtypes = [ci, ci]
         L.bm2f_msda_check_im2col_step.restype = ci
         L.bm2f_msda_forward.argtypes = [vp, i64p, i64p, vp, vp, vp] + [ci] * 8 + [tp, vp]
@@ -95,7 +97,10 @@ def _check(rc: int, what: str):
 def make_tuning(**kw):
     t = Tuning()
     for k, v in kw.items():
-        setattr(t, k, int(v))
+        if k == "variant":              # A/B selector of the anchor-sorted backward (reserved[0])
+            t.reserved[0] = int(v)
+        else:
+            setattr(t, k, int(v))
     return t
 
 

@@ -4,24 +4,28 @@
 #include "api_common.cuh"
 #include "msda_bwd_sorted.cuh"
 
+#include <atomic>
+
 namespace bm2f {
 namespace host {
 
 namespace {
 constexpr int kCells = 8192;      // 16-bit anchor cells per chunk (16 KB)
 
-template <int L_, int RMAX, int NWARP, int LPP, bool FUSED, int CPS>
+std::atomic<long long *> g_prof{nullptr};     // diagnostics: bm2f_msda_debug_phase_profile
+
+template <int L_, int RMAX, int NWARP, int LPP, bool FUSED, int CPS, bool PIPE>
 int launch(const FastParams &p, int marg, const CUtensorMap &ml, const CUtensorMap &mw, const CUtensorMap &mg, int sms,
            long long est_jobs, cudaStream_t st)
 {
     constexpr int smem = SortedSmem<L_, RMAX, kCells>::kBytes;
-    auto kern = msda_bwd_sorted_kernel<L_, RMAX, NWARP, LPP, FUSED, kCells, CPS>;
-    int rc = ensure_dynamic_smem<&msda_bwd_sorted_kernel<L_, RMAX, NWARP, LPP, FUSED, kCells, CPS>>(
+    int rc = ensure_dynamic_smem<&msda_bwd_sorted_kernel<L_, RMAX, NWARP, LPP, FUSED, kCells, CPS, PIPE>>(
         smem, "cudaFuncSetAttribute(sorted backward smem)");
     if (rc) return rc;
     const long long grid_max = static_cast<long long>(sms) * CPS;
     const int grid = static_cast<int>(est_jobs < grid_max ? est_jobs : grid_max);
-    kern<<<grid, NWARP * 32, smem, st>>>(p, marg, ml, mw, mg);
+    msda_bwd_sorted_kernel<L_, RMAX, NWARP, LPP, FUSED, kCells, CPS, PIPE>
+        <<<grid, NWARP * 32, smem, st>>>(p, marg, g_prof.load(std::memory_order_relaxed), ml, mw, mg);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "launch msda_bwd_sorted_kernel");
     count_launch(1);
@@ -29,12 +33,29 @@ int launch(const FastParams &p, int marg, const CUtensorMap &ml, const CUtensorM
 }
 
 template <int L_, int RMAX, bool FUSED>
-int pick(const FastParams &p, int marg, int lanes, const CUtensorMap &ml, const CUtensorMap &mw, const CUtensorMap &mg,
-         int sms, long long est_jobs, cudaStream_t st)
+int pick(const FastParams &p, int marg, int lanes, int variant, const CUtensorMap &ml, const CUtensorMap &mw,
+         const CUtensorMap &mg, int sms, long long est_jobs, cudaStream_t st)
 {
-    // two CTAs of 8 warps per SM: while one sits in the short single-threaded / barrier phases the other computes
-    if (lanes == 4) return launch<L_, RMAX, 8, 4, FUSED, 2>(p, marg, ml, mw, mg, sms, est_jobs, st);
-    return launch<L_, RMAX, 8, 8, FUSED, 2>(p, marg, ml, mw, mg, sms, est_jobs, st);
+    // default: two CTAs of 8 warps per SM — while one sits in the short single-threaded / barrier phases the other computes
+#define BM2F_V(NWARP, LPP, CPS, PIPE, R) return launch<L_, R, NWARP, LPP, FUSED, CPS, PIPE>(p, marg, ml, mw, mg, sms, est_jobs, st)
+    if constexpr (L_ == 3 && !FUSED) {          // A/B variants (tuning.reserved[0]) for the benchmark shape only
+        switch (variant * 10 + lanes) {
+        case 18: BM2F_V(8, 8, 2, true, RMAX);
+        case 14: BM2F_V(8, 4, 2, true, RMAX);
+        case 28: BM2F_V(16, 8, 1, true, 8);
+        case 24: BM2F_V(16, 4, 1, true, 8);
+        case 38: BM2F_V(6, 8, 2, true, RMAX);
+        case 34: BM2F_V(6, 4, 2, true, RMAX);
+        case 48: BM2F_V(12, 8, 1, true, 9);
+        case 44: BM2F_V(12, 4, 1, true, 9);
+        case 58: BM2F_V(16, 8, 1, false, 8);
+        case 54: BM2F_V(16, 4, 1, false, 8);
+        default: break;
+        }
+    }
+    if (lanes == 4) BM2F_V(8, 4, 2, false, RMAX);
+    BM2F_V(8, 8, 2, false, RMAX);
+#undef BM2F_V
 }
 }  // namespace
 
@@ -65,9 +86,10 @@ int run_bwd_sorted(FastParams p, const Dims &d, const bm2f_msda_tuning_t &t, boo
     // lower bound on the chunk count (tiles hold at most 32 x RMAX queries); the kernel enumerates the exact tiles
     // from the device-resident shape table
     const long long est_jobs = static_cast<long long>(d.N) * d.M * ((d.Lq + 32 * 6 - 1) / (32 * 6));
+    const int variant = t.reserved[0];
 #define BM2F_SORTED(L_, RMAX)                                                                                         \
-    return fused ? pick<L_, RMAX, true>(p, marg, lanes, ml, mw, mg, sms, est_jobs, st)                                \
-                 : pick<L_, RMAX, false>(p, marg, lanes, ml, mw, mg, sms, est_jobs, st)
+    return fused ? pick<L_, RMAX, true>(p, marg, lanes, variant, ml, mw, mg, sms, est_jobs, st)                       \
+                 : pick<L_, RMAX, false>(p, marg, lanes, variant, ml, mw, mg, sms, est_jobs, st)
     switch (d.L) {
     case 1: BM2F_SORTED(1, 6);
     case 2: BM2F_SORTED(2, 6);
@@ -78,5 +100,12 @@ int run_bwd_sorted(FastParams p, const Dims &d, const bm2f_msda_tuning_t &t, boo
     return fail(BM2F_ERR_UNSUPPORTED, "sorted backward: L = %d", d.L);
 }
 
+void set_phase_profile(long long *dev) { g_prof.store(dev, std::memory_order_relaxed); }
+
 }  // namespace host
 }  // namespace bm2f
+
+extern "C" void bm2f_msda_debug_phase_profile(void *device_buffer)
+{
+    bm2f::host::set_phase_profile(static_cast<long long *>(device_buffer));
+}

@@ -86,6 +86,7 @@ __device__ __forceinline__ void sorted_build_tabs(SortedTabs &t, const FastParam
         t.H[l] = static_cast<int>(p.shapes[2 * l]);
         t.W[l] = static_cast<int>(p.shapes[2 * l + 1]);
         t.start[l] = static_cast<int>(p.start[l]);
+        if (!level_in_bounds(p.start[l], p.shapes[2 * l], p.shapes[2 * l + 1], p.S)) { t.H[l] = 0; t.W[l] = 0; t.start[l] = 0; }
         total += t.H[l] * t.W[l];
     }
     int jobs = 0;
@@ -202,8 +203,7 @@ __device__ __forceinline__ uint32_t cell_offset(const uint32_t *cnt, int cell)
 template <int NT, int NW>
 __device__ __forceinline__ int sorted_block_scan(uint32_t *cnt, int n, uint32_t *warp_sums, int tid)
 {
-    constexpr int NWARPS = NT / 32, PER = NW / NT;
-    static_assert(NW % NT == 0 && PER % 4 == 0, "whole uint4s per thread");
+    constexpr int NWARPS = NT / 32, PER = ((NW + NT - 1) / NT + 3) / 4 * 4;      // whole uint4s per thread
     const int lane = tid & 31, warp = tid >> 5;
     uint32_t carry = 0;
 #pragma unroll
@@ -255,9 +255,9 @@ __device__ __forceinline__ int sorted_block_scan(uint32_t *cnt, int n, uint32_t 
 
 constexpr int kSortedSkip = -1;       // record already final ({ga, gx, gy, a}); not in the sorted list
 
-template <int L_, int RMAX, int NWARP, int LPP, bool FUSED, int CELLS_MAX, int CPS>
+template <int L_, int RMAX, int NWARP, int LPP, bool FUSED, int CELLS_MAX, int CPS, bool PIPE>
 __global__ void __launch_bounds__(NWARP * 32, CPS)
-msda_bwd_sorted_kernel(const FastParams p, const int marg, const __grid_constant__ CUtensorMap tm_loc,
+msda_bwd_sorted_kernel(const FastParams p, const int marg, long long *prof_out, const __grid_constant__ CUtensorMap tm_loc,
                        const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_go)
 {
     constexpr int P_ = 4, LP = L_ * P_, NT = NWARP * 32, D = 32, MD = kHeads * D;
@@ -333,6 +333,11 @@ msda_bwd_sorted_kernel(const FastParams p, const int marg, const __grid_constant
     (void)grad_out_unused;
     float *grad_value = static_cast<float *>(p.grad_value);
 
+    // optional phase profile (tools/bwd_phases.py): cycles thread 0 spends in each phase, summed over this CTA's chunks
+    const bool prof = prof_out != nullptr && tid == 0;
+    long long pt_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long t_prev = prof ? clock64() : 0;
+
     uint32_t phase = 0;
     for (int j = blockIdx.x; j < total_jobs; j += gridDim.x, phase ^= 1) {
         const SortedJob job = sorted_decode_job(tabs, p, j);
@@ -352,6 +357,7 @@ msda_bwd_sorted_kernel(const FastParams p, const int marg, const __grid_constant
         float *gbm = grad_value + img;
 
         mbar_wait(&bar_la, phase);
+        if (prof) { const long long c = clock64(); pt_[0] += c - t_prev; t_prev = c; }     // window + clear + wait loc/attn
 
         // ---- phase 0 (fused): softmax over each query's logits, loc = ref + offset / (W, H); lane = query ----
         if constexpr (FUSED) {
@@ -483,9 +489,11 @@ msda_bwd_sorted_kernel(const FastParams p, const int marg, const __grid_constant
             }
         }
         __syncthreads();
+        if (prof) { const long long c = clock64(); pt_[1] += c - t_prev; t_prev = c; }     // (prologue +) phase 1
 
         // ---- scan + scatter: points sorted by anchor cell ----
         const int nsorted = sorted_block_scan<NT, NW>(s_cnt, ncells, warp_sums, tid);
+        if (prof) { const long long c = clock64(); pt_[2] += c - t_prev; t_prev = c; }     // scan
 #pragma unroll
         for (int l = 0; l < L_; ++l) {
 #pragma unroll
@@ -499,6 +507,7 @@ msda_bwd_sorted_kernel(const FastParams p, const int marg, const __grid_constant
             }
         }
         __syncthreads();
+        if (prof) { const long long c = clock64(); pt_[3] += c - t_prev; t_prev = c; }     // scatter
         // loc / attn buffers are free: prefetch the next chunk's
         SortedJob next{};
         if (tid == 0 && have_next) {
@@ -508,6 +517,7 @@ msda_bwd_sorted_kernel(const FastParams p, const int marg, const __grid_constant
 
         // ---- phase 2: lane groups walk equal ranges of the sorted points ----
         if (!go_ready) mbar_wait(&bar_go, phase);
+        if (prof) { const long long c = clock64(); pt_[4] += c - t_prev; t_prev = c; }
         {
             const int lg = lane / LPP, sub = lane % LPP;
             const unsigned gmask = (LPP == 32 ? 0xffffffffu : ((1u << LPP) - 1u)) << (lg * LPP);
@@ -535,35 +545,34 @@ msda_bwd_sorted_kernel(const FastParams p, const int marg, const __grid_constant
                             VecIO<float, 4>::red_add(dst + 4 * n, rv);
                         }
                     }
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) acc[k][c] = 0.f;
                 }
             };
-
-            for (; i < iend; ++i) {
-                const int pt = s_perm[i];
-                const float4 rec = s_rec[pt];
-                const int packed = __float_as_int(rec.w);
-                if (packed != cur) {
-                    if (cur != kSortedSkip) flush();
-                    cur = packed;
-                    cmask = (packed >> 24) & 15;
-                    const int lvl = (packed >> 28) & 3;
-                    cW = W[0];
+            // anchor of a record -> corner mask, level width, element offset of the anchor pixel
+            auto decode = [&](int packed, int &mask, int &wl, long long &e) {
+                mask = (packed >> 24) & 15;
+                const int lvl = (packed >> 28) & 3;
+                wl = W[0];
 #pragma unroll
-                    for (int k = 1; k < L_; ++k)
-                        if (lvl == k) cW = W[k];
-                    e00 = static_cast<long long>((packed & 0xffffff) - (cW + 1)) * MD;
+                for (int k = 1; k < L_; ++k)
+                    if (lvl == k) wl = W[k];
+                e = static_cast<long long>((packed & 0xffffff) - (wl + 1)) * MD;
+            };
+            auto load_lines = [&](float (&dst)[4][CH], int mask, int wl, long long e) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float *srcp = vb + e00 + ((k & 1) ? MD : 0) + ((k >> 1) ? static_cast<long long>(cW) * MD : 0);
+                for (int k = 0; k < 4; ++k) {
+                    const float *srcp = vb + e + ((k & 1) ? MD : 0) + ((k >> 1) ? static_cast<long long>(wl) * MD : 0);
 #pragma unroll
-                        for (int n = 0; n < NV; ++n) {
-                            float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if ((cmask >> k) & 1) t4 = __ldg(reinterpret_cast<const float4 *>(srcp) + n);
-                            v[k][4 * n] = t4.x; v[k][4 * n + 1] = t4.y; v[k][4 * n + 2] = t4.z; v[k][4 * n + 3] = t4.w;
-                            acc[k][4 * n] = 0.f; acc[k][4 * n + 1] = 0.f; acc[k][4 * n + 2] = 0.f; acc[k][4 * n + 3] = 0.f;
-                        }
+                    for (int n = 0; n < NV; ++n) {
+                        float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if ((mask >> k) & 1) t4 = __ldg(reinterpret_cast<const float4 *>(srcp) + n);
+                        dst[k][4 * n] = t4.x; dst[k][4 * n + 1] = t4.y; dst[k][4 * n + 2] = t4.z; dst[k][4 * n + 3] = t4.w;
                     }
                 }
+            };
+            // one point: grad_output row of its query from shared memory, four accumulators, three dot products
+            auto process = [&](int pt, const float4 rec) {
                 const int qi = pt / LP;
                 float go[CH];
 #pragma unroll
@@ -596,10 +605,68 @@ msda_bwd_sorted_kernel(const FastParams p, const int marg, const __grid_constant
 #pragma unroll
                     for (int c = 0; c < CH; ++c) acc[k][c] = fmaf(cw[k], go[c], acc[k][c]);
                 if (sub == 0) s_rec[pt] = make_float4(pa, a * px, a * py, a);
+            };
+
+            if constexpr (PIPE) {
+                // the value lines of the NEXT anchor are requested while the current point is processed: the global
+                // (L2) latency of an anchor change is overlapped instead of stalling the group at every change
+                if (i < iend) {
+                    int pt = s_perm[i];
+                    float4 rec = s_rec[pt];
+                    cur = __float_as_int(rec.w);
+                    decode(cur, cmask, cW, e00);
+                    load_lines(v, cmask, cW, e00);
+                    for (; i < iend; ++i) {
+                        const bool has_n = i + 1 < iend;
+                        int pt_n = 0;
+                        float4 rec_n = make_float4(0.f, 0.f, 0.f, 0.f);
+                        int packed_n = kSortedSkip;
+                        if (has_n) {
+                            pt_n = s_perm[i + 1];
+                            rec_n = s_rec[pt_n];
+                            packed_n = __float_as_int(rec_n.w);
+                        }
+                        const bool trans = packed_n != cur;
+                        float vn[4][CH];
+                        int nmask = 0, nW = 0;
+                        long long ne = 0;
+                        if (trans && has_n) {
+                            decode(packed_n, nmask, nW, ne);
+                            load_lines(vn, nmask, nW, ne);
+                        }
+                        process(pt, rec);
+                        if (trans) {
+                            flush();
+                            if (has_n) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                                    for (int c = 0; c < CH; ++c) v[k][c] = vn[k][c];
+                                cur = packed_n; cmask = nmask; cW = nW; e00 = ne;
+                            }
+                        }
+                        pt = pt_n;
+                        rec = rec_n;
+                    }
+                }
+            } else {
+                for (; i < iend; ++i) {
+                    const int pt = s_perm[i];
+                    const float4 rec = s_rec[pt];
+                    const int packed = __float_as_int(rec.w);
+                    if (packed != cur) {
+                        if (cur != kSortedSkip) flush();
+                        cur = packed;
+                        decode(cur, cmask, cW, e00);
+                        load_lines(v, cmask, cW, e00);
+                    }
+                    process(pt, rec);
+                }
+                if (cur != kSortedSkip) flush();
             }
-            if (cur != kSortedSkip) flush();
         }
         __syncthreads();
+        if (prof) { const long long c = clock64(); pt_[5] += c - t_prev; t_prev = c; pt_[7] += nsorted; }   // phase 2
         // grad_output rows are free: prefetch the next chunk's
         if (tid == 0 && have_next) issue_go(next);
 
@@ -636,8 +703,11 @@ msda_bwd_sorted_kernel(const FastParams p, const int marg, const __grid_constant
                 }
             }
         }
+        if (prof) { const long long c = clock64(); pt_[6] += c - t_prev; t_prev = c; }     // phase 3 (thread 0's share)
         // the next iteration's barrier (after the counters are cleared) orders these record reads before phase 1 rewrites them
     }
+    if (prof)
+        for (int i = 0; i < 8; ++i) prof_out[blockIdx.x * 8 + i] = pt_[i];
 }
 
 }  // namespace bm2f

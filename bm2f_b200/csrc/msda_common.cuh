@@ -189,6 +189,14 @@ struct VecIO<__nv_bfloat16, 2> {
     }
 };
 
+// A level whose slice [start, start + H*W) does not lie inside the S pixels of `value` (a level table that disagrees
+// with the tensor; the reference asserts the sum on the host, ops/modules/ms_deform_attn.py:96) is treated as EMPTY by
+// every kernel: H = W = 0 drops all its corners, so nothing is read or written outside value / grad_value.
+__device__ __forceinline__ bool level_in_bounds(long long start, long long H, long long W, long long S)
+{
+    return H >= 0 && W >= 0 && start >= 0 && H <= S && W <= S && start + H * W <= S;
+}
+
 // ------------------------------------------------------------------------------------------
 // One bilinear footprint: the four corner weights / validity of a sampling point.
 // ------------------------------------------------------------------------------------------

@@ -66,6 +66,7 @@ __device__ __forceinline__ void build_tabs(Tabs<L_> &t, const FastParams &p)
         t.H[l] = static_cast<int>(p.shapes[2 * l]);
         t.W[l] = static_cast<int>(p.shapes[2 * l + 1]);
         t.start[l] = static_cast<int>(p.start[l]);
+        if (!level_in_bounds(p.start[l], p.shapes[2 * l], p.shapes[2 * l + 1], p.S)) { t.H[l] = 0; t.W[l] = 0; t.start[l] = 0; }
         total += t.H[l] * t.W[l];
     }
     int jobs = 0;

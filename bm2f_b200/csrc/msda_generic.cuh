@@ -78,8 +78,9 @@ __global__ void __launch_bounds__(256) msda_fwd_generic_kernel(const GenericPara
         const int c = c0 + lane;
         T acc = 0;
         for (int l = 0; l < p.L; ++l) {
-            const int H = static_cast<int>(p.shapes[2 * l]), W = static_cast<int>(p.shapes[2 * l + 1]);
-            const T *vl = value + (static_cast<long long>(b) * p.S + p.start[l]) * row + static_cast<long long>(m) * p.D;
+            const bool lvl_ok = level_in_bounds(p.start[l], p.shapes[2 * l], p.shapes[2 * l + 1], p.S);
+            const int H = lvl_ok ? static_cast<int>(p.shapes[2 * l]) : 0, W = lvl_ok ? static_cast<int>(p.shapes[2 * l + 1]) : 0;
+            const T *vl = value + (static_cast<long long>(b) * p.S + (lvl_ok ? p.start[l] : 0)) * row + static_cast<long long>(m) * p.D;
             for (int pt = 0; pt < p.P; ++pt) {
                 const int i = l * p.P + pt;
                 const Taps<T> t = resolve_taps<T>(loc[2 * i], loc[2 * i + 1], H, W);
@@ -112,8 +113,9 @@ __global__ void __launch_bounds__(256) msda_bwd_generic_kernel(const GenericPara
     const long long row = static_cast<long long>(p.M) * p.D;
 
     for (int l = 0; l < p.L; ++l) {
-        const int H = static_cast<int>(p.shapes[2 * l]), W = static_cast<int>(p.shapes[2 * l + 1]);
-        const long long base = (static_cast<long long>(b) * p.S + p.start[l]) * row + static_cast<long long>(m) * p.D;
+        const bool lvl_ok = level_in_bounds(p.start[l], p.shapes[2 * l], p.shapes[2 * l + 1], p.S);
+        const int H = lvl_ok ? static_cast<int>(p.shapes[2 * l]) : 0, W = lvl_ok ? static_cast<int>(p.shapes[2 * l + 1]) : 0;
+        const long long base = (static_cast<long long>(b) * p.S + (lvl_ok ? p.start[l] : 0)) * row + static_cast<long long>(m) * p.D;
         for (int pt = 0; pt < p.P; ++pt) {
             const int i = l * p.P + pt;
             const Taps<T> t = resolve_taps<T>(loc[2 * i], loc[2 * i + 1], H, W);

@@ -130,6 +130,9 @@ class MSDeformAttnTransformerEncoder(nn.Module):
             spatial_shapes_list if spatial_shapes_list is not None else spatial_shapes, valid_ratios, src.device)
         if unit_valid_ratios:
             reference_points.pixel_centres = True
+        if spatial_shapes_list is not None and torch.is_tensor(spatial_shapes):
+            # lets MSDeformAttn.forward check the table against Len_in on the host (no device sync per layer)
+            spatial_shapes.hw_list = [(int(h), int(w)) for h, w in spatial_shapes_list]
         for layer in self.layers:
             output = layer(output, pos, reference_points, spatial_shapes, level_start_index, padding_mask)
         return output

@@ -92,6 +92,7 @@ class MSDeformAttn(nn.Module):
         return (self.fuse_prologue and self.tcgen05_linear and src.is_cuda and src.dtype == torch.float32
                 and pos is not None and pos.dtype == torch.float32 and reference_points.shape[-1] == 2
                 and reference_points.dtype == torch.float32
+                and not (torch.is_grad_enabled() and reference_points.requires_grad)
                 and all(linear_func.supported(l, src) for l in (self.value_proj, self.sampling_offsets, self.attention_weights))
                 and bool(MSDA.ms_deform_attn_fused_supported(self.n_heads, self.d_model // self.n_heads, self.n_levels,
                                                              self.n_points, False)))
@@ -130,10 +131,21 @@ class MSDeformAttn(nn.Module):
         N, Len_in, _ = input_flatten.shape
         if not query.is_cuda:
             raise RuntimeError("MSDeformAttn: Not implemented on the CPU (this build has no CPU fallback)")
-        # no device->host sync here: the level table is validated on the device side of the op
+        # the reference's check (ops/modules/ms_deform_attn.py:96).  Callers that built the table from a Python list
+        # (bm2f_b200.encoder) attach it as `hw_list`, so the check costs no device->host sync; a bare tensor is checked
+        # exactly like the reference does (one sync).  The kernels additionally treat a level that does not fit
+        # inside `input_flatten` as empty, so a wrong table can never read or write out of bounds.
+        hw_list = getattr(input_spatial_shapes, "hw_list", None)
+        if hw_list is not None:
+            assert sum(int(h) * int(w) for h, w in hw_list) == Len_in
+        else:
+            assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == Len_in
 
+        # the fused kernels return no gradient for reference_points (Mask2Former builds them from the level shapes):
+        # learnable / refined reference points take the unfused path, which propagates it through sampling_locations
+        ref_needs_grad = torch.is_grad_enabled() and reference_points.requires_grad
         use_fused = (self.fuse_prologue and reference_points.shape[-1] == 2 and reference_points.dtype == torch.float32
-                     and query.dtype == torch.float32
+                     and query.dtype == torch.float32 and not ref_needs_grad
                      and MSDA.ms_deform_attn_fused_supported(self.n_heads, self.d_model // self.n_heads, self.n_levels,
                                                              self.n_points, False))
         if use_fused:

@@ -20,6 +20,7 @@ What runs where on CUDA float32 (`fused = True`, the default):
 the comparison arm on the GPU)."""
 from __future__ import annotations
 
+import collections
 import math
 from collections import namedtuple
 from typing import Callable, Dict, List, Optional, Union
@@ -86,7 +87,11 @@ class PositionEmbeddingSine(nn.Module):
         if scale is not None and normalize is False:
             raise ValueError("normalize should be True if scale is passed")
         self.scale = 2 * math.pi if scale is None else scale
-        self._cache = {}
+        self._cache = collections.OrderedDict()     # (H, W, device) -> table; small LRU, see tokens()
+
+    # Inference sees many image sizes: keep the few most recent level shapes (a training run with fixed crops hits 3),
+    # not one table per shape ever seen.  The kernel that fills a table is a single cheap pass.
+    CACHE_ENTRIES = 12
 
     def tokens(self, height, width, like):
         key = (int(height), int(width), like.device)
@@ -95,7 +100,18 @@ class PositionEmbeddingSine(nn.Module):
             tab = MSDA.sine_position_embedding(like, int(height), int(width), self.num_pos_feats, float(self.temperature),
                                                float(self.scale), bool(self.normalize))
             self._cache[key] = tab
+            while len(self._cache) > self.CACHE_ENTRIES:
+                self._cache.popitem(last=False)
+        else:
+            self._cache.move_to_end(key)
         return tab
+
+    def __deepcopy__(self, memo):
+        # cached device tables are derived state: a copy (or a .to() of it) starts empty
+        new = type(self)(self.num_pos_feats, self.temperature, self.normalize, self.scale if self.normalize else None)
+        new.scale = self.scale
+        memo[id(self)] = new
+        return new
 
     def forward(self, x, mask=None):
         if mask is not None:

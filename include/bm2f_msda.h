@@ -91,7 +91,7 @@ typedef struct {
     int bwd_margin; /* anchor-sorted backward: window margin around a query tile in pixels of the sampled level; points
                        further out take the slow per-corner path inside the kernel.  0 = default (6)                  */
     int bwd_lanes;  /* anchor-sorted backward: lanes per sampling point, 8 (x 4 channels, default) or 4 (x 8 channels)  */
-    int reserved[4];
+    int reserved[4]; /* reserved[0]: anchor-sorted backward A/B variant for L = 3 (msda_bwd_sorted.cu: pick) */
 } bm2f_msda_tuning_t;
 
 /* Library / ABI identification. */
@@ -104,6 +104,12 @@ const char *bm2f_msda_last_error(void);
 /* Number of kernels this library has launched since load (all threads).  bench.py reports
  * the difference over its timed region as `gpu_launches`. */
 uint64_t bm2f_msda_launch_count(void);
+
+/* Diagnostics (tools/bwd_phases.py): when device_buffer != NULL, every anchor-sorted backward launched afterwards makes
+ * thread 0 of each CTA record the cycles it spends per phase — 8 int64 per CTA: wait for loc/attn, phase 1, scan,
+ * scatter, wait for grad_output, phase 2, phase 3, sorted points — into device_buffer[blockIdx.x * 8 ...] (room for
+ * 2 * SM count CTAs).  NULL switches it off.  Process-wide, not synchronised: a measurement aid, not an API. */
+void bm2f_msda_debug_phase_profile(void *device_buffer);
 
 /* Process-wide default tuning used when a call passes tuning == NULL. */
 void bm2f_msda_set_default_tuning(const bm2f_msda_tuning_t *tuning);

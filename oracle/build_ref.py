@@ -7,6 +7,8 @@ build.  Output: oracle/_ref/msda_reference_cuda<EXT_SUFFIX> (git-ignored, travel
 
 It is used only (a) by bench.py to time "the reference's own CUDA op" beside the new kernels and
 (b) by tests/test_gpu_reference_op.py to record its parity against the same oracle.
+stage_ops_py() additionally stages the reference's Python files of the op package (test.py, functions/, modules/)
+unmodified into oracle/_ref/ops_unmodified/ for tests/test_gpu_reference_dropin.py.
 
 Run: python oracle/build_ref.py     (needs /root/reference; a no-op with a message otherwise)
 """
@@ -69,6 +71,38 @@ def build(force=False):
     return OUT
 
 
+REF_OPS = "/root/reference/mask2former/modeling/pixel_decoder/ops"
+STAGE_DIR = os.path.join(OUT_DIR, "ops_unmodified")
+STAGED = ("test.py", "functions/__init__.py", "functions/ms_deform_attn_func.py", "modules/__init__.py",
+          "modules/ms_deform_attn.py")
+MANIFEST = os.path.join(os.path.dirname(HERE), "tests", "golden", "ref_ops_sha256.json")
+
+
+def stage_ops_py():
+    """Stage the reference's own Python files of the op package — its only test (ops/test.py), its autograd function
+    and its nn.Module — byte for byte into oracle/_ref/ops_unmodified/ops/ (git-ignored, travels to the GPU box), so
+    that tests/test_gpu_reference_dropin.py can run them UNCHANGED on top of this repository's
+    `MultiScaleDeformableAttention` extension ("test.py must run unchanged against the new
+    module").  Nothing is copied into the tracked tree; the committed manifest holds only SHA-256 digests, which the
+    test uses to prove the staged files are the reference's."""
+    import hashlib
+    import json
+    import shutil
+    if not os.path.isdir(REF_OPS):
+        return STAGE_DIR if os.path.isdir(STAGE_DIR) else None
+    digests = {}
+    for rel in STAGED:
+        dst = os.path.join(STAGE_DIR, "ops", rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        shutil.copyfile(os.path.join(REF_OPS, rel), dst)
+        digests[rel] = hashlib.sha256(open(dst, "rb").read()).hexdigest()
+    if not os.path.exists(MANIFEST) or json.load(open(MANIFEST)) != digests:
+        with open(MANIFEST, "w") as f:
+            json.dump(digests, f, indent=1, sort_keys=True)
+            f.write("\n")
+    return STAGE_DIR
+
+
 def load():
     """Import oracle/_ref/msda_reference_cuda (None when it was never built)."""
     import importlib.util
@@ -84,3 +118,4 @@ def load():
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
+    print(stage_ops_py())

@@ -76,7 +76,7 @@ def test_sorted_backward_config_shapes_vs_oracle(cfg, batch, dist, built):
 
 
 def test_sorted_backward_rejects_what_it_does_not_cover(built):
-    inp = W.make_inputs(SMALL_LEVELS, 1, seed=5, n_query=77)          # Lq != S
+    inp = W.make_inputs(SMALL_LEVELS, 1, seed=5, dist="uniform", n_query=77)          # Lq != S
     with pytest.raises(cabi.MSDAError, match="anchor-sorted"):
         run_cabi(inp["value"], inp["shapes"], inp["start"], inp["loc"], inp["attn"], inp["grad_out"],
                  tuning=cabi.make_tuning(bwd=2))
