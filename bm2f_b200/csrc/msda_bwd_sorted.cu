@@ -3,6 +3,7 @@
 // queries are the pixels of the levels (Lq == S, encoder self-attention).
 #include "api_common.cuh"
 #include "msda_bwd_sorted.cuh"
+#include "msda_bwd_pixel.cuh"
 
 #include <atomic>
 
@@ -32,6 +33,24 @@ int launch(const FastParams &p, int marg, const CUtensorMap &ml, const CUtensorM
     return BM2F_OK;
 }
 
+template <int L_, int RMAX, int NWARP, bool FUSED, int CPS, bool F2>
+int launch_pixel(const FastParams &p, int marg, const CUtensorMap &ml, const CUtensorMap &mw, const CUtensorMap &mg, int sms,
+                 long long est_jobs, cudaStream_t st)
+{
+    constexpr int smem = PixelSmem<L_, RMAX, kCells>::kBytes;
+    int rc = ensure_dynamic_smem<&msda_bwd_pixel_kernel<L_, RMAX, NWARP, FUSED, kCells, CPS, F2>>(
+        smem, "cudaFuncSetAttribute(pixel-owner backward smem)");
+    if (rc) return rc;
+    const long long grid_max = static_cast<long long>(sms) * CPS;
+    const int grid = static_cast<int>(est_jobs < grid_max ? est_jobs : grid_max);
+    msda_bwd_pixel_kernel<L_, RMAX, NWARP, FUSED, kCells, CPS, F2>
+        <<<grid, NWARP * 32, smem, st>>>(p, marg, g_prof.load(std::memory_order_relaxed), ml, mw, mg);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "launch msda_bwd_pixel_kernel");
+    count_launch(1);
+    return BM2F_OK;
+}
+
 template <int L_, int RMAX, bool FUSED>
 int pick(const FastParams &p, int marg, int lanes, int variant, const CUtensorMap &ml, const CUtensorMap &mw,
          const CUtensorMap &mg, int sms, long long est_jobs, cudaStream_t st)
@@ -39,6 +58,10 @@ int pick(const FastParams &p, int marg, int lanes, int variant, const CUtensorMa
     // default: two CTAs of 8 warps per SM — while one sits in the short single-threaded / barrier phases the other computes
 #define BM2F_V(NWARP, LPP, CPS, PIPE, R) return launch<L_, R, NWARP, LPP, FUSED, CPS, PIPE>(p, marg, ml, mw, mg, sms, est_jobs, st)
     if constexpr (L_ == 3 && !FUSED) {          // A/B variants (tuning.reserved[0]) for the benchmark shape only
+        if (variant == 6) return launch_pixel<L_, 5, 8, FUSED, 2, false>(p, marg, ml, mw, mg, sms, est_jobs, st);
+        if (variant == 7) return launch_pixel<L_, 8, 16, FUSED, 1, false>(p, marg, ml, mw, mg, sms, est_jobs, st);
+        if (variant == 8) return launch_pixel<L_, 5, 8, FUSED, 2, true>(p, marg, ml, mw, mg, sms, est_jobs, st);
+        if (variant == 9) return launch_pixel<L_, 8, 16, FUSED, 1, true>(p, marg, ml, mw, mg, sms, est_jobs, st);
         switch (variant * 10 + lanes) {
         case 18: BM2F_V(8, 8, 2, true, RMAX);
         case 14: BM2F_V(8, 4, 2, true, RMAX);
@@ -85,7 +108,7 @@ int run_bwd_sorted(FastParams p, const Dims &d, const bm2f_msda_tuning_t &t, boo
         return rc;
     // lower bound on the chunk count (tiles hold at most 32 x RMAX queries); the kernel enumerates the exact tiles
     // from the device-resident shape table
-    const long long est_jobs = static_cast<long long>(d.N) * d.M * ((d.Lq + 32 * 6 - 1) / (32 * 6));
+    const long long est_jobs = static_cast<long long>(d.N) * d.M * ((d.Lq + 32 * 8 - 1) / (32 * 8));
     const int variant = t.reserved[0];
 #define BM2F_SORTED(L_, RMAX)                                                                                         \
     return fused ? pick<L_, RMAX, true>(p, marg, lanes, variant, ml, mw, mg, sms, est_jobs, st)                       \

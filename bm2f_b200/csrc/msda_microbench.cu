@@ -15,6 +15,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #define CK(x)                                                                               \
     do {                                                                                    \
@@ -210,8 +211,59 @@ __global__ void __launch_bounds__(512) smem_red_kernel(int iters, uint32_t *sink
     if (threadIdx.x == 0) sink[blockIdx.x] = acc[blockIdx.x & 1023];
 }
 
-int main()
+// Shared-memory gather: every warp instruction reads four pseudo-random 128-byte rows of a 96 KB shared-memory window
+// with 8 lanes x 16 B each (LDS.128) — the rate a value window staged in shared memory would be read at.
+__global__ void __launch_bounds__(512) smem_gather_kernel(int iters, float *sink)
 {
+    extern __shared__ __align__(128) float win[];
+    constexpr int kRows = 768;
+    for (int i = threadIdx.x; i < kRows * 32; i += blockDim.x) win[i] = 1.0f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, grp = lane >> 3, sub = lane & 7;
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        const uint32_t h = mix((gwarp * 977u + i) * 64u + grp);
+        const uint32_t row = (uint32_t)(((uint64_t)h * kRows) >> 32);
+        const float4 v = *reinterpret_cast<const float4 *>(win + row * 32 + sub * 4);
+        acc += v.x + v.y + v.z + v.w;
+    }
+    if (acc == 123.456f) *sink = acc;
+}
+
+// --quick: the few peaks bench.py divides by, measured on the GPU and in the run that reports them; one JSON line.
+int quick_main()
+{
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    const size_t bytes_buf = 512ull << 20;
+    float *buf, *sink;
+    CK(cudaMalloc(&buf, bytes_buf));
+    CK(cudaMalloc(&sink, 4));
+    CK(cudaMemset(buf, 0, bytes_buf));
+    const int sms = prop.multiProcessorCount, threads = 512, grid = sms * 4, warps = grid * threads / 32;
+    const uint32_t n44 = (uint32_t)(44.0 * 1048576.0 / 128), n352 = (uint32_t)(352.0 * 1048576.0 / 128);
+    const double gl2 = (double)warps * 512 * 4 * 128.0 /
+                       time_ms([&] { gather_kernel<1><<<grid, threads>>>(buf, n44, 512, 0, sink); }, 5) * 1e-6;
+    const double gl1 = (double)(sms * threads / 32) * 4096 * 4 * 128.0 /
+                       time_ms([&] { gather_kernel<1><<<sms, threads>>>(buf, n352, 4096, 768, sink); }, 5) * 1e-6;
+    const double red = (double)warps * 128 * 4 * 128.0 /
+                       time_ms([&] { red_kernel<1><<<grid, threads>>>(buf, n44, 128, 0); }, 5) * 1e-6;
+    CK(cudaFuncSetAttribute(smem_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 768 * 128));
+    const double lds = (double)(sms * 2 * threads / 32) * 4096 * 4 * 128.0 /
+                       time_ms([&] { smem_gather_kernel<<<sms * 2, threads, 768 * 128>>>(4096, sink); }, 5) * 1e-6;
+    const size_t n = bytes_buf / 2;
+    const double copy = 2.0 * n / time_ms([&] { CK(cudaMemcpyAsync(buf, (char *)buf + n, n, cudaMemcpyDeviceToDevice)); }, 5) * 1e-6;
+    printf("{\"device\": \"%s\", \"sms\": %d, \"unit\": \"GB/s of 128-B lines\", \"gather_8x16B_l2_44MB\": %.1f, "
+           "\"gather_8x16B_l1_96KB\": %.1f, \"red_8xv4f32_l2_44MB\": %.1f, \"lds_8x16B_smem_96KB\": %.1f, \"d2d_copy_rw\": %.1f}\n",
+           prop.name, sms, gl2, gl1, red, lds, copy);
+    return 0;
+}
+
+int main(int argc, char **argv)
+{
+    if (argc > 1 && !strcmp(argv[1], "--quick")) return quick_main();
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
     printf("# device %s  SMs %d  L2 %.1f MB  smem/SM %zu KB\n", prop.name, prop.multiProcessorCount,

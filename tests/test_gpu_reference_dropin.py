@@ -55,12 +55,17 @@ def test_reference_test_py_runs_unchanged(staged):
 
 def test_reference_module_on_our_extension_equals_our_module(staged):
     """the reference's MSDeformAttn (its Python, our native op) vs bm2f_b200's MSDeformAttn with the same parameters"""
-    for path in (PKG, staged):
-        if path not in sys.path:
-            sys.path.insert(0, path)
-    import MultiScaleDeformableAttention as MSDA
+    import bm2f_b200
+    MSDA = bm2f_b200.load_extension()          # registers this repository's build as `MultiScaleDeformableAttention`
     assert os.path.dirname(os.path.abspath(MSDA.__file__)) == PKG          # ours, not the reference build
-    from ops.modules import MSDeformAttn as RefModule                       # staged, unmodified
+    # `ops` must resolve to the staged reference package (a namespace package, no __init__.py, like in the reference
+    # tree) and not to bm2f_b200/ops: only the staged directory goes on sys.path
+    assert "ops" not in sys.modules
+    sys.path.insert(0, staged)
+    try:
+        from ops.modules import MSDeformAttn as RefModule                   # staged, unmodified
+    finally:
+        sys.path.remove(staged)
     assert os.path.abspath(sys.modules[RefModule.__module__].__file__).startswith(os.path.abspath(staged))
     from bm2f_b200 import workloads as W
     from bm2f_b200.ops.modules import MSDeformAttn
