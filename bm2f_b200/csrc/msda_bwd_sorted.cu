@@ -4,6 +4,7 @@
 #include "api_common.cuh"
 #include "msda_bwd_sorted.cuh"
 #include "msda_bwd_pixel.cuh"
+#include "msda_bwd_owner.cuh"
 
 #include <atomic>
 
@@ -51,6 +52,24 @@ int launch_pixel(const FastParams &p, int marg, const CUtensorMap &ml, const CUt
     return BM2F_OK;
 }
 
+template <int L_, int RMAX, int NWARP, bool FUSED, int CPS, int CELLS>
+int launch_owner(const FastParams &p, int marg, const CUtensorMap &ml, const CUtensorMap &mw, const CUtensorMap &mg, int sms,
+                 long long est_jobs, cudaStream_t st)
+{
+    constexpr int smem = OwnerSmem<L_, RMAX, CELLS, NWARP>::kBytes;
+    int rc = ensure_dynamic_smem<&msda_bwd_owner_kernel<L_, RMAX, NWARP, FUSED, CELLS, CPS>>(
+        smem, "cudaFuncSetAttribute(owner backward smem)");
+    if (rc) return rc;
+    const long long grid_max = static_cast<long long>(sms) * CPS;
+    const int grid = static_cast<int>(est_jobs < grid_max ? est_jobs : grid_max);
+    msda_bwd_owner_kernel<L_, RMAX, NWARP, FUSED, CELLS, CPS>
+        <<<grid, NWARP * 32, smem, st>>>(p, marg, g_prof.load(std::memory_order_relaxed), ml, mw, mg);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "launch msda_bwd_owner_kernel");
+    count_launch(1);
+    return BM2F_OK;
+}
+
 template <int L_, int RMAX, bool FUSED>
 int pick(const FastParams &p, int marg, int lanes, int variant, const CUtensorMap &ml, const CUtensorMap &mw,
          const CUtensorMap &mg, int sms, long long est_jobs, cudaStream_t st)
@@ -58,6 +77,9 @@ int pick(const FastParams &p, int marg, int lanes, int variant, const CUtensorMa
     // default: two CTAs of 8 warps per SM — while one sits in the short single-threaded / barrier phases the other computes
 #define BM2F_V(NWARP, LPP, CPS, PIPE, R) return launch<L_, R, NWARP, LPP, FUSED, CPS, PIPE>(p, marg, ml, mw, mg, sms, est_jobs, st)
     if constexpr (L_ == 3 && !FUSED) {          // A/B variants (tuning.reserved[0]) for the benchmark shape only
+        if (variant == 10) return launch_owner<L_, 5, 8, FUSED, 2, 4096>(p, marg, ml, mw, mg, sms, est_jobs, st);
+        if (variant == 11) return launch_owner<L_, 4, 8, FUSED, 2, 4096>(p, marg, ml, mw, mg, sms, est_jobs, st);
+        if (variant == 12) return launch_owner<L_, 3, 8, FUSED, 2, 4096>(p, marg, ml, mw, mg, sms, est_jobs, st);
         if (variant == 6) return launch_pixel<L_, 5, 8, FUSED, 2, false>(p, marg, ml, mw, mg, sms, est_jobs, st);
         if (variant == 7) return launch_pixel<L_, 8, 16, FUSED, 1, false>(p, marg, ml, mw, mg, sms, est_jobs, st);
         if (variant == 8) return launch_pixel<L_, 5, 8, FUSED, 2, true>(p, marg, ml, mw, mg, sms, est_jobs, st);
