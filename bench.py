@@ -11,14 +11,21 @@ own input tensors.  Default workload = BASELINE.json configs[1]: COCO panoptic R
   value    images/s, whole job, inputs resident in HBM, device-timed (CUDA events, max over ranks)
   e2e      same metric through the C ABI's host-buffer entry: pinned host inputs copied in and all
            results copied out inside the timed region
-  roofline dominant kernel (backward) against the measured HBM copy peak; the gather-level view
-           (L1/L2 line traffic) is reported next to it under "gather"
-  cpu_baseline / --impl reference: the reference's CPU path (F.grid_sample formulation, restated in
-           oracle/msda_oracle.py:torch_port_forward) on this box's host cores, bounded sample
+  roofline dominant kernel (backward) against the measured HBM copy peak, plus SURVEY §8d's two-level
+           bound max(bytes_hbm / BW_hbm, bytes_gather / BW_L2, bytes_red / BW_red) with the gather / RED
+           peaks measured by bm2f_b200/msda_microbench ON THIS GPU IN THIS RUN (before the timed region)
+  cpu_baseline / --impl reference: the reference's CPU path on this box's host cores, bounded sample
+           (1 image of the batch, all 6 layers per step): the reference's OWN ms_deform_attn_core_pytorch
+           from the byte-identical staged copy oracle/_ref/ops_unmodified (kind "reference") when it
+           travelled with the tree, else the restatement oracle/msda_oracle.py (kind "port")
 
-Multi-GPU (torchrun, one rank per GPU): the batch is per-GPU (weak scaling, images are independent
-— SURVEY.md §8e); the only collective is the NCCL all-reduce of the 4.93 MB projection-weight
-gradient bucket of the training configs, overlapped on a side stream.
+Multi-GPU (torchrun, one rank per GPU): the partition SURVEY.md §8e / BASELINE config 2 name — the
+global batch (16) is split over the ranks, 16/8/4/2 images per GPU ("strong"); --scaling weak keeps
+16 images per GPU.  Images are independent; the only collective is the NCCL all-reduce of the
+4.93 MB projection-weight gradient bucket of the training configs: real gradients of six MSDeformAttn
+modules (bm2f_b200.dist.GradBucket), launched on a side stream and overlapped with the step.  The
+module-level step with one bucket per layer overlapped with the backward of the earlier layers is
+reported next to it under "ddp_module".
 """
 from __future__ import annotations
 
@@ -125,6 +132,58 @@ def profile_facts():
     return {}
 
 
+def measure_gather_peaks(gpu_index: int):
+    """L1 / L2 gather and L2 RED line rates of THIS GPU, measured now by the stand-alone microbenchmark
+    (bm2f_b200/csrc/msda_microbench.cu --quick: 8 lanes x 16 B gathers from a 44 MB / 96 KB footprint,
+    red.global.add.v4.f32 to a 44 MB footprint, device copy).  None when the binary is missing."""
+    exe = os.path.join(ROOT, "bm2f_b200", "msda_microbench")
+    if not os.path.exists(exe):
+        return None
+    env = dict(os.environ)
+    vis = env.get("CUDA_VISIBLE_DEVICES")
+    env["CUDA_VISIBLE_DEVICES"] = vis.split(",")[gpu_index] if vis else str(gpu_index)
+    try:
+        r = subprocess.run([exe, "--quick"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120, env=env)
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+        d = json.loads(line)
+        d["source"] = "this run (bm2f_b200/msda_microbench --quick, same GPU, before the timed region)"
+        return d
+    except Exception as e:  # pragma: no cover
+        log("microbenchmark failed:", repr(e))
+        return None
+
+
+def reference_cpu_function():
+    """(callable, kind).  The reference's own CPU path, ms_deform_attn_core_pytorch
+    (/root/reference/mask2former/modeling/pixel_decoder/ops/functions/ms_deform_attn_func.py:52-72), imported from the
+    byte-identical copy oracle/build_ref.py staged under the git-ignored oracle/_ref/ops_unmodified (it travels to the
+    GPU box; /root/reference does not) -> kind "reference".  Without it: the restatement in oracle/ -> kind "port"."""
+    import importlib
+    import types
+    stage = os.path.join(ROOT, "oracle", "_ref", "ops_unmodified")
+    fn = os.path.join(stage, "ops", "functions", "ms_deform_attn_func.py")
+    if os.path.exists(fn):
+        try:
+            # the file imports the native module at the top and only calls it for CUDA tensors: on the CPU path a
+            # stand-in of that name is enough (and keeps every kernel of this repository out of the reference arm)
+            if "MultiScaleDeformableAttention" not in sys.modules:
+                sys.modules["MultiScaleDeformableAttention"] = types.ModuleType("MultiScaleDeformableAttention")
+            if stage not in sys.path:
+                sys.path.insert(0, stage)
+            mod = importlib.import_module("ops.functions.ms_deform_attn_func")
+            return mod.ms_deform_attn_core_pytorch, "reference"
+        except Exception as e:  # pragma: no cover
+            log("staged reference function not importable:", repr(e))
+    from oracle import msda_oracle as O
+    return (lambda v, sh, loc, aw: O.torch_port_forward(v, sh, loc, aw)), "port"
+
+
+def workload_config(wl, world, nb, scaling):
+    """config keys shared by both arms (the driver compares them)"""
+    return {"workload": wl.name, "cfg": wl.cfg, "levels": wl.levels, "global_batch": nb * world if scaling == "weak" else wl.batch,
+            "layers": wl.n_layers, "heads": 8, "head_dim": 32, "points": 4, "mode": wl.mode, "parallelism": f"dp{world}"}
+
+
 def cpu_model():
     try:
         for line in open("/proc/cpuinfo"):
@@ -135,69 +194,172 @@ def cpu_model():
     return "unknown"
 
 
-def cpu_reference_sample(wl, n_images, n_layers, threads):
-    """Times the reference's CPU path (torch port) on `n_images` x `n_layers` image-layers and
-    returns images/s for the full 6-layer stack, extrapolated linearly (layers are identical work)."""
-    from oracle import msda_oracle as O
+def cpu_reference_step(wl, fn, n_images, threads):
+    """One bounded step of the reference's CPU path: `n_images` images of the batch through all wl.n_layers layers
+    (forward, and backward through autograd where the config trains).  Returns the wall time of the step."""
     torch.set_num_threads(threads)
-    inp = W.make_inputs(wl.levels, n_images, seed=1234 + wl.cfg)
     bwd = wl.mode == "fwd+bwd"
-    dt = torch.float32
-
-    def once():
+    inp = cpu_reference_step.cache.get((wl.cfg, n_images))
+    if inp is None:
+        inp = W.make_inputs(wl.levels, n_images, seed=1234 + wl.cfg)
+        cpu_reference_step.cache[(wl.cfg, n_images)] = inp
+    t0 = time.perf_counter()
+    for _ in range(wl.n_layers):
         if bwd:
-            O.torch_port_forward_backward(inp["value"].to(dt), inp["shapes"], inp["loc"].to(dt), inp["attn"].to(dt),
-                                          inp["grad_out"].to(dt))
+            v, loc, aw = (inp[k].clone().requires_grad_(True) for k in ("value", "loc", "attn"))
+            out = fn(v, inp["shapes"], loc, aw)
+            out.backward(inp["grad_out"])
         else:
             with torch.no_grad():
-                O.torch_port_forward(inp["value"].to(dt), inp["shapes"], inp["loc"].to(dt), inp["attn"].to(dt))
-    once()                                     # warm-up
-    times = []
-    for _ in range(n_layers):
-        t0 = time.perf_counter(); once(); times.append(time.perf_counter() - t0)
-    per_layer = statistics.median(times)
-    return n_images / (per_layer * wl.n_layers), per_layer
+                fn(inp["value"], inp["shapes"], inp["loc"], inp["attn"])
+    return time.perf_counter() - t0
+
+
+cpu_reference_step.cache = {}
+
+
+def cpu_sample_images(wl):
+    return 2 if wl.S < 8000 else 1
 
 
 # --------------------------------------------------------------------------------------------
-# reference arm: CPU only
+# reference arm: the reference's CPU implementation of the path, host cores only
 # --------------------------------------------------------------------------------------------
 def run_reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
-    n_img = 2 if wl.S < 8000 else 1
-    t0 = time.perf_counter()
-    step_times = []
-    per_layer_all = []
-    total = args.warmup + args.steps
-    for i in range(total):
-        ips, per_layer = cpu_reference_sample(wl, n_img, 1, threads)
+    fn, kind = reference_cpu_function()
+    n_img = cpu_sample_images(wl)
+    t_start = time.perf_counter()
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt = cpu_reference_step(wl, fn, n_img, threads)
         if i >= args.warmup:
-            step_times.append(per_layer * wl.n_layers * wl.batch / n_img)    # full-batch 6-layer step, extrapolated
-            per_layer_all.append(per_layer)
-        if time.perf_counter() - t0 > 150:                                   # stay within a few minutes
+            times.append(dt)
+        if time.perf_counter() - t_start > 240 and times:                    # stay within a few minutes
             break
-    per_layer = statistics.median(per_layer_all)
-    ips = n_img / (per_layer * wl.n_layers)
-    sample = (f"{n_img} image(s) x 1 layer {wl.mode} per step, {len(per_layer_all)} timed steps; images/s = "
-              f"images / (median layer time x {wl.n_layers} layers)")
+    step_s = sum(times) / len(times)
+    ips = n_img / step_s
+    sample = (f"each step = {n_img} image(s) of the batch x {wl.n_layers} layers {wl.mode} ({kind}: "
+              f"ms_deform_attn_core_pytorch, F.grid_sample), {threads} torch threads; images/s = {n_img} / step time")
+    cfg = workload_config(wl, world, wl.batch, "strong")
+    cfg.update({"sample_images_per_step": n_img,
+                "note": "the reference has no native CPU kernel: its CPU path is ms_deform_attn_core_pytorch"})
     line = {
         "impl": "reference", "metric": "MSDeformAttn %s images/s" % wl.mode, "value": ips, "unit": "images/s",
-        "n_gpus": args.gpus, "steps": len(per_layer_all), "warmup": args.warmup,
-        "ms_per_step": 1e3 * statistics.median(step_times), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl.name, "cfg": wl.cfg, "levels": wl.levels, "batch": wl.batch, "layers": wl.n_layers,
-                   "mode": wl.mode, "note": "reference CPU path = ms_deform_attn_core_pytorch (F.grid_sample), "
-                                            "restated in oracle/msda_oracle.py; the reference has no native CPU kernel"},
-        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample,
+        "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * step_s,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": cfg,
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": kind, "sample": sample,
                          "cpu": cpu_model()},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+def pin_to_gpu_numa(local: int):
+    """Run this rank (and therefore its pinned allocations, first-touch) on the cores local to its GPU.  Returns a
+    short description for the JSON line; a no-op when sysfs does not say or all GPUs sit on one node."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = open(base + "/numa_node").read().strip()
+        cpus = open(base + "/local_cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                ids.update(range(int(a), int(b) + 1))
+            elif part:
+                ids.add(int(part))
+        ids &= set(os.sched_getaffinity(0))
+        if ids:
+            os.sched_setaffinity(0, ids)
+        return {"pci": bdf, "numa_node": node, "local_cpulist": cpus, "pinned_cpus": len(ids)}
+    except Exception as e:  # pragma: no cover
+        return {"error": repr(e)}
+
+
+def pcie_ceiling(dist, dev, nbytes=1 << 29, reps=4):
+    """Both directions at once, pinned memory, EVERY rank at the same time (the ranks share the host's memory and PCIe
+    root complexes): GB/s each way per GPU = the ceiling of the e2e leg on this box at this N."""
+    h_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def once(n):
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            with torch.cuda.stream(s1):
+                d_in.copy_(h_in, non_blocking=True)
+            with torch.cuda.stream(s2):
+                h_out.copy_(d_out, non_blocking=True)
+        s1.synchronize(); s2.synchronize()
+        return time.perf_counter() - t0
+    once(1)
+    dt = once(reps)
+    if dist:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    return reps * nbytes / dt / 1e9
+
+
+def run_ddp_module(wl, nb, dev, dist, world, modules, buckets, steps):
+    """The training-config step at module level: six MSDeformAttn modules (fused sampling + tcgen05 projections, so the
+    projection-weight gradients exist), forward + backward per layer, and one gradient bucket PER LAYER all-reduced on
+    a side stream as soon as that layer's backward has been launched — it overlaps the backward of the next layer."""
+    from bm2f_b200 import workloads as Wl
+    shapes, start = Wl.level_tensors(wl.levels, dev)
+    g = torch.Generator(device="cpu").manual_seed(99)
+    src = torch.randn(nb, wl.S, 256, generator=g).to(dev)
+    pos = (torch.randn(nb, wl.S, 256, generator=g) * 0.1).to(dev)
+    gout = torch.randn(nb, wl.S, 256, generator=g).to(dev)
+    ref_pts = Wl.reference_points(wl.levels, nb).to(dev)
+    comm = torch.cuda.Stream()
+    q = (src + pos)
+
+    def step():
+        for m, bk in zip(modules, buckets):
+            for prm in bk.params:
+                prm.grad = None
+            qq = q.detach().requires_grad_(True)
+            x = src.detach().requires_grad_(True)
+            y = m(qq, ref_pts, x, shapes, start, None)
+            y.backward(gout)
+            if dist:
+                bk.pack()
+                comm.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(comm):
+                    dist.all_reduce(bk.flat)
+                    bk.flat.mul_(1.0 / world)
+        torch.cuda.current_stream().wait_stream(comm)
+    step(); step()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        step()
+    b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    if dist:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
 
 
 # --------------------------------------------------------------------------------------------
@@ -219,9 +381,11 @@ def run_ours(args, wl):
         dist_mod.init_process_group("nccl", device_id=dev)
         dist = dist_mod
 
+    numa = pin_to_gpu_numa(local)
     import bm2f_b200
     from bm2f_b200 import build as b200_build
     from bm2f_b200 import cabi
+    from bm2f_b200 import dist as b200_dist
     # the native libraries normally travel with the tree; build them if this is a bare checkout
     # (local rank 0 compiles, the other ranks wait for the files)
     if not (os.path.exists(b200_build.LIB) and os.path.exists(b200_build.EXT)):
@@ -240,9 +404,22 @@ def run_ours(args, wl):
         kv = dict(x.split("=") for x in args.tuning.split(","))
         cabi.set_default_tuning(cabi.make_tuning(**{k: int(v) for k, v in kv.items()}))
 
+    # gather / RED peaks of this GPU, measured now (rank 0; the other ranks are idle meanwhile)
+    peaks_run = measure_gather_peaks(local) if rank == 0 else None
+    if dist:
+        dist.barrier()
+
     bwd = wl.mode == "fwd+bwd"
     vdt = torch.bfloat16 if wl.dtype == "bf16" else torch.float32
-    nb = wl.batch                                   # per-GPU batch (weak scaling)
+    scaling = args.scaling or ("strong" if world > 1 else "weak")
+    if scaling == "strong":
+        # rank r owns images [r * N / G, (r + 1) * N / G) of the global batch
+        _, nb = b200_dist.shard_batch(wl.batch, world, rank)
+        if nb == 0:
+            raise SystemExit(f"bench.py: global batch {wl.batch} leaves rank {rank} of {world} without images")
+    else:
+        nb = wl.batch                               # per-GPU batch fixed
+    images_total = wl.batch if scaling == "strong" else nb * world
     step_arg = 128
 
     # ---- inputs: one seeded batch from the CPU generator, one copy per layer (rolled along batch) ----
@@ -261,7 +438,27 @@ def run_ours(args, wl):
         f"{wl.dtype} {wl.mode}")
     in_bytes = sum(t.numel() * t.element_size() for t in layers[0].values())
 
-    grad_bucket = torch.zeros(PROJ_GRAD_ELEMS, device=dev) if (dist and bwd) else None
+    # training configs: the projection-weight gradients of six MSDeformAttn modules (real values: one small
+    # forward + backward through the module path fills them), one flat DDP-style bucket
+    modules, grad_bucket, layer_buckets = None, None, None
+    if bwd and wl.dtype == "f32" and (dist or args.ddp_module):
+        from bm2f_b200.ops.modules import MSDeformAttn
+        torch.manual_seed(7 + rank)
+        modules = [MSDeformAttn(256, wl.L, 8, 4).to(dev) for _ in range(wl.n_layers)]
+        sm_levels = ((4, 4), (8, 8), (16, 16))[:wl.L] if wl.L <= 3 else tuple((2 << i, 2 << i) for i in range(wl.L))
+        sh_s, st_s = W.level_tensors(sm_levels, dev)
+        S_s = sum(h * w for h, w in sm_levels)
+        for m in modules:
+            with torch.no_grad():
+                m.sampling_offsets.weight.normal_(0, 0.01)
+                m.attention_weights.weight.normal_(0, 0.05)
+            xs = torch.randn(1, S_s, 256, device=dev, requires_grad=True)
+            m(xs, W.reference_points(sm_levels, 1).to(dev), xs, sh_s, st_s, None).sum().backward()
+        bucket_obj = b200_dist.GradBucket(b200_dist.projection_parameters(modules))
+        assert bucket_obj.numel == PROJ_GRAD_ELEMS or wl.L != 3
+        bucket_obj.pack()
+        grad_bucket = bucket_obj.flat if dist else None
+        layer_buckets = [b200_dist.GradBucket(b200_dist.projection_parameters([m])) for m in modules]
     comm_stream = torch.cuda.Stream() if grad_bucket is not None else None
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -359,7 +556,6 @@ def run_ours(args, wl):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
     ms_per_step = elapsed_ms / args.steps
-    images_total = nb * world
     value = images_total / (ms_per_step * 1e-3)
 
     kms = {k: statistics.mean(a.elapsed_time(b) for a, b in v) for k, v in kernel_events.items() if v}
@@ -368,10 +564,32 @@ def run_ours(args, wl):
     e2e = None
     if not args.no_e2e:
         try:
-            e2e = run_e2e(cabi, wl, base, nb, bwd, min(args.steps, 3), dist, world)
+            e2e = run_e2e(cabi, wl, base, nb, images_total, bwd, min(args.steps, 3), dist, world)
         except Exception as e:  # pragma: no cover
             log("e2e leg failed:", repr(e))
             e2e = {"value": None, "unit": "images/s", "error": repr(e)}
+
+    if e2e and e2e.get("value"):
+        try:
+            ceil_gbs = pcie_ceiling(dist, dev)
+            e2e["pcie_ceiling_GBs_each_way_per_gpu"] = ceil_gbs
+            e2e["frac_of_pcie_ceiling"] = e2e["pcie_GBs_each_way"] / ceil_gbs
+            e2e["pcie_ceiling_source"] = f"this run: {world} rank(s) copying both ways at once, pinned memory"
+            e2e["numa"] = numa
+        except Exception as e:  # pragma: no cover
+            log("pcie ceiling probe failed:", repr(e))
+
+    ddp_module = None
+    if modules is not None and (dist or args.ddp_module):
+        try:
+            ms_mod = run_ddp_module(wl, nb, dev, dist, world, modules, layer_buckets, max(2, min(args.steps, 5)))
+            ddp_module = {"value": images_total / (ms_mod * 1e-3), "unit": "images/s", "ms_per_step": ms_mod,
+                          "what": "six MSDeformAttn modules fwd+bwd (fused sampling kernels + tcgen05 projections), one "
+                                  "gradient bucket per layer all-reduced on a side stream while the next layer runs"
+                                  if dist else "six MSDeformAttn modules fwd+bwd (no collective at N = 1)"}
+        except Exception as e:  # pragma: no cover
+            log("ddp_module leg failed:", repr(e))
+            ddp_module = {"error": repr(e)}
 
     if rank != 0:
         if dist:
@@ -385,37 +603,43 @@ def run_ours(args, wl):
     dom = "bwd" if bwd else "fwd"
     alg_bytes = W.hbm_bytes(wl.S, dom, wl.dtype) * nb          # per launch (SURVEY §8d per image-layer x images)
     achieved = alg_bytes / (kms[dom] * 1e-3) / 1e9
+    traffic = facts.get("dram_bytes_per_launch", {}).get(f"cfg{wl.cfg}_{dom}") if nb == wl.batch else None
     roofline = {"bound": "hbm", "kernel": "msda_%s_fast_kernel (+grad_value zero-fill)" % dom if bwd else "msda_fwd_fast_kernel",
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": facts.get("dram_bytes_per_launch", {}).get(f"cfg{wl.cfg}_{dom}"),
-                "peak_source": peak_src, "ms_per_launch": kms[dom],
+                "traffic": traffic, "peak_source": peak_src, "ms_per_launch": kms[dom],
                 "algorithmic_bytes_per_launch": alg_bytes}
     gather = {}
     for k in kms:
         gb = W.gather_bytes(wl.S, k, wl.dtype) * nb
         gather[k] = {"ms_per_launch": kms[k], "line_traffic_GBs": gb / (kms[k] * 1e-3) / 1e9,
                      "hbm_GBs": W.hbm_bytes(wl.S, k, wl.dtype) * nb / (kms[k] * 1e-3) / 1e9}
-    peaks_g = facts.get("gather_peaks") or {}
-    gather["measured_peaks"] = peaks_g or None
-    if peaks_g:
-        # forward: gathered 128-B lines vs the measured L1 line rate of the same access shape (8 lanes x 16 B);
-        # backward: RED lines vs the measured red.global.add.v4.f32 rate (L2-side limit)
+    gather["measured_peaks"] = peaks_run
+    if peaks_run:
+        # SURVEY §8d's two-level bound, every peak measured on this GPU in this run: the op cannot run faster than
+        # its compulsory HBM bytes at the HBM rate, its gathered corner lines at the L2 gather rate of the same
+        # access shape (8 lanes x 16 B), and — backward, as long as every corner is one L2 reduction — its RED lines
+        # at the red.global.add.v4.f32 rate
+        l2g, l1g, red = (peaks_run["gather_8x16B_l2_44MB"], peaks_run["gather_8x16B_l1_96KB"],
+                         peaks_run["red_8xv4f32_l2_44MB"])
+        corner_bytes = W.gather_bytes(wl.S, "fwd", wl.dtype) * nb         # 48 lines per (query, head), once
+        terms = {"hbm": alg_bytes / (peaks["hbm_gbs"] * 1e9) * 1e3, "l2_gather": corner_bytes / (l2g * 1e9) * 1e3}
+        if dom == "bwd":
+            terms["l2_red_per_corner"] = corner_bytes / (red * 1e9) * 1e3
+        lb = max(terms.values())
+        roofline["lower_bound_ms"] = lb
+        roofline["lower_bound_terms_ms"] = terms
+        roofline["lower_bound_binding"] = max(terms, key=terms.get)
+        roofline["frac_of_lower_bound"] = lb / kms[dom]
+        roofline["lower_bound_peaks"] = {"hbm_GBs": peaks["hbm_gbs"], "hbm_source": peak_src, "l2_gather_8x16B_GBs": l2g,
+                                         "l1_gather_8x16B_GBs": l1g, "l2_red_v4f32_GBs": red,
+                                         "gather_red_source": peaks_run["source"]}
         if "fwd" in gather:
-            gather["fwd"]["frac_of_measured_l1_gather_peak"] = gather["fwd"]["line_traffic_GBs"] / peaks_g["l1_resident_8x16B"]
+            gather["fwd"]["frac_of_l1_gather_peak_this_run"] = gather["fwd"]["line_traffic_GBs"] / l1g
+            gather["fwd"]["frac_of_l2_gather_peak_this_run"] = gather["fwd"]["line_traffic_GBs"] / l2g
         if "bwd" in gather:
-            red_gbs = W.gather_bytes(wl.S, "fwd", wl.dtype) * nb / (kms["bwd"] * 1e-3) / 1e9
+            red_gbs = corner_bytes / (kms["bwd"] * 1e-3) / 1e9
             gather["bwd"]["red_line_traffic_GBs"] = red_gbs
-            gather["bwd"]["frac_of_measured_red_peak"] = red_gbs / peaks_g["red_v4_l2_resident"]
-        # the HBM roofline is not the binding one for this op (gather/scatter demand is 15x the compulsory HBM
-        # bytes): name the limit that binds the dominant kernel and the fraction reached
-        if dom == "bwd" and "bwd" in gather:
-            roofline["binding_limit"] = ("L2 red.global.add.v4.f32 line rate, measured %.0f GB/s "
-                                         "(profiles/r01_microbench.txt)" % peaks_g["red_v4_l2_resident"])
-            roofline["frac_of_binding_limit"] = gather["bwd"]["frac_of_measured_red_peak"]
-        elif "fwd" in gather:
-            roofline["binding_limit"] = ("L1 gather line rate of the 8 lanes x 16 B access shape, measured %.0f GB/s "
-                                         "(profiles/r01_microbench.txt)" % peaks_g["l1_resident_8x16B"])
-            roofline["frac_of_binding_limit"] = gather["fwd"]["frac_of_measured_l1_gather_peak"]
+            gather["bwd"]["frac_of_red_peak_this_run"] = red_gbs / red
 
     # ---- reference CUDA op, same inputs, same timing (only when oracle/_ref was built) ----------------
     ref_cuda = None
@@ -447,31 +671,33 @@ def run_ours(args, wl):
                                 "/root/reference in place (oracle/build_ref.py), same inputs, 1 GPU",
                         "speedup_ours": ref_ms / ms_per_step if world == 1 else None}
 
-    # ---- CPU baseline (rank 0, N=1 only) --------------------------------------------------------------------
+    # ---- CPU baseline (rank 0, N=1 only): same bounded step as --impl reference ---------------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        n_img = 2 if wl.S < 8000 else 1
-        reps = 5
-        ips, per_layer = cpu_reference_sample(wl, n_img, reps, threads)
-        cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "cpu": cpu_model(),
-               "sample": f"{n_img} image(s) x 1 layer {wl.mode}, median of {reps} (1 warm-up); layer time "
-                         f"{per_layer * 1e3:.0f} ms x {wl.n_layers} layers; torch {torch.__version__} "
-                         f"{torch.get_num_threads()} threads"}
+        fn, kind = reference_cpu_function()
+        n_img = cpu_sample_images(wl)
+        cpu_reference_step(wl, fn, n_img, threads)                      # warm-up
+        ts = [cpu_reference_step(wl, fn, n_img, threads) for _ in range(3)]
+        step_s = statistics.median(ts)
+        cpu = {"value": n_img / step_s, "unit": "images/s", "cores": threads, "kind": kind, "cpu": cpu_model(),
+               "sample": f"{n_img} image(s) of the batch x {wl.n_layers} layers {wl.mode} per step, median of 3 steps "
+                         f"(1 warm-up), step {step_s * 1e3:.0f} ms; torch {torch.__version__} {torch.get_num_threads()} threads"}
 
+    cfg = workload_config(wl, world, nb, scaling)
+    cfg.update({"batch_per_gpu": nb,
+                "l2_policy": f"inputs larger than L2: {in_bytes / 1e6:.0f} MB of inputs per layer, 6 distinct "
+                             "layer input sets, no flush needed",
+                "collective": ("all-reduce of the 4.93 MB projection-gradient bucket per step (real gradients of six "
+                               "MSDeformAttn modules), side stream") if grad_bucket is not None else "none",
+                "tuning": args.tuning or "default", "cuda_graph": graph is not None})
     line = {
         "metric": "MSDeformAttn %s images/s" % wl.mode, "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
-        "config": {"workload": wl.name, "cfg": wl.cfg, "levels": wl.levels, "batch_per_gpu": nb,
-                   "global_batch": images_total, "layers": wl.n_layers, "heads": 8, "head_dim": 32, "points": 4,
-                   "mode": wl.mode, "parallelism": f"dp{world}",
-                   "l2_policy": f"inputs larger than L2: {in_bytes / 1e6:.0f} MB of inputs per layer, 6 distinct "
-                                "layer input sets, no flush needed",
-                   "collective": "all-reduce of 4.93 MB projection-gradient bucket per step" if grad_bucket is not None else "none",
-                   "tuning": args.tuning or "default", "cuda_graph": graph is not None},
+        "scaling": scaling, "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
+        "config": cfg,
         "roofline": roofline, "gather": gather, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-        "clocks": clocks, "reference_cuda": ref_cuda,
+        "clocks": clocks, "reference_cuda": ref_cuda, "ddp_module": ddp_module,
     }
     print(json.dumps(line), flush=True)
     if dist:
@@ -480,7 +706,7 @@ def run_ours(args, wl):
     return 0
 
 
-def run_e2e(cabi, wl, base, nb, bwd, steps, dist, world):
+def run_e2e(cabi, wl, base, nb, images_total, bwd, steps, dist, world):
     """Same step through bm2f_msda_forward_backward_host: pinned host tensors in, results out."""
     code = cabi.DTYPE_BF16 if wl.dtype == "bf16" else cabi.DTYPE_F32
     vdt = torch.bfloat16 if wl.dtype == "bf16" else torch.float32
@@ -513,7 +739,7 @@ def run_e2e(cabi, wl, base, nb, bwd, steps, dist, world):
     nbytes = lambda *ts: sum(t.numel() * t.element_size() for t in ts if t is not None)
     h2d = wl.n_layers * nbytes(hv, hl, ha, hg)
     d2h = wl.n_layers * nbytes(ho, hgv, hgl, hga)
-    return {"value": nb * world / (dt / steps), "unit": "images/s", "h2d_bytes_per_step": h2d,
+    return {"value": images_total / (dt / steps), "unit": "images/s", "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * dt / steps, "steps": steps,
             "path": "bm2f_msda_forward_backward_host (C ABI), pinned host buffers, chunked copies pipelined over three slots",
             "pcie_GBs_each_way": max(h2d, d2h) / (dt / steps) / 1e9}
@@ -531,6 +757,11 @@ def main():
     ap.add_argument("--graph", action="store_true",
                     help="replay one step (all layers, fwd+bwd) from a CUDA graph in the timed loop: for launch-bound "
                          "configs (cfg 1: one 512^2 image, 35 us of launch overhead per layer)")
+    ap.add_argument("--scaling", default="", choices=["", "strong", "weak"],
+                    help="N > 1: strong (default) splits the config's global batch over the ranks (SURVEY section 8e: "
+                         "16/8/4/2 images per GPU); weak keeps the config's batch on every GPU")
+    ap.add_argument("--ddp-module", action="store_true",
+                    help="also time the module-level step (six MSDeformAttn modules, per-layer gradient buckets) at N = 1")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")

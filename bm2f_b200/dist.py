@@ -21,6 +21,13 @@ def shard_batch(total: int, world: int, rank: int) -> Tuple[int, int]:
     return first, count
 
 
+def trainable_parameters(module: torch.nn.Module) -> List[torch.nn.Parameter]:
+    """EVERY parameter of an encoder / pixel decoder that takes a gradient, in registration order: what a data-parallel
+    training step has to exchange when the whole mirror (FFN, LayerNorm, level_embed, input_proj, FPN convolutions) is
+    trained, not only the four MSDeformAttn projections (use with GradBucket, or wrap the module in DDP)."""
+    return [p for p in module.parameters() if p.requires_grad]
+
+
 def projection_parameters(modules: Iterable[torch.nn.Module]) -> List[torch.nn.Parameter]:
     """Parameters of the hot path that need gradient exchange, in a deterministic order:
     for every MSDeformAttn-like module its sampling_offsets, attention_weights, value_proj and
@@ -34,8 +41,10 @@ def projection_parameters(modules: Iterable[torch.nn.Module]) -> List[torch.nn.P
 
 
 class GradBucket:
-    """One flat fp32 bucket for the projection gradients; all_reduce(sum) then scale by 1/world
-    (DDP semantics).  `stream` lets the caller overlap the collective with remaining backward work."""
+    """One flat fp32 bucket for a list of parameters' gradients; all_reduce(sum) then scale by 1/world (DDP semantics).
+    With `projection_parameters` it is the hot path's own exchange (bench.py); a training loop that updates the rest of
+    the encoder / decoder mirror must bucket `trainable_parameters(model)` instead, or those gradients are never
+    reduced.  pack() / flat / unpack() are separate so that the caller can run the collective on a side stream."""
 
     def __init__(self, params: List[torch.nn.Parameter], group=None):
         self.params = params
@@ -43,23 +52,23 @@ class GradBucket:
         self.numel = sum(p.numel() for p in params)
         dev = params[0].device if params else torch.device("cpu")
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        self.views, off = [], 0
+        for p in params:                                   # the bucket seen through the parameters' shapes
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
 
     def pack(self):
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            g = p.grad if p.grad is not None else torch.zeros_like(p)
-            self.flat[off:off + n].copy_(g.reshape(-1))
-            off += n
+        """gradients -> bucket: one multi-tensor copy (a handful of launches, not one per parameter)"""
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
+        if grads:
+            torch._foreach_copy_(self.views, grads)
 
     def unpack(self):
-        off = 0
         for p in self.params:
-            n = p.numel()
             if p.grad is None:
                 p.grad = torch.empty_like(p)
-            p.grad.copy_(self.flat[off:off + n].view_as(p))
-            off += n
+        if self.params:
+            torch._foreach_copy_([p.grad for p in self.params], self.views)
 
     def all_reduce(self):
         import torch.distributed as dist

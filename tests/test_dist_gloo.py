@@ -93,5 +93,13 @@ def test_reference_arm_under_torchrun_only_rank0_works():
     assert len(lines) == 1
     import json
     d = json.loads(lines[0])
-    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    staged = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ops_unmodified", "ops", "functions", "ms_deform_attn_func.py"))
+    assert d["impl"] == "reference" and d["value"] > 0
+    # the reference's own function when its byte-identical copy travelled with the tree, the restatement otherwise
+    assert d["cpu_baseline"]["kind"] == ("reference" if staged else "port")
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["n_gpus"] == 2
+    # a real, bounded step: value = sample images / measured step time, and the step list fits the run
+    n = d["config"]["sample_images_per_step"]
+    assert abs(d["value"] - n / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
+    for k in ("workload", "cfg", "levels", "global_batch", "layers", "heads", "head_dim", "points", "mode", "parallelism"):
+        assert k in d["config"], k
