@@ -604,7 +604,9 @@ def run_ours(args, wl):
     alg_bytes = W.hbm_bytes(wl.S, dom, wl.dtype) * nb          # per launch (SURVEY §8d per image-layer x images)
     achieved = alg_bytes / (kms[dom] * 1e-3) / 1e9
     traffic = facts.get("dram_bytes_per_launch", {}).get(f"cfg{wl.cfg}_{dom}") if nb == wl.batch else None
-    roofline = {"bound": "hbm", "kernel": "msda_%s_fast_kernel (+grad_value zero-fill)" % dom if bwd else "msda_fwd_fast_kernel",
+    sorted_bwd = (bwd and wl.dtype == "f32" and nb * wl.S >= 65536 and "bwd=" not in (args.tuning or ""))   # msda_api.cu:choose_bwd_sorted
+    kname = ("msda_bwd_sorted_kernel" if sorted_bwd else "msda_bwd_fast_kernel") + " (+grad_value zero-fill)" if bwd else "msda_fwd_fast_kernel"
+    roofline = {"bound": "hbm", "kernel": kname,
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                 "traffic": traffic, "peak_source": peak_src, "ms_per_launch": kms[dom],
                 "algorithmic_bytes_per_launch": alg_bytes}
@@ -623,13 +625,16 @@ def run_ours(args, wl):
                          peaks_run["red_8xv4f32_l2_44MB"])
         corner_bytes = W.gather_bytes(wl.S, "fwd", wl.dtype) * nb         # 48 lines per (query, head), once
         terms = {"hbm": alg_bytes / (peaks["hbm_gbs"] * 1e9) * 1e3, "l2_gather": corner_bytes / (l2g * 1e9) * 1e3}
-        if dom == "bwd":
-            terms["l2_red_per_corner"] = corner_bytes / (red * 1e9) * 1e3
         lb = max(terms.values())
         roofline["lower_bound_ms"] = lb
         roofline["lower_bound_terms_ms"] = terms
         roofline["lower_bound_binding"] = max(terms, key=terms.get)
         roofline["frac_of_lower_bound"] = lb / kms[dom]
+        if dom == "bwd":
+            # not a bound of the op, a limit of every kernel that sends each bilinear corner to L2 as its own
+            # reduction (the per-corner kernel sits on it; the anchor-sorted kernel merges corners that share an anchor,
+            # the pixel-owner kernel escapes it and is issue-bound instead: profiles/README.md)
+            roofline["one_red_per_corner_limit_ms"] = corner_bytes / (red * 1e9) * 1e3
         roofline["lower_bound_peaks"] = {"hbm_GBs": peaks["hbm_gbs"], "hbm_source": peak_src, "l2_gather_8x16B_GBs": l2g,
                                          "l1_gather_8x16B_GBs": l1g, "l2_red_v4f32_GBs": red,
                                          "gather_red_source": peaks_run["source"]}

@@ -15,7 +15,7 @@
 #include "msda_generic.cuh"
 
 #ifndef BM2F_BWD_SORTED_DEFAULT
-#define BM2F_BWD_SORTED_DEFAULT 0     // flipped once the kernel is measured faster on the B200
+#define BM2F_BWD_SORTED_DEFAULT 1     // anchor-sorted backward for large encoder shapes (8 % faster at cfg 2, profiles/r02_*)
 #endif
 
 namespace bm2f {
@@ -38,7 +38,10 @@ int choose_bwd_sorted(const Dims &d, int dtype, const bm2f_msda_tuning_t &t, boo
     if (t.bwd == 2 && !ok)
         return fail(BM2F_ERR_UNSUPPORTED, "anchor-sorted backward needs float32, D=32, M=8, P=4, L<=4, num_query == spatial_size "
                     "and order == 0 (got D=%d M=%d P=%d L=%d Lq=%d S=%d dtype=%d)", d.D, d.M, d.P, d.L, d.Lq, d.S, dtype);
-    *sorted = ok && t.bwd != 1 && (t.bwd == 2 || BM2F_BWD_SORTED_DEFAULT);
+    // default: only where it was measured faster — enough (image, query) rows to fill the machine with whole chunks
+    // (a single 512^2 image is launch / tail bound and stays on the per-corner kernel)
+    const bool big = static_cast<long long>(d.N) * d.Lq >= 65536;
+    *sorted = ok && t.bwd != 1 && (t.bwd == 2 || (BM2F_BWD_SORTED_DEFAULT && big));
     return BM2F_OK;
 }
 

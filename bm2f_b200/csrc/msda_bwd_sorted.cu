@@ -118,7 +118,7 @@ int run_bwd_sorted(FastParams p, const Dims &d, const bm2f_msda_tuning_t &t, boo
     if (cc < 10) return fail(BM2F_ERR_CUDA, "this library contains sm_100a code only; device has cc %d.x", cc);
     const int marg = t.bwd_margin > 0 ? t.bwd_margin : 6;
     if (marg > 64) return fail(BM2F_ERR_INVALID, "bwd_margin %d out of range (1..64)", marg);
-    const int lanes = t.bwd_lanes == 4 ? 4 : 8;
+    const int lanes = t.bwd_lanes == 8 ? 8 : 4;       // 4 lanes x 8 channels per point measured faster (2.53 vs 2.92 ms, cfg 2)
     p.order = t.order;
     p.rows = 0;
     const int LP = d.L * d.P;

@@ -443,21 +443,34 @@ msda_bwd_sorted_kernel(const FastParams p, const int marg, long long *prof_out, 
                     c = (static_cast<uint32_t>(cell) << 16) | rank;
                     rec = make_float4(a, f.lh, f.lw, __int_as_float((pix + W[l] + 1) | (mask << 24) | (l << 28)));
                 }
-                // points outside the window: this warp processes them now, one corner line (32 channels) at a time
+                // points outside the window: this warp processes them now, FOUR at a time — lane group g (8 lanes x 4
+                // channels, the per-corner kernel's shape: 128-bit gathers, vector REDs, 3-step shuffle reductions)
+                // takes the g-th pending point; the group's first lane writes the point's final record
                 unsigned fb = __ballot_sync(0xffffffffu, live && !inside);
+                const bool mine_fallback = live && !inside;
                 if (fb) {
                     if (!go_ready) { mbar_wait(&bar_go, phase); go_ready = true; }
-                    float ga = 0.f, gx = 0.f, gy = 0.f;
+                    const int lg4 = lane >> 3, sub4 = lane & 7;
                     while (fb) {
-                        const int src = __ffs(fb) - 1;
-                        fb &= fb - 1;
-                        const float a_ = __shfl_sync(0xffffffffu, a, src);
-                        const float lh = __shfl_sync(0xffffffffu, f.lh, src), lw = __shfl_sync(0xffffffffu, f.lw, src);
-                        const int pix_ = __shfl_sync(0xffffffffu, pix, src);
-                        const int mask_ = __shfl_sync(0xffffffffu, mask, src);
-                        const int qi_ = __shfl_sync(0xffffffffu, qi, src);
+                        // the lg4-th set bit of fb (or none)
+                        unsigned rest = fb;
+                        int src = -1;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const int bpos = rest ? __ffs(rest) - 1 : -1;
+                            if (g == lg4) src = bpos;
+                            rest &= rest - 1;
+                        }
+                        fb = rest;
+                        const int s_ = src < 0 ? 0 : src;
+                        const float a_ = __shfl_sync(0xffffffffu, a, s_);
+                        const float lh = __shfl_sync(0xffffffffu, f.lh, s_), lw = __shfl_sync(0xffffffffu, f.lw, s_);
+                        const int pix_ = __shfl_sync(0xffffffffu, pix, s_);
+                        const int mask_all = __shfl_sync(0xffffffffu, mask, s_);
+                        const int mask_ = src < 0 ? 0 : mask_all;
+                        const int pt_ = __shfl_sync(0xffffffffu, pt, s_);
                         const float hh = 1.f - lh, hw = 1.f - lw;
-                        const float g = s_go[qi_ * D + lane];
+                        const float4 g4 = *reinterpret_cast<const float4 *>(s_go + (pt_ / LP) * D + sub4 * 4);
                         const float cw[4] = {hh * hw, hh * lw, lh * hw, lh * lw};
                         const int poff[4] = {0, 1, W[l], W[l] + 1};
                         float t[4];
@@ -465,26 +478,27 @@ msda_bwd_sorted_kernel(const FastParams p, const int marg, long long *prof_out, 
                         for (int k = 0; k < 4; ++k) {
                             t[k] = 0.f;
                             if ((mask_ >> k) & 1) {
-                                const long long e = static_cast<long long>(pix_ + poff[k]) * MD + lane;
-                                t[k] = g * __ldg(vbm + e);
-                                const float rv[1] = {a_ * cw[k] * g};
-                                VecIO<float, 1>::red_add(gbm + e, rv);
+                                const long long e = static_cast<long long>(pix_ + poff[k]) * MD + sub4 * 4;
+                                const float4 v4 = __ldg(reinterpret_cast<const float4 *>(vbm + e));
+                                t[k] = (g4.x * v4.x + g4.y * v4.y) + (g4.z * v4.z + g4.w * v4.w);
+                                const float wk = a_ * cw[k];
+                                const float rv[4] = {wk * g4.x, wk * g4.y, wk * g4.z, wk * g4.w};
+                                VecIO<float, 4>::red_add(gbm + e, rv);
                             }
                         }
                         float pa = hh * (hw * t[0] + lw * t[1]) + lh * (hw * t[2] + lw * t[3]);
                         float px = hh * (t[1] - t[0]) + lh * (t[3] - t[2]);
                         float py = hw * (t[2] - t[0]) + lw * (t[3] - t[1]);
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
+                        for (int o = 4; o > 0; o >>= 1) {
                             pa += __shfl_xor_sync(0xffffffffu, pa, o);
                             px += __shfl_xor_sync(0xffffffffu, px, o);
                             py += __shfl_xor_sync(0xffffffffu, py, o);
                         }
-                        if (lane == src) { ga = pa; gx = a_ * px; gy = a_ * py; }
+                        if (src >= 0 && sub4 == 0) s_rec[pt_] = make_float4(pa, a_ * px, a_ * py, a_);
                     }
-                    if (live && !inside) rec = make_float4(ga, gx, gy, a);
                 }
-                s_rec[pt] = rec;
+                if (!mine_fallback) s_rec[pt] = rec;
                 cr[l * ITERS + it] = c;
             }
         }

@@ -85,12 +85,13 @@ typedef struct {
     int geo;        /* forward A/B variants (same results): 1 = geometry warps (per-point footprints
                        computed once, 32-byte records in shared memory; with ctas_per_sm = 2: two CTAs per SM),
                        3 = geometry warps + 256-bit gathers (L = 3); 0 / 2 = default kernel                   */
-    int bwd;        /* backward kernel: 0 = default (anchor-sorted when it applies: float32, D = 32, M = 8, P = 4, L <= 4,
-                       num_query == spatial_size, order == 0; per-corner otherwise), 1 = per-corner vector REDs
-                       (msda_bwd_fast_kernel, round 1), 2 = anchor-sorted, error if it does not apply */
+    int bwd;        /* backward kernel: 0 = default (anchor-sorted when it applies — float32, D = 32, M = 8, P = 4, L <= 4,
+                       num_query == spatial_size, order == 0 — and batch * num_query >= 65536; per-corner otherwise),
+                       1 = per-corner vector REDs (msda_bwd_fast_kernel), 2 = anchor-sorted, error if it does not apply
+                        */
     int bwd_margin; /* anchor-sorted backward: window margin around a query tile in pixels of the sampled level; points
                        further out take the slow per-corner path inside the kernel.  0 = default (6)                  */
-    int bwd_lanes;  /* anchor-sorted backward: lanes per sampling point, 8 (x 4 channels, default) or 4 (x 8 channels)  */
+    int bwd_lanes;  /* anchor-sorted backward: lanes per sampling point, 4 (x 8 channels, default) or 8 (x 4 channels)  */
     int reserved[4]; /* reserved[0]: anchor-sorted backward A/B variant for L = 3 (msda_bwd_sorted.cu: pick) */
 } bm2f_msda_tuning_t;
 
