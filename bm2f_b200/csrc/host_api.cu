@@ -14,36 +14,56 @@ extern "C" {
 // ---------------------------------------------------------------------------------------------
 namespace {
 constexpr int kHostSlots = 3;   // chunks in flight: one uploading, one computing / downloading, one draining
+constexpr int kMaxDevices = 64;
+// One state per device ordinal, each behind its own lock: two host threads driving two GPUs do not serialise, and
+// nothing of one device is ever freed or re-created because another device called in.
 struct HostPath {
     std::mutex mu;
-    int dev = -1;
+    bool live = false;
     cudaStream_t streams[kHostSlots] = {};
     void *ws[kHostSlots] = {};
     size_t ws_bytes = 0;
     int64_t *tabs = nullptr;  // shapes (2L) + start (L)
-} g_host;
+} g_host[kMaxDevices];
 
 size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+// current device must be the state's device; the state's lock is held by the caller
+void release_locked(HostPath &h)
+{
+    for (int i = 0; i < kHostSlots; ++i) {
+        if (h.streams[i]) { cudaStreamSynchronize(h.streams[i]); cudaStreamDestroy(h.streams[i]); }
+        if (h.ws[i]) cudaFree(h.ws[i]);
+        h.streams[i] = nullptr;
+        h.ws[i] = nullptr;
+    }
+    if (h.tabs) cudaFree(h.tabs);
+    h.tabs = nullptr;
+    h.ws_bytes = 0;
+    h.live = false;
+}
+
+// asynchronous copies into / out of caller-owned host buffers must not outlive an error return
+int drain_and_return(HostPath &h, int rc)
+{
+    for (int i = 0; i < kHostSlots; ++i)
+        if (h.streams[i]) cudaStreamSynchronize(h.streams[i]);
+    return rc;
+}
 }  // namespace
 
 int bm2f_msda_release_host_workspace(void)
 {
-    std::lock_guard<std::mutex> lk(g_host.mu);
-    if (g_host.dev < 0) return BM2F_OK;
     int cur = 0;
     cudaError_t e = cudaGetDevice(&cur);
     if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
-    if ((e = cudaSetDevice(g_host.dev)) != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    for (int i = 0; i < kHostSlots; ++i) {
-        if (g_host.streams[i]) { cudaStreamSynchronize(g_host.streams[i]); cudaStreamDestroy(g_host.streams[i]); }
-        if (g_host.ws[i]) cudaFree(g_host.ws[i]);
-        g_host.streams[i] = nullptr;
-        g_host.ws[i] = nullptr;
+    for (int dev = 0; dev < kMaxDevices; ++dev) {
+        HostPath &h = g_host[dev];
+        std::lock_guard<std::mutex> lk(h.mu);
+        if (!h.live) continue;
+        if ((e = cudaSetDevice(dev)) != cudaSuccess) { cudaSetDevice(cur); return cuda_fail(e, "cudaSetDevice"); }
+        release_locked(h);
     }
-    if (g_host.tabs) cudaFree(g_host.tabs);
-    g_host.tabs = nullptr;
-    g_host.ws_bytes = 0;
-    g_host.dev = -1;
     cudaSetDevice(cur);
     return BM2F_OK;
 }
@@ -76,40 +96,37 @@ int bm2f_msda_forward_backward_host(const void *value_host, const int64_t *spati
                                (bwd ? align256(o_img) + align256(gv_img) + align256(l_img) + align256(a_img) : 0)) +
                               4096;
 
-    std::lock_guard<std::mutex> lk(g_host.mu);
     int dev = 0;
     cudaError_t ce = cudaGetDevice(&dev);
     if (ce != cudaSuccess) return cuda_fail(ce, "cudaGetDevice");
-    if (g_host.dev != dev || g_host.ws_bytes < slot_bytes) {
+    if (dev < 0 || dev >= kMaxDevices) return fail(BM2F_ERR_UNSUPPORTED, "device ordinal %d >= %d", dev, kMaxDevices);
+    HostPath &h = g_host[dev];
+    std::lock_guard<std::mutex> lk(h.mu);
+    if (!h.live || h.ws_bytes < slot_bytes) {
         for (int i = 0; i < kHostSlots; ++i) {
-            if (g_host.ws[i]) cudaFree(g_host.ws[i]);
-            g_host.ws[i] = nullptr;
-            if (!g_host.streams[i] || g_host.dev != dev) {
-                if ((ce = cudaStreamCreateWithFlags(&g_host.streams[i], cudaStreamNonBlocking)) != cudaSuccess)
-                    return cuda_fail(ce, "cudaStreamCreate");
-            }
-            if ((ce = cudaMalloc(&g_host.ws[i], slot_bytes)) != cudaSuccess) {
-                g_host.ws_bytes = 0;
+            if (h.ws[i]) { cudaStreamSynchronize(h.streams[i]); cudaFree(h.ws[i]); }
+            h.ws[i] = nullptr;
+            if (!h.streams[i] && (ce = cudaStreamCreateWithFlags(&h.streams[i], cudaStreamNonBlocking)) != cudaSuccess)
+                return cuda_fail(ce, "cudaStreamCreate");
+            if ((ce = cudaMalloc(&h.ws[i], slot_bytes)) != cudaSuccess) {
+                h.ws_bytes = 0;
                 return cuda_fail(ce, "cudaMalloc(host-path workspace)");
             }
         }
-        if (!g_host.tabs || g_host.dev != dev) {
-            if ((ce = cudaMalloc(reinterpret_cast<void **>(&g_host.tabs), sizeof(int64_t) * 3 * kMaxLevels)) !=
-                cudaSuccess)
-                return cuda_fail(ce, "cudaMalloc(level tables)");
-        }
-        g_host.ws_bytes = slot_bytes;
-        g_host.dev = dev;
+        if (!h.tabs && (ce = cudaMalloc(reinterpret_cast<void **>(&h.tabs), sizeof(int64_t) * 3 * kMaxLevels)) != cudaSuccess)
+            return cuda_fail(ce, "cudaMalloc(level tables)");
+        h.ws_bytes = slot_bytes;
+        h.live = true;
     }
-    cudaStream_t s0 = g_host.streams[0];
-    if ((ce = cudaMemcpyAsync(g_host.tabs, spatial_shapes_host, sizeof(int64_t) * 2 * d.L, cudaMemcpyHostToDevice,
+    cudaStream_t s0 = h.streams[0];
+    if ((ce = cudaMemcpyAsync(h.tabs, spatial_shapes_host, sizeof(int64_t) * 2 * d.L, cudaMemcpyHostToDevice,
                               s0)) != cudaSuccess)
         return cuda_fail(ce, "H2D spatial_shapes");
-    if ((ce = cudaMemcpyAsync(g_host.tabs + 2 * kMaxLevels, level_start_index_host, sizeof(int64_t) * d.L,
+    if ((ce = cudaMemcpyAsync(h.tabs + 2 * kMaxLevels, level_start_index_host, sizeof(int64_t) * d.L,
                               cudaMemcpyHostToDevice, s0)) != cudaSuccess)
         return cuda_fail(ce, "H2D level_start_index");
     if ((ce = cudaStreamSynchronize(s0)) != cudaSuccess) return cuda_fail(ce, "sync level tables");
-    const int64_t *d_shapes = g_host.tabs, *d_start = g_host.tabs + 2 * kMaxLevels;
+    const int64_t *d_shapes = h.tabs, *d_start = h.tabs + 2 * kMaxLevels;
 
     auto hp = [](const void *base, size_t off) { return static_cast<const char *>(base) + off; };
     auto hpw = [](void *base, size_t off) { return static_cast<char *>(base) + off; };
@@ -121,26 +138,26 @@ int bm2f_msda_forward_backward_host(const void *value_host, const int64_t *spati
     int slot = 0;
     for (int b0 = 0; b0 < d.N; b0 += chunk, slot = (slot + 1) % kHostSlots) {
         const int nb = (d.N - b0 < chunk) ? d.N - b0 : chunk;
-        cudaStream_t st = g_host.streams[slot];
-        char *w = static_cast<char *>(g_host.ws[slot]);
+        cudaStream_t st = h.streams[slot];
+        char *w = static_cast<char *>(h.ws[slot]);
         auto take = [&](size_t per_img) { char *r = w; w += static_cast<size_t>(chunk) * align256(per_img); return r; };
         char *dv = take(v_img), *dl = take(l_img), *da = take(a_img), *dout = take(o_img);
         char *dgo = nullptr, *dgv = nullptr, *dgl = nullptr, *dga = nullptr;
         if (bwd) { dgo = take(o_img); dgv = take(gv_img); dgl = take(l_img); dga = take(a_img); }
 
 #define BM2F_CP(dst, src, bytes, kind, what)                                                           \
-    if ((ce = cudaMemcpyAsync(dst, src, bytes, kind, st)) != cudaSuccess) return cuda_fail(ce, what);
+    if ((ce = cudaMemcpyAsync(dst, src, bytes, kind, st)) != cudaSuccess) return drain_and_return(h, cuda_fail(ce, what));
         BM2F_CP(dv, hp(value_host, b0 * v_img), nb * v_img, cudaMemcpyHostToDevice, "H2D value")
         BM2F_CP(dl, hp(sampling_loc_host, b0 * l_img), nb * l_img, cudaMemcpyHostToDevice, "H2D sampling_loc")
         BM2F_CP(da, hp(attn_weight_host, b0 * a_img), nb * a_img, cudaMemcpyHostToDevice, "H2D attn_weight")
         if (bwd) BM2F_CP(dgo, hp(grad_output_host, b0 * o_img), nb * o_img, cudaMemcpyHostToDevice, "H2D grad_output")
         rc = bm2f_msda_forward(dv, d_shapes, d_start, dl, da, dout, nb, d.S, d.M, d.D, d.L, d.Lq, d.P, dtype, tuning,
                                st);
-        if (rc) return rc;
+        if (rc) return drain_and_return(h, rc);
         if (bwd) {
             rc = bm2f_msda_backward(dv, d_shapes, d_start, dl, da, dgo, dgv, dgl, dga, nb, d.S, d.M, d.D, d.L, d.Lq,
                                     d.P, dtype, tuning, st);
-            if (rc) return rc;
+            if (rc) return drain_and_return(h, rc);
         }
         if (output_host) BM2F_CP(hpw(output_host, b0 * o_img), dout, nb * o_img, cudaMemcpyDeviceToHost, "D2H output")
         if (bwd) {
@@ -156,7 +173,7 @@ int bm2f_msda_forward_backward_host(const void *value_host, const int64_t *spati
 #undef BM2F_CP
     }
     for (int i = 0; i < kHostSlots; ++i)
-        if ((ce = cudaStreamSynchronize(g_host.streams[i])) != cudaSuccess) return cuda_fail(ce, "host-path sync");
+        if ((ce = cudaStreamSynchronize(h.streams[i])) != cudaSuccess) return drain_and_return(h, cuda_fail(ce, "host-path sync"));
     return BM2F_OK;
 }
 

@@ -34,8 +34,12 @@
  *     zeroed; `grad_value` is zero-filled by the library (reference: at::zeros, .cu:59,126);
  *     grad_sampling_loc and grad_attn_weight are fully overwritten.
  *   - Every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the
- *     legacy default stream).  No internal synchronisation, no static mutable state other
- *     than a launch counter and a thread-local error string: re-entrant across streams.
+ *     legacy default stream).  No internal synchronisation: re-entrant across streams and devices.  The library's
+ *     static state is: a launch counter (atomic), a thread-local error string, cached device attributes, the
+ *     process-wide default tuning (bm2f_msda_set_default_tuning: set it before concurrent use, it is read without a
+ *     lock), the diagnostics pointer of bm2f_msda_debug_phase_profile, and — host-buffer entry only — one workspace
+ *     per device ordinal, each behind its own lock (calls for different devices run concurrently; two calls for the
+ *     same device serialise).
  *   - Return value: 0 on success; a negative BM2F_ERR_* code otherwise, in which case
  *     bm2f_msda_last_error() returns a message for the calling thread.  Unlike the
  *     reference (which only printf's launch failures, .cuh:953-957,1326-1330) kernel-launch

@@ -62,8 +62,12 @@ def test_linear_batched_input_and_autograd(msda):
     y2 = lin2(x2)
     y2.square().sum().backward()
     assert torch.allclose(y, y2, atol=2e-5, rtol=1e-5)
-    assert torch.allclose(x.grad, x2.grad, atol=1e-3, rtol=1e-4)
-    assert torch.allclose(lin.weight.grad, lin2.weight.grad, atol=1e-2, rtol=1e-4)
+    # gradients: north-star bar, 1e-4 of the largest entry (the weight gradient's fp32 accumulation chain in TMEM
+    # measures 3e-5)
+    rel = lambda a, b: ((a - b).abs().max() / b.abs().max()).item()
+    assert rel(x.grad, x2.grad) <= 1e-4
+    assert rel(lin.weight.grad, lin2.weight.grad) <= 1e-4
+    assert rel(lin.bias.grad, lin2.bias.grad) <= 1e-4
 
 
 def test_linear_rejects_unsupported(msda):

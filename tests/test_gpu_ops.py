@@ -208,8 +208,19 @@ def test_module_forward_backward_vs_torch_port(ops):
     ref = mod.output_proj(O.torch_port_forward(value, shapes, loc, aw))
     grads = torch.autograd.grad(ref.sum(), (q2, x2))
     assert (out - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
-    assert rel_err(q.grad.cpu().numpy(), grads[0].cpu().numpy()) <= 2e-3     # through TF32-free fp32 GEMMs
-    assert rel_err(x.grad.cpu().numpy(), grads[1].cpu().numpy()) <= 2e-3
+    # gradients at the north-star bar (1e-4 of the largest entry).  grad wrt the value input is continuous in the
+    # sampling locations and is compared everywhere.  grad wrt the query passes through grad_sampling_loc, whose
+    # one-sided derivative flips when a sampling coordinate sits next to an integer pixel coordinate and the two
+    # implementations' offsets (two different fp32 GEMMs) round to different sides: it is compared on the queries none of
+    # whose 96 sampling points lies within 1e-3 px of such a kink (the same rule as tests/helpers.py:smooth_mask for the
+    # core op); the others must still agree to 2e-3.
+    assert rel_err(x.grad.cpu().numpy(), grads[1].cpu().numpy()) <= 1e-4
+    smooth = smooth_mask(loc.detach().cpu().numpy(), shapes.cpu().numpy(), eps=1e-3)        # (N, Lq, M, L, P, 2)
+    rows = torch.from_numpy(smooth.reshape(2, S, -1).all(-1)).to(dev)
+    assert rows.float().mean().item() > 0.3
+    gq, gr = q.grad * rows[..., None], grads[0] * rows[..., None]
+    assert rel_err(gq.cpu().numpy(), gr.cpu().numpy()) <= 1e-4
+    assert rel_err(q.grad.cpu().numpy(), grads[0].cpu().numpy()) <= 2e-3
 
 
 def test_module_padding_mask_and_box_reference(ops):
