@@ -127,6 +127,17 @@ size_t bm2f_linear_workspace_bytes(int out_features, int in_features)
 }
 
 namespace {
+bm2f_linear_tuning_t g_linear_tuning = {};      // A/B variants only (bm2f_linear_set_tuning)
+}  // namespace
+
+int bm2f_linear_set_tuning(const bm2f_linear_tuning_t *tuning)
+{
+    if (tuning) g_linear_tuning = *tuning;
+    else memset(&g_linear_tuning, 0, sizeof(g_linear_tuning));
+    return BM2F_OK;
+}
+
+namespace {
 // y[rows, n_out] = x[rows, k_red] * w'[n_out, k_red]^T (+ bias); w' = weight or its transpose
 int linear_common(const void *x, const void *weight, const void *bias, void *y, void *workspace, int rows, int n_out,
                   int k_red, int transpose_weight, int split, void *stream, int relu = 0, const void *mask = nullptr /* output mask */,
@@ -137,21 +148,15 @@ int linear_common(const void *x, const void *weight, const void *bias, void *y, 
     if (k_red <= 0 || k_red % kGemmBlockK != 0 || k_red > kGemmKMax)
         return fail(BM2F_ERR_UNSUPPORTED, "tcgen05 projection GEMM needs a reduction length that is a multiple of %d "
                     "and <= %d (got %d)", kGemmBlockK, kGemmKMax, k_red);
-    // split 3 / 1: persistent kernel (double-buffered TMEM accumulator); +10: one tile per CTA (kept for A/B);
-    // +20: persistent kernel with coalesced-store epilogue instead of the TMA store (A/B);
-    // +30: persistent kernel in clusters of two CTAs with TMA-multicast weights (A/B)
-    // +40 / +50 / +60: more activation bytes in flight (8 producer warps x 5 k-blocks / 4 x 4 / 8 x 4) (A/B)
-    // +70: CTA pairs issuing tcgen05.mma.cta_group::2 (M = 256 per pair)
-    // split 1 (single TF32 pass) loads the activation tile by TMA straight into the MMA stage by default (= 1 + 80);
-    // 1 + 50 selects the register-staged activation path of the three-term kernel for comparison
-    int xvar = 0;
-    if (split >= 40) { xvar = split / 10 - 3; split -= (xvar + 3) * 10; }
-    const bool cluster2 = split >= 30;
-    if (cluster2) split -= 30;
-    const bool stg_epilogue = split >= 20;
-    if (stg_epilogue) split -= 20;
-    const bool one_tile = split >= 10;
-    if (one_tile) split -= 10;
+    // kernel variant (bm2f_linear_tuning_t.variant, A/B only): 0 persistent kernel (double-buffered TMEM accumulator),
+    // 1 one tile per CTA, 2 coalesced-store epilogue instead of the TMA store, 3 clusters of two CTAs with TMA-multicast
+    // weights, 4 / 5 / 6 more activation bytes in flight (8 producer warps x 5 k-blocks / 4 x 4 / 8 x 4), 7 CTA pairs
+    // issuing tcgen05.mma.cta_group::2 (M = 256 per pair).  split 1 (single TF32 pass) loads the activation tile by TMA
+    // straight into the MMA stage by default; variant 5 selects the register-staged activation path for comparison
+    const int variant = g_linear_tuning.variant;
+    if (variant < 0 || variant > 8) return fail(BM2F_ERR_INVALID, "bm2f_linear_tuning_t.variant %d out of range (0..8)", variant);
+    const int xvar = variant >= 4 ? variant - 3 : 0;
+    const bool cluster2 = variant == 3, stg_epilogue = variant == 2, one_tile = variant == 1;
     if (split != 1 && split != 3) return fail(BM2F_ERR_INVALID, "split must be 3 (tf32x3) or 1 (single TF32 pass)");
     if (!aligned16(x) || !aligned16(y) || !aligned16(weight) || !aligned16(workspace) || (bias && !aligned16(bias)))
         return fail(BM2F_ERR_UNSUPPORTED, "linear: tensors must be 16-byte aligned");
@@ -235,9 +240,9 @@ int linear_dw_common(const void *grad_y, const void *x, void *grad_weight, void 
         return fail(BM2F_ERR_UNSUPPORTED, "weight-gradient GEMM needs in_features to be a multiple of 256 (got %d)",
                     in_features);
     if (out_features > 8192 || in_features > 8192) return fail(BM2F_ERR_UNSUPPORTED, "layer too large");
-    // split + 100 * c (A/B knob): cap the rows one CTA reduces at 256 * c, i.e. shorten the TMEM accumulation chain
-    int row_cap = 0;
-    if (split >= 100) { row_cap = (split / 100) * 256; split %= 100; }
+    // A/B knob: cap the rows one CTA reduces at 256 * c, i.e. shorten the TMEM accumulation chain
+    if (g_linear_tuning.dw_row_cap < 0) return fail(BM2F_ERR_INVALID, "bm2f_linear_tuning_t.dw_row_cap must be >= 0");
+    const int row_cap = g_linear_tuning.dw_row_cap * 256;
     if (split != 1 && split != 3) return fail(BM2F_ERR_INVALID, "split must be 3 (tf32x3) or 1 (single TF32 pass)");
     int sms = 0, cc = 0;
     int rc = device_info(&sms, &cc);

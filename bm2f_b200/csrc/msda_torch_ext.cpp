@@ -551,6 +551,13 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("ms_deform_attn_fused_backward", &ms_deform_attn_fused_backward, "backward of the fused op");
     m.def("linear_tf32x3", &linear_tf32x3, "tcgen05 projection GEMM (y = x W^T + b), split=3: tf32x3, 1: tf32");
     m.def("linear_tf32x3_supported", &linear_tf32x3_supported);
+    m.def("linear_set_tuning", [](int variant, int dw_row_cap) {
+        bm2f_linear_tuning_t t = {};
+        t.variant = variant;
+        t.dw_row_cap = dw_row_cap;
+        bm2f_linear_set_tuning(&t);
+    }, "A/B kernel variants of the tcgen05 GEMMs (bm2f_linear_tuning_t); (0, 0) = defaults", pybind11::arg("variant") = 0,
+          pybind11::arg("dw_row_cap") = 0);
     m.def("linear_tf32x3_backward_weight", &linear_tf32x3_backward_weight, "grad_W = grad_y^T x, grad_b = sum grad_y (tcgen05)");
     m.def("linear_tf32x3_backward_input", &linear_tf32x3_backward_input, "grad_x = grad_y @ weight (tcgen05)");
     m.def("linear_tf32x3_backward_input_accumulate", &linear_tf32x3_backward_input_accumulate,

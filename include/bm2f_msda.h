@@ -191,13 +191,25 @@ int bm2f_msda_fused_backward(const void *value, const int64_t *spatial_shapes,
  * float32 in / out; output width a multiple of 256 or one of {288, 192, 96}, reduction length a multiple of 32
  * (forward: in_features = 256 = d_model; bm2f_linear_backward_input: grad_x = grad_y * weight, width 256).
  * split = 3: three-term TF32 split with fp32 accumulation (fp32-grade result, what the fp32 reference
- * module needs); split = 1: single TF32 pass.  Adding a multiple of 10 selects a kernel variant kept for A/B
- * measurements (same results): +10 one tile per CTA, +20 coalesced-store epilogue, +30 clusters of two
- * CTAs with TMA-multicast weights, +40 / +50 / +60 more activation k-blocks in flight, +70 CTA pairs issuing
- * tcgen05.mma.cta_group::2; for bm2f_linear_backward_weight +100*c caps the rows reduced per CTA at 256*c.  `workspace` = bm2f_linear_workspace_bytes() of device
- * memory for the hi/lo halves of the weight (rewritten on every call).  bias may be NULL.
+ * module needs); split = 1: single TF32 pass; nothing else is accepted.  `workspace` =
+ * bm2f_linear_workspace_bytes() of device memory for the hi/lo halves of the weight (rewritten on every call).
+ * bias may be NULL.
  */
 size_t bm2f_linear_workspace_bytes(int out_features, int in_features);
+
+/* Kernel variants of the GEMMs kept for A/B measurements (same results).  Process-wide, read without a
+ * lock: a measurement tool sets it, production code never does.  NULL restores the defaults (all zero). */
+typedef struct {
+    int variant;      /* forward / grad_x GEMM: 0 = default (persistent kernel; single TF32 pass: activation tile by TMA),
+                         1 = one tile per CTA, 2 = coalesced-store epilogue instead of the TMA store, 3 = clusters of two
+                         CTAs with TMA-multicast weights, 4 / 5 / 6 = more activation k-blocks in flight (8 producer warps
+                         x 5 / 4 x 4 / 8 x 4; with split = 1, 5 = register-staged activations), 7 = CTA pairs issuing
+                         tcgen05.mma.cta_group::2 */
+    int dw_row_cap;   /* weight-gradient GEMM: rows reduced per CTA capped at 256 * dw_row_cap (shortens the fp32
+                         accumulation chain in TMEM); 0 = no cap */
+    int reserved[6];
+} bm2f_linear_tuning_t;
+int bm2f_linear_set_tuning(const bm2f_linear_tuning_t *tuning);
 int bm2f_linear_forward(const void *x, const void *weight, const void *bias, void *y, void *workspace,
                         int rows, int out_features, int in_features, int split, void *stream);
 int bm2f_linear_backward_input(const void *grad_y, const void *weight, void *grad_x, void *workspace,

@@ -30,8 +30,14 @@ def test_linear_tf32x3_matches_fp64(msda, out_features, rows):
     assert err3 < err1
     ynb = msda.linear_tf32x3(x, w, None, 3)
     assert torch.allclose(ynb + b, y3, atol=1e-5, rtol=1e-5)
-    # split + 10 = the one-tile-per-CTA kernel; 3 / 1 = persistent kernel (where the width allows it)
-    y13 = msda.linear_tf32x3(x, w, b, 13)
+    # tuning variant 1 = the one-tile-per-CTA kernel; default = persistent kernel (where the width allows it)
+    msda.linear_set_tuning(1, 0)
+    try:
+        y13 = msda.linear_tf32x3(x, w, b, 3)
+    finally:
+        msda.linear_set_tuning(0, 0)
+    with pytest.raises(RuntimeError, match="split must be"):
+        msda.linear_tf32x3(x, w, b, 13)                           # no variant selectors hidden in `split`
     assert torch.equal(y13, y3) or (y13 - y3).abs().max().item() <= 1e-6 * ref.abs().max().item()
 
 
@@ -107,11 +113,11 @@ def test_linear_backward_weight_matches_fp64(msda, out_features, rows):
     assert not gb2.defined() if hasattr(gb2, "defined") else gb2 is None or gb2.numel() == 0
 
 
-@pytest.mark.parametrize("variant,name", [(33, "cluster of 2, TMA-multicast weights"), (73, "CTA pair, tcgen05 cta_group::2"),
-                                          (43, "8 producer warps x 5 k-blocks"), (53, "4 x 4"), (23, "coalesced-store epilogue")])
+@pytest.mark.parametrize("variant,name", [(3, "cluster of 2, TMA-multicast weights"), (7, "CTA pair, tcgen05 cta_group::2"),
+                                          (4, "8 producer warps x 5 k-blocks"), (5, "4 x 4"), (2, "coalesced-store epilogue")])
 @pytest.mark.parametrize("in_features,out_features", [(256, 256), (256, 1024), (1024, 256)])
 def test_linear_kernel_variants_match_default(msda, variant, name, in_features, out_features):
-    """The A/B variants of the persistent GEMM kept in the library (split + 20 / 30 / 40 / 50 / 70) compute
+    """The A/B variants of the persistent GEMM kept in the library (bm2f_linear_tuning_t.variant) compute
     the same tiles with the same MMA order as the default kernel: results equal to 1e-6, on ragged and odd tile counts
     (the cluster variants walk row tiles in pairs; an odd count leaves one CTA of the last pair without rows)."""
     dev = torch.device("cuda:0")
@@ -121,7 +127,11 @@ def test_linear_kernel_variants_match_default(msda, variant, name, in_features, 
         w = torch.randn(out_features, in_features, device=dev) / in_features ** 0.5
         b = torch.randn(out_features, device=dev)
         y0 = msda.linear_tf32x3(x, w, b, 3)
-        y1 = msda.linear_tf32x3(x, w, b, variant)
+        msda.linear_set_tuning(variant, 0)
+        try:
+            y1 = msda.linear_tf32x3(x, w, b, 3)
+        finally:
+            msda.linear_set_tuning(0, 0)
         ref = x.double() @ w.double().t() + b.double()
         scale = ref.abs().max().item()
         assert (y1.double() - ref).abs().max().item() <= 1e-5 * scale, (name, rows)

@@ -25,8 +25,11 @@ for n in (256, 288, 192, 96):
     t_tf32 = t(lambda: F.linear(x, w, b)); e_tf32 = ((F.linear(x, w, b).double() - ref).abs().max() / ref.abs().max()).item()
     torch.backends.cuda.matmul.allow_tf32 = False
     t3 = t(lambda: MSDA.linear_tf32x3(x, w, b, 3)); e3 = ((MSDA.linear_tf32x3(x, w, b, 3).double() - ref).abs().max() / ref.abs().max()).item()
-    t13 = t(lambda: MSDA.linear_tf32x3(x, w, b, 13))
-    t23 = t(lambda: MSDA.linear_tf32x3(x, w, b, 23)); e23 = ((MSDA.linear_tf32x3(x, w, b, 23).double() - ref).abs().max() / ref.abs().max()).item()
+    MSDA.linear_set_tuning(1, 0)          # A/B variants: bm2f_linear_tuning_t.variant
+    t13 = t(lambda: MSDA.linear_tf32x3(x, w, b, 3))
+    MSDA.linear_set_tuning(2, 0)
+    t23 = t(lambda: MSDA.linear_tf32x3(x, w, b, 3)); e23 = ((MSDA.linear_tf32x3(x, w, b, 3).double() - ref).abs().max() / ref.abs().max()).item()
+    MSDA.linear_set_tuning(0, 0)
     t1 = t(lambda: MSDA.linear_tf32x3(x, w, b, 1)); e1 = ((MSDA.linear_tf32x3(x, w, b, 1).double() - ref).abs().max() / ref.abs().max()).item()
     gb = rows * (256 + n) * 4 / 1e9
     fl = 2.0 * rows * 256 * n / 1e12
@@ -46,7 +49,8 @@ for n in (256, 192, 96):
 g = torch.randn(rows, 256, device=dev)
 ref = g.double().t() @ x.double()
 for c in (0, 16, 8, 4, 2):
-    sp = 3 + 100 * c
-    t_dw = t(lambda: MSDA.linear_tf32x3_backward_weight(g, x, sp, True))
-    e = ((MSDA.linear_tf32x3_backward_weight(g, x, sp, True)[0].double() - ref).abs().max() / ref.abs().max()).item()
+    MSDA.linear_set_tuning(0, c)          # bm2f_linear_tuning_t.dw_row_cap
+    t_dw = t(lambda: MSDA.linear_tf32x3_backward_weight(g, x, 3, True))
+    e = ((MSDA.linear_tf32x3_backward_weight(g, x, 3, True)[0].double() - ref).abs().max() / ref.abs().max()).item()
+    MSDA.linear_set_tuning(0, 0)
     print(f"dW N=256 rows={rows} row cap {256 * c if c else 'none'}: {t_dw:.3f} ms (err {e:.1e})")
