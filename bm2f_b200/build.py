@@ -54,7 +54,7 @@ def _run(cmd):
 
 
 # translation units of libbm2f_msda.so (compiled in parallel, then linked)
-LIB_UNITS = ("api_common.cu", "msda_api.cu", "msda_bwd_sorted.cu", "linear_api.cu", "glue_api.cu", "host_api.cu")
+LIB_UNITS = ("api_common.cu", "msda_api.cu", "msda_bwd_sorted.cu", "linear_api.cu", "glue_api.cu", "fpn_api.cu", "host_api.cu")
 OBJ_DIR = os.path.join(PKG, "_obj")
 
 

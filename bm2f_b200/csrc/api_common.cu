@@ -82,7 +82,7 @@ int device_info(int *sms, int *cc_major)
 
 // 2-D fp32 matrix (rows x cols, row-major) -> boxes of (box_rows x box_cols).
 int make_map(CUtensorMap *map, const float *base, uint64_t rows, uint64_t cols, uint32_t box_rows,
-             uint32_t box_cols, bool swizzle128)
+             uint32_t box_cols, int swizzle)
 {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(BM2F_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
@@ -92,7 +92,8 @@ int make_map(CUtensorMap *map, const float *base, uint64_t rows, uint64_t cols, 
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstride, box,
                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                          swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                       : swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(BM2F_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return BM2F_OK;

@@ -40,8 +40,9 @@ int ensure_dynamic_smem(int bytes, const char *what)
 }
 
 // 2-D fp32 matrix (rows x cols, row-major) -> boxes of (box_rows x box_cols).
+// swizzle: 0 none, 1 (true) SWIZZLE_128B, 2 SWIZZLE_128B_ATOM_32B (32-byte swizzle units: MN-major TF32 MMA operands)
 int make_map(CUtensorMap *map, const float *base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols,
-             bool swizzle128 = false);
+             int swizzle = 0);
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

@@ -23,7 +23,7 @@ constexpr int kGnC = 256;       // conv_dim
 constexpr int kGnGroups = 32;   // nn.GroupNorm(32, conv_dim): 8 channels = 2 float4 per group
 
 // in (B, R, C) -> out (B, C, R)
-__global__ void __launch_bounds__(256) transpose_batched_kernel(const float *__restrict__ in, float *__restrict__ out,
+static __global__ void __launch_bounds__(256) transpose_batched_kernel(const float *__restrict__ in, float *__restrict__ out,
                                                                 int R, int C)
 {
     __shared__ float tile[32][33];
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) transpose_batched_kernel(const float *__r
 }
 
 // sums[(n * 32 + g) * 2 + {0, 1}] += sum y, sum y^2 over this CTA's rows of image n.  grid (chunks, batch).
-__global__ void __launch_bounds__(256) groupnorm_tokens_stats_kernel(const float *__restrict__ y, double *__restrict__ sums,
+static __global__ void __launch_bounds__(256) groupnorm_tokens_stats_kernel(const float *__restrict__ y, double *__restrict__ sums,
                                                                      int tokens)
 {
     __shared__ float s_part[8][64][2];
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) groupnorm_tokens_stats_kernel(const float
 }
 
 // forward: mean / rstd;  backward: c1 = sum(dy*gamma)/cnt, c2 = sum(dy*gamma*xhat)/cnt
-__global__ void groupnorm_tokens_finalize_kernel(const double *__restrict__ sums, float *__restrict__ a, float *__restrict__ b,
+static __global__ void groupnorm_tokens_finalize_kernel(const double *__restrict__ sums, float *__restrict__ a, float *__restrict__ b,
                                                  int n_stats, double count, float eps, int forward)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -94,7 +94,7 @@ __global__ void groupnorm_tokens_finalize_kernel(const double *__restrict__ sums
 }
 
 // out[n, t, :] = (y[n, t, :] - mean[n, g]) * rstd[n, g] * gamma + beta, out rows at out + n * out_batch_stride + t * 256
-__global__ void __launch_bounds__(256) groupnorm_tokens_apply_kernel(const float *__restrict__ y, const float *__restrict__ mean,
+static __global__ void __launch_bounds__(256) groupnorm_tokens_apply_kernel(const float *__restrict__ y, const float *__restrict__ mean,
                                                                      const float *__restrict__ rstd,
                                                                      const float *__restrict__ gamma,
                                                                      const float *__restrict__ beta, float *__restrict__ out,
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256) groupnorm_tokens_apply_kernel(const float
 }
 
 // backward pass 1: per (n, g) sums of dy*gamma and dy*gamma*xhat (fp64 atomics), per-channel dgamma / dbeta (fp32 atomics)
-__global__ void __launch_bounds__(256) groupnorm_tokens_bwd_stats_kernel(const float *__restrict__ grad_out,
+static __global__ void __launch_bounds__(256) groupnorm_tokens_bwd_stats_kernel(const float *__restrict__ grad_out,
                                                                          long long grad_batch_stride,
                                                                          const float *__restrict__ y,
                                                                          const float *__restrict__ mean,
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) groupnorm_tokens_bwd_stats_kernel(const f
 }
 
 // backward pass 2: grad_y = rstd * (dy*gamma - c1 - xhat * c2)
-__global__ void __launch_bounds__(256) groupnorm_tokens_bwd_apply_kernel(const float *__restrict__ grad_out,
+static __global__ void __launch_bounds__(256) groupnorm_tokens_bwd_apply_kernel(const float *__restrict__ grad_out,
                                                                          long long grad_batch_stride,
                                                                          const float *__restrict__ y,
                                                                          const float *__restrict__ mean,
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(256) groupnorm_tokens_bwd_apply_kernel(const f
 // pos[t, c], t = i * W + j: c < F: y part, c >= F: x part (position_encoding.py:33-52 with mask = None, normalize = True):
 //   e = (i + 1) / (H + 1e-6) * scale   (resp. (j + 1) / (W + 1e-6));  v = e / temperature^(2 * (k / 2) / F), k = c mod F;
 //   sin for even k, cos for odd k.  Same fp32 operation order as torch (true divisions, no reciprocal multiplies).
-__global__ void sine_pos_embed_kernel(float *__restrict__ out, int H, int W, int F, float temperature, float scale,
+static __global__ void sine_pos_embed_kernel(float *__restrict__ out, int H, int W, int F, float temperature, float scale,
                                       int normalize)
 {
     const int C = 2 * F;

@@ -41,6 +41,11 @@ struct LinearParams {
     const float *addend;    // optional (M, N): epilogue adds it (gradient accumulation; may alias y: a tile is read, then
                             // written, by the one CTA that owns it)
     int split;           // 3 = tf32x3 (fp32-grade), 1 = single TF32 pass
+    // CONV instantiation (3 x 3 convolution over token rows, conv3x3 in fpn_api.cu): x is the zero-haloed image
+    // (batch, conv_h + 2, conv_w + 2, ldx) and M counts its rows; K = 9 * ldx, k-block kb belongs to tap kb / (ldx / 32)
+    // whose activation row is the tile row shifted by (tap / 3 - 1) * (conv_w + 2) + (tap % 3 - 1); y is the dense
+    // (batch, conv_h, conv_w, N) image: halo rows of a tile are computed and dropped
+    int ldx, conv_w, conv_h;
 };
 
 
@@ -455,7 +460,7 @@ constexpr int kXtmaStages = 4;
 // XTMA (single TF32 pass only): the activation tile needs no hi/lo split, so it is TMA-loaded straight into the MMA
 // stage like the weights (the tensor core ignores the low 13 mantissa bits); the producer warps idle and the freed
 // shared memory holds four stages.
-template <int NT, int CL = 1, int PW = kGemmProducerWarps, int XD = 3, bool PAIR = false, bool XTMA = false>
+template <int NT, int CL = 1, int PW = kGemmProducerWarps, int XD = 3, bool PAIR = false, bool XTMA = false, bool CONV = false>
 __global__ void __launch_bounds__(gemm_threads_persistent(PW), 1)
 linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CUtensorMap tm_whi,
                                 const __grid_constant__ CUtensorMap tm_wlo, const __grid_constant__ CUtensorMap tm_y,
@@ -465,6 +470,7 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
     constexpr int kXBytes = kGemmBlockM * kGemmBlockK * 4;
     static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
     static_assert(!XTMA || (CL == 1 && !PAIR), "XTMA: single CTAs");
+    static_assert(!CONV || (CL == 1 && !PAIR), "CONV: single CTAs");
     constexpr int kStages = XTMA ? kXtmaStages : PAIR ? kPairStages : kGemmStages;
     constexpr int kWBytes = (PAIR ? N / 2 : N) * kGemmBlockK * 4;   // PAIR: this CTA's half of the weight k-block
     constexpr int kSlots = XTMA ? 1 : 2;                            // hi (+ lo) tiles per operand and stage
@@ -534,13 +540,24 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
             int g = 0;
             for (TileIter ti = first_tile(); ti.tile < num_tiles; next_tile(ti)) {
                 const int wrow = ti.sl * NT;
+                int kc = 0, tdx = -1, tdy = -1;          // CONV: channel block and tap offset of this k-block
                 for (int kb = 0; kb < kKBlocks; ++kb, ++g) {
                     const int s = g % kStages;
                     mbar_wait_bounded(&empty_bar[s], ((g / kStages) & 1) ^ 1);
                     uint64_t *tbar = &full_bar[s];
                     mbar_arrive_expect_tx(tbar, XTMA ? kWBytes + kXBytes : p.split == 3 ? 2 * kWBytes : kWBytes);
-                    if (XTMA)      // rows past M are zero-filled by the TMA unit
-                        tma_load_2d(stage_ptr(s), &tm_x, kb * kGemmBlockK, (ti.rt * CL + crank) * kGemmBlockM, tbar);
+                    if (XTMA) {    // rows past M (CONV: also before row 0) are zero-filled by the TMA unit
+                        if (CONV) {
+                            tma_load_2d(stage_ptr(s), &tm_x, kc * kGemmBlockK,
+                                        ti.rt * kGemmBlockM + tdy * (p.conv_w + 2) + tdx, tbar);
+                            if (++kc == p.ldx / kGemmBlockK) {
+                                kc = 0;
+                                if (++tdx == 2) { tdx = -1; ++tdy; }
+                            }
+                        } else {
+                            tma_load_2d(stage_ptr(s), &tm_x, kb * kGemmBlockK, (ti.rt * CL + crank) * kGemmBlockM, tbar);
+                        }
+                    }
                     unsigned char *w_hi = stage_ptr(s) + kSlots * kXBytes;
                     if (CL == 1) {
                         tma_load_2d(w_hi, &tm_whi, kb * kGemmBlockK, wrow, tbar);
@@ -651,13 +668,20 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
         const int t = threadIdx.x - 64;
         const int c16 = t & 7, rsub = t >> 3;
         auto load_x = [&](int rt, int kb, float4 (&v)[kPasses]) {
-            const int rbase = rt * kGemmBlockM + rsub;
-            const size_t cbase = static_cast<size_t>(kb) * kGemmBlockK;
+            int rbase = rt * kGemmBlockM + rsub;
+            size_t cbase = static_cast<size_t>(kb) * kGemmBlockK;
+            const int ld = CONV ? p.ldx : p.K;
+            if (CONV) {            // k-block -> (tap, channel block); the tap shifts the row inside the zero-haloed image
+                const int cpk = p.ldx / kGemmBlockK, tap = kb / cpk;
+                cbase = static_cast<size_t>(kb - tap * cpk) * kGemmBlockK;
+                rbase += (tap / 3 - 1) * (p.conv_w + 2) + (tap % 3 - 1);
+            }
 #pragma unroll
             for (int j = 0; j < kPasses; ++j) {
                 const int gr = rbase + kRowsPerPass * j;
-                v[j] = gr < p.M ? __ldg(reinterpret_cast<const float4 *>(p.x + static_cast<size_t>(gr) * p.K + cbase) + c16)
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[j] = (gr < p.M && (!CONV || gr >= 0))
+                           ? __ldg(reinterpret_cast<const float4 *>(p.x + static_cast<size_t>(gr) * ld + cbase) + c16)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
         // kXDepth k-blocks of X are in flight per thread (registers): with one block in flight the kernel is bound by
@@ -711,6 +735,19 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
         for (TileIter ti = first_tile(); ti.tile < num_tiles; next_tile(ti), ++i) {
             const int b = i & 1;
             const int rt_own = ti.rt * CL + crank;              // this CTA's row tile of the group
+            // CONV: the 8 rows this lane stores per 32-column chunk, as rows of the dense image (-1: halo or past the end)
+            int conv_row[8];
+            if (CONV) {
+                const int wp = p.conv_w + 2, hp = p.conv_h + 2;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int pr = rt_own * kGemmBlockM + q * 32 + it * 4 + (lane >> 3);
+                    const int img = pr / (hp * wp), rem = pr - img * (hp * wp);
+                    const int yp = rem / wp, xp = rem - yp * wp;
+                    conv_row[it] = (pr < p.M && yp >= 1 && yp <= p.conv_h && xp >= 1 && xp <= p.conv_w)
+                                       ? (img * p.conv_h + yp - 1) * p.conv_w + xp - 1 : -1;
+                }
+            }
             mbar_wait_bounded(&acc_full[b], (i >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
@@ -727,7 +764,7 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
                 unsigned char *stg = staging + q * (2 * 4096) + (chunk & 1) * 4096;
                 const uint32_t stg_s = smem_u32(stg);
                 const int grow = rt_own * kGemmBlockM + q * 32 + lane;     // this thread's output row
-                if (chunk >= 2 && p.store_mode == 0) {
+                if (chunk >= 2 && p.store_mode == 0 && !CONV) {
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                     __syncwarp();
                 }
@@ -752,7 +789,18 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
                     }
                     sts128(stg_s + lane * 128 + ((((c >> 2) ^ (lane & 7))) << 4), o);
                 }
-                if (p.store_mode == 0) {
+                if (CONV) {
+                    __syncwarp();
+                    const int ch = lane & 7;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int row = it * 4 + (lane >> 3);
+                        const float4 v = *reinterpret_cast<const float4 *>(stg + row * 128 + ((ch ^ (row & 7)) << 4));
+                        if (conv_row[it] >= 0)
+                            *reinterpret_cast<float4 *>(p.y + static_cast<size_t>(conv_row[it]) * p.N + ti.sl * NT + c0 + ch * 4) = v;
+                    }
+                    __syncwarp();
+                } else if (p.store_mode == 0) {
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) {
@@ -778,7 +826,7 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
                 }
             }
         }
-        if (lane == 0 && p.store_mode == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (lane == 0 && p.store_mode == 0 && !CONV) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -830,14 +878,22 @@ struct LinearDwParams {
     int M, N, ldx;
     int rows_per_chunk;  // multiple of 32
     int split;
+    // 3 x 3 convolution weight gradient (tf32x3 path; the single-pass path is conv_dw_tma_kernel): conv_wp = W + 2 > 0,
+    // g and x are zero-haloed (rows, 256) images, blockIdx.z = filter tap: x rows are shifted by the tap and the tap's
+    // 256 columns of dw (N, ld_dw = 9 * 256) are written
+    int conv_wp, ld_dw;
 };
 
-__global__ void __launch_bounds__(kDwThreads, 1) linear_dw_tf32x3_kernel(const LinearDwParams p)
+static __global__ void __launch_bounds__(kDwThreads, 1) linear_dw_tf32x3_kernel(const LinearDwParams p)
 {
     constexpr int kABytes = 128 * 128;                 // 128 features x 128 B
     constexpr int kBBytes = kDwNB * 128;               // 272 features x 128 B
     constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
-    const int k0 = blockIdx.z * 256;                   // feature slice of x handled by this CTA
+    const int k0 = p.conv_wp ? 0 : blockIdx.z * 256;   // feature slice of x handled by this CTA
+    const int dw_c0 = blockIdx.z * 256;                // its columns of dw
+    const int ld_dw = p.conv_wp ? p.ld_dw : p.ldx;
+    const int tz = static_cast<int>(blockIdx.z);
+    const int xshift = p.conv_wp ? (tz / 3 - 1) * p.conv_wp + (tz % 3 - 1) : 0;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t full_bar[kGemmStages], empty_bar[kGemmStages], acc_bar;
@@ -934,7 +990,9 @@ __global__ void __launch_bounds__(kDwThreads, 1) linear_dw_tf32x3_kernel(const L
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int r = rb + b * 8 + i;
-                        v[a][b][i] = ((a > 0 || a_ok) && r < r_end) ? __ldg(src[a] + static_cast<size_t>(r) * ld[a]) : 0.f;
+                        const int rs = a > 0 ? r + xshift : r;        // conv: x row of this tap (halo rows are zero)
+                        v[a][b][i] = ((a > 0 || a_ok) && r < r_end && rs >= 0 && rs < p.M)
+                                         ? __ldg(src[a] + static_cast<size_t>(rs) * ld[a]) : 0.f;
                     }
         };
         float cur[3][4][4], nxt[3][4][4];
@@ -979,7 +1037,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) linear_dw_tf32x3_kernel(const L
                 tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, acc);
                 if (n < p.N) {
                     if (c0 < 256) {
-                        float *dst = p.dw + static_cast<size_t>(n) * p.ldx + k0 + c0;
+                        float *dst = p.dw + static_cast<size_t>(n) * ld_dw + dw_c0 + c0;
 #pragma unroll
                         for (int c = 0; c < 32; c += 4) {
                             const float r4[4] = {acc[c], acc[c + 1], acc[c + 2], acc[c + 3]};
@@ -1012,7 +1070,7 @@ constexpr int linear_smem_bytes()
 
 // W (N, K) -> W_hi, W_lo (exact TF32 split); tiny, run once per weight version
 // transpose != 0: w is (cols, rows) row-major and hi / lo receive its transpose (rows, cols)
-__global__ void split_tf32_kernel(const float *__restrict__ w, float *__restrict__ hi, float *__restrict__ lo, int n,
+static __global__ void split_tf32_kernel(const float *__restrict__ w, float *__restrict__ hi, float *__restrict__ lo, int n,
                                   int rows, int cols, int transpose)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -24,7 +24,7 @@ __device__ __forceinline__ float warp_sum(float v)
     return v;
 }
 
-__global__ void __launch_bounds__(256) add_layernorm_fwd_kernel(const float *__restrict__ x, const float *__restrict__ r,
+static __global__ void __launch_bounds__(256) add_layernorm_fwd_kernel(const float *__restrict__ x, const float *__restrict__ r,
                                                                 const float *__restrict__ gamma,
                                                                 const float *__restrict__ beta, float eps,
                                                                 float *__restrict__ z, float *__restrict__ y,
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) add_layernorm_fwd_kernel(const float *__r
     }
 }
 
-__global__ void __launch_bounds__(256) add_layernorm_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ z,
+static __global__ void __launch_bounds__(256) add_layernorm_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ z,
                                                                 const float *__restrict__ mean,
                                                                 const float *__restrict__ rstd,
                                                                 const float *__restrict__ gamma, float *__restrict__ dz,
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) add_layernorm_bwd_kernel(const float *__r
 // value.masked_fill(padding_mask[..., None], 0) without touching unmasked rows (reference:
 // ops/modules/ms_deform_attn.py:99-100; Mask2Former always passes an all-False mask, msdeformattn.py:62): one warp per
 // row reads the mask byte and only masked rows are written.  Used in place on tensors the caller owns.
-__global__ void __launch_bounds__(256) zero_masked_rows_kernel(float *__restrict__ x, const unsigned char *__restrict__ mask,
+static __global__ void __launch_bounds__(256) zero_masked_rows_kernel(float *__restrict__ x, const unsigned char *__restrict__ mask,
                                                                int rows, int channels)
 {
     const int lane = threadIdx.x & 31;

@@ -525,6 +525,158 @@ std::vector<at::Tensor> groupnorm_tokens_backward(const at::Tensor &grad_out, in
     return {dy, dgamma, dbeta};
 }
 
+// ---- FPN tail (bm2f_conv3x3_*, bm2f_fpn_*, bm2f_groupnorm_relu_tokens_*; msdeformattn.py:341-358) ---------------
+namespace {
+void check_tokens4(const at::Tensor &t, const char *what, int64_t halo)
+{
+    TORCH_CHECK(t.is_cuda(), what, ": CUDA tensors only (no CPU path)");
+    TORCH_CHECK(t.scalar_type() == at::kFloat && t.dim() == 4 && t.size(3) == 256 && t.is_contiguous(), what,
+                ": contiguous float32 (batch, height", halo ? " + 2" : "", ", width", halo ? " + 2" : "", ", 256) expected");
+}
+at::Tensor conv_workspace(const at::Tensor &like)
+{
+    return at::empty({static_cast<int64_t>(bm2f_conv3x3_workspace_bytes(256, 256))}, like.options().dtype(at::kByte));
+}
+}  // namespace
+
+// x_halo (batch, H + 2, W + 2, 256) zero-haloed -> (batch, H, W, 256); weight (256, 256, 3, 3)
+at::Tensor conv3x3_tokens_forward(const at::Tensor &x_halo, const at::Tensor &weight, int64_t split)
+{
+    check_tokens4(x_halo, "conv3x3_tokens_forward", 1);
+    TORCH_CHECK(weight.is_cuda() && weight.scalar_type() == at::kFloat && weight.dim() == 4 && weight.size(0) == 256 &&
+                    weight.size(1) == 256 && weight.size(2) == 3 && weight.size(3) == 3,
+                "conv3x3_tokens_forward: weight must be float32 (256, 256, 3, 3)");
+    const c10::cuda::CUDAGuard guard(x_halo.device());
+    const int batch = static_cast<int>(x_halo.size(0)), h = static_cast<int>(x_halo.size(1)) - 2, w = static_cast<int>(x_halo.size(2)) - 2;
+    TORCH_CHECK(h > 0 && w > 0, "conv3x3_tokens_forward: empty image");
+    auto y = at::empty({batch, h, w, 256}, x_halo.options());
+    auto ws = conv_workspace(x_halo);
+    const int rc = bm2f_conv3x3_forward(x_halo.data_ptr(), weight.contiguous().data_ptr(), y.data_ptr(), ws.data_ptr(), batch, h,
+                                        w, 256, 256, static_cast<int>(split), at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == BM2F_OK, "conv3x3_tokens_forward: ", bm2f_msda_last_error());
+    return y;
+}
+
+at::Tensor conv3x3_tokens_backward_input(const at::Tensor &grad_halo, const at::Tensor &weight, int64_t split)
+{
+    check_tokens4(grad_halo, "conv3x3_tokens_backward_input", 1);
+    const c10::cuda::CUDAGuard guard(grad_halo.device());
+    const int batch = static_cast<int>(grad_halo.size(0)), h = static_cast<int>(grad_halo.size(1)) - 2, w = static_cast<int>(grad_halo.size(2)) - 2;
+    auto gx = at::empty({batch, h, w, 256}, grad_halo.options());
+    auto ws = conv_workspace(grad_halo);
+    const int rc = bm2f_conv3x3_backward_input(grad_halo.data_ptr(), weight.contiguous().data_ptr(), gx.data_ptr(), ws.data_ptr(),
+                                               batch, h, w, 256, 256, static_cast<int>(split),
+                                               at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == BM2F_OK, "conv3x3_tokens_backward_input: ", bm2f_msda_last_error());
+    return gx;
+}
+
+at::Tensor conv3x3_tokens_backward_weight(const at::Tensor &grad_halo, const at::Tensor &x_halo, int64_t split)
+{
+    check_tokens4(grad_halo, "conv3x3_tokens_backward_weight", 1);
+    check_tokens4(x_halo, "conv3x3_tokens_backward_weight", 1);
+    TORCH_CHECK(grad_halo.sizes() == x_halo.sizes(), "conv3x3_tokens_backward_weight: shape mismatch");
+    const c10::cuda::CUDAGuard guard(grad_halo.device());
+    const int batch = static_cast<int>(x_halo.size(0)), h = static_cast<int>(x_halo.size(1)) - 2, w = static_cast<int>(x_halo.size(2)) - 2;
+    auto gw = at::empty({256, 256, 3, 3}, x_halo.options());
+    auto ws = conv_workspace(x_halo);
+    const int rc = bm2f_conv3x3_backward_weight(grad_halo.data_ptr(), x_halo.data_ptr(), gw.data_ptr(), ws.data_ptr(), batch, h, w,
+                                                256, 256, static_cast<int>(split), at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == BM2F_OK, "conv3x3_tokens_backward_weight: ", bm2f_msda_last_error());
+    return gw;
+}
+
+// mean, rstd (batch, 32) of y (batch, tokens, 256)
+std::vector<at::Tensor> groupnorm_tokens_stats(const at::Tensor &y, double eps)
+{
+    TORCH_CHECK(y.is_cuda(), "groupnorm_tokens_stats: CUDA tensors only (no CPU path)");
+    TORCH_CHECK(y.scalar_type() == at::kFloat && y.dim() >= 3 && y.size(-1) == 256 && y.is_contiguous(),
+                "groupnorm_tokens_stats: y must be contiguous float32 (batch, ..., 256)");
+    const c10::cuda::CUDAGuard guard(y.device());
+    const int batch = static_cast<int>(y.size(0)), tokens = static_cast<int>(y.numel() / y.size(0) / 256);
+    auto mean = at::empty({batch, 32}, y.options());
+    auto rstd = at::empty({batch, 32}, y.options());
+    auto ws = at::empty({static_cast<int64_t>(bm2f_groupnorm_tokens_workspace_bytes(batch))}, y.options().dtype(at::kByte));
+    const int rc = bm2f_groupnorm_tokens_stats(y.data_ptr(), static_cast<float>(eps), mean.data_ptr(), rstd.data_ptr(),
+                                               ws.data_ptr(), batch, tokens, 256, 32, at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == BM2F_OK, "groupnorm_tokens_stats: ", bm2f_msda_last_error());
+    return {mean, rstd};
+}
+
+// y_halo (batch, H + 2, W + 2, 256) = GroupNorm(lateral (batch, H, W, 256)) + bilinear upsample of enc_level
+// (batch, enc_h * enc_w, 256): rows contiguous, the batch stride is free (a level's slice of the (batch, S, 256) encoder
+// output is passed as a view, no copy)
+at::Tensor fpn_merge_forward(const at::Tensor &lateral, const at::Tensor &mean, const at::Tensor &rstd,
+                             const at::Tensor &gamma, const at::Tensor &beta, const at::Tensor &enc_level, int64_t enc_h,
+                             int64_t enc_w)
+{
+    check_tokens4(lateral, "fpn_merge_forward", 0);
+    TORCH_CHECK(enc_level.is_cuda() && enc_level.scalar_type() == at::kFloat && enc_level.dim() == 3 &&
+                    enc_level.size(2) == 256 && enc_level.stride(2) == 1 && enc_level.stride(1) == 256 &&
+                    enc_level.size(0) == lateral.size(0) && enc_level.size(1) == enc_h * enc_w,
+                "fpn_merge_forward: enc_level must be float32 (batch, enc_h * enc_w, 256) with contiguous rows");
+    const c10::cuda::CUDAGuard guard(lateral.device());
+    const int batch = static_cast<int>(lateral.size(0)), h = static_cast<int>(lateral.size(1)), w = static_cast<int>(lateral.size(2));
+    auto y = at::empty({batch, h + 2, w + 2, 256}, lateral.options());
+    const int rc = bm2f_fpn_merge_forward(lateral.data_ptr(), mean.contiguous().data_ptr(), rstd.contiguous().data_ptr(),
+                                          gamma.contiguous().data_ptr(), beta.contiguous().data_ptr(), enc_level.data_ptr(),
+                                          batch > 1 ? enc_level.stride(0) : enc_h * enc_w * 256, y.data_ptr(), batch, h, w,
+                                          static_cast<int>(enc_h), static_cast<int>(enc_w), 256,
+                                          at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == BM2F_OK, "fpn_merge_forward: ", bm2f_msda_last_error());
+    return y;
+}
+
+// adjoint of the upsample: grad_y (batch, H, W, 256) -> (batch, enc_h * enc_w, 256)
+at::Tensor fpn_upsample_backward(const at::Tensor &grad_y, int64_t enc_h, int64_t enc_w)
+{
+    check_tokens4(grad_y, "fpn_upsample_backward", 0);
+    const c10::cuda::CUDAGuard guard(grad_y.device());
+    const int batch = static_cast<int>(grad_y.size(0)), h = static_cast<int>(grad_y.size(1)), w = static_cast<int>(grad_y.size(2));
+    auto ge = at::empty({batch, enc_h * enc_w, 256}, grad_y.options());
+    const int rc = bm2f_fpn_upsample_backward(grad_y.data_ptr(), ge.data_ptr(), enc_h * enc_w * 256, batch, h, w,
+                                              static_cast<int>(enc_h), static_cast<int>(enc_w), 256,
+                                              at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == BM2F_OK, "fpn_upsample_backward: ", bm2f_msda_last_error());
+    return ge;
+}
+
+at::Tensor groupnorm_relu_tokens_apply(const at::Tensor &y, const at::Tensor &mean, const at::Tensor &rstd,
+                                       const at::Tensor &gamma, const at::Tensor &beta)
+{
+    check_tokens4(y, "groupnorm_relu_tokens_apply", 0);
+    const c10::cuda::CUDAGuard guard(y.device());
+    auto out = at::empty_like(y);
+    const int rc = bm2f_groupnorm_relu_tokens_apply(y.data_ptr(), mean.contiguous().data_ptr(), rstd.contiguous().data_ptr(),
+                                                    gamma.contiguous().data_ptr(), beta.contiguous().data_ptr(), out.data_ptr(),
+                                                    static_cast<int>(y.size(0)), static_cast<int>(y.size(1) * y.size(2)), 256, 32,
+                                                    at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == BM2F_OK, "groupnorm_relu_tokens_apply: ", bm2f_msda_last_error());
+    return out;
+}
+
+// returns grad_halo (batch, H + 2, W + 2, 256), grad_gamma, grad_beta
+std::vector<at::Tensor> groupnorm_relu_tokens_backward(const at::Tensor &grad_out, const at::Tensor &y, const at::Tensor &mean,
+                                                       const at::Tensor &rstd, const at::Tensor &gamma, const at::Tensor &beta)
+{
+    check_tokens4(y, "groupnorm_relu_tokens_backward", 0);
+    check_tokens4(grad_out, "groupnorm_relu_tokens_backward", 0);
+    TORCH_CHECK(grad_out.sizes() == y.sizes(), "groupnorm_relu_tokens_backward: shape mismatch");
+    const c10::cuda::CUDAGuard guard(y.device());
+    const int batch = static_cast<int>(y.size(0)), h = static_cast<int>(y.size(1)), w = static_cast<int>(y.size(2));
+    auto gh = at::empty({batch, h + 2, w + 2, 256}, y.options());
+    auto dgamma = at::empty({256}, y.options());
+    auto dbeta = at::empty({256}, y.options());
+    auto ws = at::empty({static_cast<int64_t>(bm2f_groupnorm_tokens_workspace_bytes(batch))}, y.options().dtype(at::kByte));
+    const int rc = bm2f_groupnorm_relu_tokens_backward(grad_out.data_ptr(), y.data_ptr(), mean.contiguous().data_ptr(),
+                                                       rstd.contiguous().data_ptr(), gamma.contiguous().data_ptr(),
+                                                       beta.contiguous().data_ptr(), gh.data_ptr(), dgamma.data_ptr(),
+                                                       dbeta.data_ptr(), ws.data_ptr(), batch, h, w, 256, 32,
+                                                       at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == BM2F_OK, "groupnorm_relu_tokens_backward: ", bm2f_msda_last_error());
+    return {gh, dgamma, dbeta};
+}
+
 at::Tensor sine_position_embedding(const at::Tensor &like, int64_t height, int64_t width, int64_t num_pos_feats,
                                    double temperature, double scale, bool normalize)
 {
@@ -570,6 +722,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("transpose_batched", &transpose_batched, "(B, R, C) -> (B, C, R)");
     m.def("groupnorm_tokens_forward", &groupnorm_tokens_forward, "GroupNorm(32, 256) on token rows, written into the encoder input");
     m.def("groupnorm_tokens_backward", &groupnorm_tokens_backward);
+    m.def("conv3x3_tokens_forward", &conv3x3_tokens_forward, "3x3 conv (256 -> 256, padding 1) of a zero-haloed token image on tcgen05");
+    m.def("conv3x3_tokens_backward_input", &conv3x3_tokens_backward_input);
+    m.def("conv3x3_tokens_backward_weight", &conv3x3_tokens_backward_weight);
+    m.def("groupnorm_tokens_stats", &groupnorm_tokens_stats);
+    m.def("fpn_merge_forward", &fpn_merge_forward, "haloed y = GroupNorm(lateral) + bilinear upsample of an encoder level");
+    m.def("fpn_upsample_backward", &fpn_upsample_backward);
+    m.def("groupnorm_relu_tokens_apply", &groupnorm_relu_tokens_apply);
+    m.def("groupnorm_relu_tokens_backward", &groupnorm_relu_tokens_backward);
     m.def("sine_position_embedding", &sine_position_embedding, "PositionEmbeddingSine for an all-False mask, token-major");
     m.def("abi_version", []() { return bm2f_msda_abi_version(); });
     m.def("build_info", []() { return std::string(bm2f_msda_build_info()); });

@@ -32,7 +32,7 @@ from torch import nn
 
 from . import load_extension
 from .encoder import MSDeformAttnTransformerEncoderOnly
-from .ops.functions import glue_func
+from .ops.functions import fpn_func, glue_func
 
 MSDA = load_extension()
 
@@ -234,8 +234,18 @@ class MSDeformAttnPixelDecoder(nn.Module):
             out = [z.transpose(1, 2).view(bs, -1, h, w) for z, (h, w) in zip(torch.split(y, sizes, dim=1), shapes_list)]
 
             # extra FPN levels, top-down (msdeformattn.py:341-351)
-            for idx, f in enumerate(self.in_features[:self.num_fpn_levels][::-1]):
-                x = features[f].float()
+            fpn_xs = [features[f].float() for f in self.in_features[:self.num_fpn_levels][::-1]]
+            if self.fused and fpn_xs and fpn_func.supported(fpn_xs, self.lateral_convs, self.output_convs, self.mask_features):
+                # token rows throughout (ops/functions/fpn_func.py): the coarser level is read where it lies in the
+                # encoder output, every FPN level stays (N, H, W, 256) until mask_features writes NCHW
+                prev, (ph, pw) = y[:, sum(sizes[:-1]):], shapes_list[-1]
+                for idx, x in enumerate(fpn_xs):
+                    tok = fpn_func.fpn_level(x, prev, ph, pw, self.lateral_convs[idx], self.output_convs[idx])
+                    out.append(tok.permute(0, 3, 1, 2))          # NCHW-shaped view (channels_last memory)
+                    prev, (ph, pw) = tok.view(bs, -1, tok.shape[-1]), tok.shape[1:3]
+                multi_scale_features = out[:self.maskformer_num_feature_levels]
+                return fpn_func.mask_features_tokens(tok, self.mask_features), out[0], multi_scale_features
+            for idx, x in enumerate(fpn_xs):
                 cur_fpn = self.lateral_convs[idx](x)
                 y = cur_fpn + F.interpolate(out[-1], size=cur_fpn.shape[-2:], mode="bilinear", align_corners=False)
                 out.append(self.output_convs[idx](y))

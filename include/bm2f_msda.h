@@ -288,6 +288,56 @@ int bm2f_sine_position_embedding(void *out, int height, int width, int num_pos_f
                                  int normalize, void *stream);
 
 /*
+ * FPN tail of the pixel decoder, token-major float32 rows of 256 channels; replaces the reference's
+ *     cur_fpn = lateral_conv(x); y = cur_fpn + F.interpolate(out[-1], size=cur_fpn.shape[-2:], mode="bilinear",
+ *     align_corners=False); y = output_conv(y); mask_features(y)              (msdeformattn.py:341-358)
+ * where lateral_conv = 1x1 conv + GroupNorm (bm2f_linear_forward + bm2f_groupnorm_tokens_stats), output_conv = 3x3 conv
+ * + GroupNorm + ReLU, mask_features = 1x1 conv with bias (bm2f_linear_forward).
+ *
+ * "haloed" image = (batch, height + 2, width + 2, 256) rows whose border rows are zero: with the padding in memory a
+ * filter tap of the 3x3 convolution is a constant row shift, so its activation tiles are plain 2-D TMA boxes.
+ *
+ * bm2f_conv3x3_forward: y (batch, height, width, 256) dense = conv2d(x, weight (256, 256, 3, 3), padding = 1, no bias)
+ *   on tcgen05; x_halo haloed.  split as for bm2f_linear_forward (1 = single TF32 pass, what cuDNN does for the
+ *   reference's nn.Conv2d under torch's default flags; 3 = tf32x3).  workspace: bm2f_conv3x3_workspace_bytes().
+ * bm2f_conv3x3_backward_input: grad_x dense from the haloed gradient of y (the same kernel with flipped taps).
+ * bm2f_conv3x3_backward_weight: grad_weight (256, 256, 3, 3) from the haloed gradient and the haloed input (split 1:
+ *   both operands reach the tensor core through TMA as MN-major tiles; split 3: transposing-producer kernel, one launch
+ *   over the 9 taps).
+ * bm2f_groupnorm_tokens_stats: mean / rstd (batch, 32) of y (batch, tokens, 256); workspace as for
+ *   bm2f_groupnorm_tokens_forward.
+ * bm2f_fpn_merge_forward: y_halo = GroupNorm(lateral; mean, rstd, gamma, beta) + bilinear upsample (align_corners =
+ *   False, torch's operation order) of enc (image n at enc + n * enc_batch_stride floats, enc_height x enc_width rows of
+ *   256) to height x width; writes the zero halo as well.
+ * bm2f_fpn_upsample_backward: grad_enc = adjoint of that upsample applied to grad_y (dense), as a gather: deterministic,
+ *   every grad_enc row is written exactly once.
+ * bm2f_groupnorm_relu_tokens_apply: out = relu(GroupNorm(y)).
+ * bm2f_groupnorm_relu_tokens_backward: gradient of relu(GroupNorm(y)) with respect to y, written as a haloed image
+ *   (the conv gradients read it); grad_gamma / grad_beta (256) are zeroed, then accumulated.  workspace:
+ *   bm2f_groupnorm_tokens_workspace_bytes(batch).
+ */
+size_t bm2f_conv3x3_workspace_bytes(int out_channels, int in_channels);
+int bm2f_conv3x3_forward(const void *x_halo, const void *weight, void *y, void *workspace, int batch, int height, int width,
+                         int out_channels, int in_channels, int split, void *stream);
+int bm2f_conv3x3_backward_input(const void *grad_halo, const void *weight, void *grad_x, void *workspace, int batch,
+                                int height, int width, int out_channels, int in_channels, int split, void *stream);
+int bm2f_conv3x3_backward_weight(const void *grad_halo, const void *x_halo, void *grad_weight, void *workspace, int batch,
+                                 int height, int width, int out_channels, int in_channels, int split, void *stream);
+int bm2f_groupnorm_tokens_stats(const void *y, float eps, void *mean, void *rstd, void *workspace, int batch, int tokens,
+                                int channels, int groups, void *stream);
+int bm2f_fpn_merge_forward(const void *lateral, const void *mean, const void *rstd, const void *gamma, const void *beta,
+                           const void *enc, int64_t enc_batch_stride, void *y_halo, int batch, int height, int width,
+                           int enc_height, int enc_width, int channels, void *stream);
+int bm2f_fpn_upsample_backward(const void *grad_y, void *grad_enc, int64_t grad_enc_batch_stride, int batch, int height,
+                               int width, int enc_height, int enc_width, int channels, void *stream);
+int bm2f_groupnorm_relu_tokens_apply(const void *y, const void *mean, const void *rstd, const void *gamma, const void *beta,
+                                     void *out, int batch, int tokens, int channels, int groups, void *stream);
+int bm2f_groupnorm_relu_tokens_backward(const void *grad_out, const void *y, const void *mean, const void *rstd,
+                                        const void *gamma, const void *beta, void *grad_halo, void *grad_gamma,
+                                        void *grad_beta, void *workspace, int batch, int height, int width, int channels,
+                                        int groups, void *stream);
+
+/*
  * Host-buffer convenience used for end-to-end measurement and by non-torch callers:
  * every pointer is a HOST pointer (pinned memory gives full PCIe rate).  The library copies
  * the inputs to a device workspace it owns for the duration of the call, runs forward and,

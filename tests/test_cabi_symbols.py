@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared():
     hdr = open(os.path.join(ROOT, "include", "bm2f_msda.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    return sorted(set(re.findall(r"\b(bm2f_(?:msda|linear|add|zero|transpose|groupnorm|sine)_[a-z0-9_]+)\s*\(", hdr)))
+    return sorted(set(re.findall(r"\b(bm2f_(?:msda|linear|add|zero|transpose|groupnorm|sine|conv3x3|fpn)_[a-z0-9_]+)\s*\(", hdr)))
 
 
 def test_header_symbols_are_exported(built):
@@ -20,7 +20,7 @@ def test_header_symbols_are_exported(built):
     declared = _declared()
     assert sorted(cabi.SYMBOLS) == declared
     out = subprocess.run(["nm", "-D", "--defined-only", cabi.LIB_PATH], capture_output=True, text=True).stdout
-    exported = set(re.findall(r" T (bm2f_(?:msda|linear|add|zero|transpose|groupnorm|sine)_[a-z0-9_]+)", out))
+    exported = set(re.findall(r" T (bm2f_(?:msda|linear|add|zero|transpose|groupnorm|sine|conv3x3|fpn)_[a-z0-9_]+)", out))
     assert set(declared) <= exported
     L = cabi.lib()
     for s in declared:
