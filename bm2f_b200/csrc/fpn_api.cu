@@ -129,14 +129,14 @@ int bm2f_conv3x3_backward_weight(const void *grad_halo, const void *x_halo, void
     int rows_per_chunk = ((rows + chunks - 1) / chunks + 31) / 32 * 32;
     chunks = (rows + rows_per_chunk - 1) / rows_per_chunk;
     if (split == 1) {
-        ConvDwParams p{};
-        p.dwk = dwk; p.rows = rows; p.rows_per_chunk = rows_per_chunk; p.wp = width + 2;
+        DwTmaParams p{};
+        p.dw = dwk; p.ld_dw = 9 * kC; p.units = 9; p.rows = rows; p.rows_per_chunk = rows_per_chunk; p.conv_wp = width + 2;
         CUtensorMap mg, mx;
         if ((rc = make_map(&mg, static_cast<const float *>(grad_halo), rows, kC, 32, 32, 2))) return rc;
         if ((rc = make_map(&mx, static_cast<const float *>(x_halo), rows, kC, 32, 32, 2))) return rc;
-        constexpr int smem = conv_dw_smem_bytes();
-        if ((rc = ensure_dynamic_smem<&conv_dw_tma_kernel>(smem, "cudaFuncSetAttribute(conv dW smem)"))) return rc;
-        conv_dw_tma_kernel<<<dim3(9, chunks), kConvDwThreads, smem, st>>>(p, mg, mx);
+        constexpr int smem = linear_dw_tma_smem_bytes();
+        if ((rc = ensure_dynamic_smem<&linear_dw_tma_kernel>(smem, "cudaFuncSetAttribute(dW TMA smem)"))) return rc;
+        linear_dw_tma_kernel<<<dim3(9, chunks), kDwTmaThreads, smem, st>>>(p, mg, mx);
     } else {
         // two 128-feature halves x 9 taps x row chunks on the transposing-producer kernel
         chunks = sms / 18;

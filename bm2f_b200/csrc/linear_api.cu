@@ -252,6 +252,37 @@ int linear_dw_common(const void *grad_y, const void *x, void *grad_weight, void 
     cudaError_t e = cudaMemsetAsync(grad_weight, 0, static_cast<size_t>(out_features) * in_features * 4, st);
     if (e == cudaSuccess && grad_bias) e = cudaMemsetAsync(grad_bias, 0, static_cast<size_t>(out_features) * 4, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(grad_weight / grad_bias)");
+    if (split == 1 && out_features % 256 == 0 && rows < (1 << 30) && aligned16(grad_y) && aligned16(x)) {
+        // single TF32 pass: both operands reach the tensor core through TMA as MN-major tiles (linear_dw_tma_kernel)
+        const int units = in_features / 256, nsl = out_features / 256;
+        int chunks = sms / (units * nsl);
+        if (chunks < 1) chunks = 1;
+        int rows_per_chunk = ((rows + chunks - 1) / chunks + 31) / 32 * 32;
+        chunks = (rows + rows_per_chunk - 1) / rows_per_chunk;
+        DwTmaParams p{};
+        p.dw = static_cast<float *>(grad_weight); p.ld_dw = in_features; p.units = units; p.rows = rows;
+        p.rows_per_chunk = rows_per_chunk; p.conv_wp = 0;
+        CUtensorMap mg, mx;
+        if ((rc = make_map(&mg, static_cast<const float *>(grad_y), rows, out_features, 32, 32, 2))) return rc;
+        if ((rc = make_map(&mx, static_cast<const float *>(x), rows, in_features, 32, 32, 2))) return rc;
+        constexpr int smem = linear_dw_tma_smem_bytes();
+        if ((rc = ensure_dynamic_smem<&linear_dw_tma_kernel>(smem, "cudaFuncSetAttribute(dW TMA smem)"))) return rc;
+        linear_dw_tma_kernel<<<dim3(units * nsl, chunks), kDwTmaThreads, smem, st>>>(p, mg, mx);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e, "launch linear_dw_tma_kernel");
+        count_launch(1);
+        if (grad_bias) {
+            int ctas = sms * 2;
+            const int rows_per_cta = (rows + ctas - 1) / ctas;
+            ctas = (rows + rows_per_cta - 1) / rows_per_cta;
+            column_sum_kernel<<<dim3(ctas, (out_features + 255) / 256), 256, 0, st>>>(
+                static_cast<const float *>(grad_y), static_cast<float *>(grad_bias), rows, out_features, rows_per_cta);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return cuda_fail(e, "launch column_sum_kernel");
+            count_launch(1);
+        }
+        return BM2F_OK;
+    }
     const int n_tiles = (out_features + 127) / 128;
     const int k_slices = in_features / 256;
     int chunks = sms / (n_tiles * k_slices);

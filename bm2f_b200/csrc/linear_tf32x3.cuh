@@ -1060,6 +1060,168 @@ static __global__ void __launch_bounds__(kDwThreads, 1) linear_dw_tf32x3_kernel(
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Weight gradient with TMA-fed MN-major operands, single TF32 pass (linear layers and the 3x3 convolution):
+//     dW[n, unit * 256 + c] = sum over rows r of G[r, n] * X[r + shift(unit), x_col0(unit) + c]
+// linear layer: unit = 256-column slice of X (shift 0); 3x3 convolution: unit = filter tap, G and X zero-haloed images,
+// shift = the tap's row shift, x_col0 = 0.  The reduction index is the ROW of both operands, i.e. both are MN-major for
+// the MMA (features contiguous, reduction strided).  tcgen05 takes MN-major TF32 operands (instruction-descriptor bits
+// 15 / 16), so the tiles go global -> shared by TMA (2-D boxes of 32 rows x 32 features) and shared -> tensor core by
+// descriptor: no transposing producer threads (linear_dw_tf32x3_kernel spends its time there).  For 32-bit MN-major
+// operands the only swizzled layout the MMA accepts is SWIZZLE_128B with 32-byte swizzle units
+// (cute::UMMA::LayoutType::SWIZZLE_128B_BASE32B = TMA's CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): canonical
+// ((32, n), (4, k)) with feature-chunk stride LBO = 4096 B (one box) and 4-row stride SBO = 512 B; one K = 8 MMA reads
+// two such 4-row atoms.
+// grid = (units x 256-row slices of dW, row chunks); CTA = a 256 x 256 block of dW: two M = 128 halves x N = 256 -> 512
+// TMEM columns.  Warp 0 TMA, warp 1 MMA, warps 2..5 epilogue (red.global.add of the partial sums; dW zeroed by the caller).
+// ------------------------------------------------------------------------------------------------------
+constexpr int kDwTmaStages = 3;
+constexpr int kDwTmaThreads = 192;
+constexpr int kDwTmaTile = 8 * 32 * 128;      // 8 feature chunks x 32 rows x 128 B = 32 KB per operand
+
+struct DwTmaParams {
+    float *dw;           // (N, ld_dw), accumulated into
+    int ld_dw;
+    int units;           // X column slices (linear) or filter taps (conv)
+    int rows;
+    int rows_per_chunk;  // multiple of 32
+    int conv_wp;         // > 0: unit = tap of a 3x3 filter over zero-haloed images of row width conv_wp
+};
+
+__device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3ffff) >> 4);          // [0,14)  start address >> 4
+    d |= static_cast<uint64_t>(4096 >> 4) << 16;                     // [16,30) leading byte offset: next 32-feature chunk
+    d |= static_cast<uint64_t>(512 >> 4) << 32;                      // [32,46) stride byte offset: next 4 reduction rows
+    d |= static_cast<uint64_t>(1) << 46;                             // [46,48) descriptor version (sm_100)
+    d |= static_cast<uint64_t>(1) << 61;                             // [61,64) layout: SWIZZLE_128B_BASE32B
+    return d;
+}
+__host__ __device__ constexpr uint32_t umma_idesc_tf32_mn(int m, int n)
+{
+    return umma_idesc_tf32(m, n) | (1u << 15) | (1u << 16);          // A and B MN-major
+}
+
+static __global__ void __launch_bounds__(kDwTmaThreads, 1)
+linear_dw_tma_kernel(const DwTmaParams p, const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_x)
+{
+    constexpr int kStageBytes = 2 * kDwTmaTile;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t full_bar[kDwTmaStages], empty_bar[kDwTmaStages], acc_bar;
+    __shared__ uint32_t tmem_base_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nslice = static_cast<int>(blockIdx.x) / p.units, unit = static_cast<int>(blockIdx.x) - nslice * p.units;
+    const int shift = p.conv_wp ? (unit / 3 - 1) * p.conv_wp + (unit % 3 - 1) : 0;
+    const int x_col0 = p.conv_wp ? 0 : unit * 256, g_col0 = nslice * 256;
+    const int r_begin = blockIdx.y * p.rows_per_chunk;
+    const int r_end = min(p.rows, r_begin + p.rows_per_chunk);
+    const int kblocks = r_end > r_begin ? (r_end - r_begin + 31) / 32 : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kDwTmaStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&acc_bar, 1);
+        fence_mbar_init();
+        tma_prefetch_desc(&tm_g);
+        tma_prefetch_desc(&tm_x);
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % kDwTmaStages;
+                mbar_wait_bounded(&empty_bar[s], ((kb / kDwTmaStages) & 1) ^ 1);
+                uint64_t *bar = &full_bar[s];
+                mbar_arrive_expect_tx(bar, kStageBytes);
+                unsigned char *g_t = smem + s * kStageBytes, *x_t = g_t + kDwTmaTile;
+                // chunks are multiples of 32 rows, so a box never reaches into the next chunk; past the last row of the
+                // tensors (and before the first, for a negative tap shift) the TMA unit fills zeros
+                const int r = r_begin + kb * 32;
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    tma_load_2d(g_t + ch * 4096, &tm_g, g_col0 + ch * 32, r, bar);
+                    tma_load_2d(x_t + ch * 4096, &tm_x, x_col0 + ch * 32, r + shift, bar);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && kblocks > 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32_mn(128, 256);
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % kDwTmaStages;
+                mbar_wait_bounded(&full_bar[s], (kb / kDwTmaStages) & 1);
+                tc_fence_after();
+                const uint32_t g_t = smem_u32(smem + s * kStageBytes), x_t = g_t + kDwTmaTile;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {               // 8 reduction rows per MMA
+                    const uint64_t db = umma_desc_mn128(x_t + k * 1024);
+                    umma_tf32(tmem_base, umma_desc_mn128(g_t + k * 1024), db, idesc, (kb | k) ? 1u : 0u);
+                    umma_tf32(tmem_base + 256, umma_desc_mn128(g_t + 4 * 4096 + k * 1024), db, idesc, (kb | k) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(&acc_bar);
+        }
+    } else if (kblocks > 0) {
+        // ---- epilogue: TMEM lane = output feature n (two halves), column = input feature c ----
+        mbar_wait_bounded(&acc_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const int n = g_col0 + half * 128 + q * 32 + lane;
+            float *dst = p.dw + static_cast<size_t>(n) * p.ld_dw + unit * 256;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 256; c0 += 32) {
+                float acc[32];
+                tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * 256 + c0, acc);
+#pragma unroll
+                for (int c = 0; c < 32; c += 4) {
+                    const float r4[4] = {acc[c], acc[c + 1], acc[c + 2], acc[c + 3]};
+                    VecIO<float, 4>::red_add(dst + c0 + c, r4);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+constexpr int linear_dw_tma_smem_bytes() { return kDwTmaStages * 2 * kDwTmaTile + 1024; }
+
+// db[c] += sum over this CTA's rows of g[r, c]  (bias gradient next to linear_dw_tma_kernel; db zeroed by the caller)
+static __global__ void __launch_bounds__(256) column_sum_kernel(const float *__restrict__ g, float *__restrict__ db, int rows,
+                                                                int cols, int rows_per_cta)
+{
+    const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+    for (int c = blockIdx.y * 256 + threadIdx.x; c < cols; c += gridDim.y * 256) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int r = r0;
+        for (; r + 3 < r1; r += 4) {
+            a0 += __ldg(g + static_cast<size_t>(r) * cols + c);
+            a1 += __ldg(g + static_cast<size_t>(r + 1) * cols + c);
+            a2 += __ldg(g + static_cast<size_t>(r + 2) * cols + c);
+            a3 += __ldg(g + static_cast<size_t>(r + 3) * cols + c);
+        }
+        for (; r < r1; ++r) a0 += __ldg(g + static_cast<size_t>(r) * cols + c);
+        atomicAdd(db + c, (a0 + a1) + (a2 + a3));
+    }
+}
+
 constexpr int linear_dw_smem_bytes() { return kGemmStages * (2 * 128 * 128 + 2 * kDwNB * 128) + 1024; }
 
 template <int NT, int NH>

@@ -235,7 +235,7 @@ def test_fused_fpn_tail_runs_on_own_kernels(msda):
     bad = [k for k in names if not k.startswith(("bm2f::", "void bm2f::")) and
            any(s in k.lower() for s in ("cudnn", "implicit_convolve", "upsample", "group_norm", "xmma", "conv2d", "cutlass"))]
     assert not bad, bad
-    assert any("conv_dw_tma_kernel" in k for k in names) and any("fpn_merge_forward_kernel" in k for k in names)
+    assert any("linear_dw_tma_kernel" in k for k in names) and any("fpn_merge_forward_kernel" in k for k in names)
     dec.fused = False                      # FPN tail and glue on torch's library kernels, same weights
     want = run()
     # both sides single-pass TF32 with different summation orders; a ReLU input within that noise of zero takes the other

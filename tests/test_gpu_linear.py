@@ -156,3 +156,24 @@ def test_backward_input_accumulate_matches_fp64(msda, rows, out_features):
     same = msda.linear_tf32x3_backward_input_accumulate(g, w, acc, True, 3)
     assert same.data_ptr() == acc.data_ptr()
     assert torch.equal(acc, out)
+
+
+@pytest.mark.parametrize("out_features,in_features", [(256, 256), (256, 1024), (1024, 256), (512, 512), (192, 256)])
+@pytest.mark.parametrize("rows", [1, 31, 1000, 32 * 148 * 3 + 5])
+def test_linear_backward_weight_single_pass_tma(msda, out_features, in_features, rows):
+    """split = 1 with a 256-multiple output width runs linear_dw_tma_kernel (both operands MN-major through TMA, bias
+    gradient by column_sum_kernel); other widths (192) stay on the transposing-producer kernel.  Compared with float64 at
+    the TF32 single-pass tolerance, relative to the largest entry."""
+    torch.manual_seed(out_features + in_features + rows)
+    dev = torch.device("cuda:0")
+    g = torch.randn(rows, out_features, device=dev)
+    x = torch.randn(rows, in_features, device=dev)
+    ref_w = g.double().t() @ x.double()
+    ref_b = g.double().sum(0)
+    gw, gb = msda.linear_tf32x3_backward_weight(g, x, 1, True)
+    assert gw.shape == (out_features, in_features) and gb.shape == (out_features,)
+    assert (gw.double() - ref_w).abs().max().item() / ref_w.abs().max().item() <= 3e-3
+    # bias gradient: fp32 column sums next to the TMA kernel, a TF32 ones-row MMA in the transposing-producer kernel
+    assert (gb.double() - ref_b).abs().max().item() / ref_b.abs().max().item() <= (1e-5 if out_features % 256 == 0 else 3e-3)
+    gw3, _ = msda.linear_tf32x3_backward_weight(g, x, 3, False)
+    assert (gw3.double() - ref_w).abs().max().item() / ref_w.abs().max().item() <= 2e-5

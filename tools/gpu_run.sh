@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 for step in "$@"; do
 case $step in
-  fpn)      echo "== fpn kernel tests"; timeout 900 python -m pytest tests/test_gpu_fpn.py -q --timeout 600 2>&1 | tail -15 ;;
+  fpn)      echo "== fpn + linear kernel tests"; timeout 900 python -m pytest tests/test_gpu_fpn.py tests/test_gpu_linear.py -q --timeout 600 2>&1 | tail -15 ;;
   decoder)  echo "== decoder tests"; timeout 1200 python -m pytest tests/test_gpu_decoder.py tests/test_gpu_fpn.py -x -q --timeout 600 2>&1 | tail -15 ;;
   suite)    echo "== full gpu suite"; timeout 2400 python -m pytest tests -m gpu -x -q --timeout 900 > gpurun_out/pytest_gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu.log ;;
   smoke)    echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 ;;
