@@ -25,7 +25,7 @@ SYMBOLS = (
     "bm2f_linear_backward_input_masked", "bm2f_linear_backward_input_accumulate", "bm2f_add_layernorm_forward",
     "bm2f_add_layernorm_backward", "bm2f_zero_masked_rows", "bm2f_transpose_batched",
     "bm2f_groupnorm_tokens_workspace_bytes", "bm2f_groupnorm_tokens_forward", "bm2f_groupnorm_tokens_backward",
-    "bm2f_sine_position_embedding", "bm2f_conv3x3_workspace_bytes", "bm2f_conv3x3_forward", "bm2f_conv3x3_backward_input",
+    "bm2f_sine_position_embedding", "bm2f_conv3x3_workspace_bytes", "bm2f_conv3x3_set_variant", "bm2f_conv3x3_forward", "bm2f_conv3x3_backward_input",
     "bm2f_conv3x3_backward_weight", "bm2f_groupnorm_tokens_stats", "bm2f_fpn_merge_forward", "bm2f_fpn_upsample_backward",
     "bm2f_groupnorm_relu_tokens_apply", "bm2f_groupnorm_relu_tokens_backward",
 )

@@ -9,6 +9,7 @@ using namespace bm2f::host;
 
 namespace {
 constexpr int kC = kFpnC;
+int g_conv_pair_tiles = 1;      // A/B: bm2f_conv3x3_set_variant(0) = one row tile per weight k-block
 
 int check_device(int *sms)
 {
@@ -44,8 +45,16 @@ int launch_conv_gemm(const float *x_halo, const float *w_hi, const float *w_lo, 
     if ((rc = make_map(&ml, w_lo, kC, 9 * kC, kC, kGemmBlockK, true))) return rc;
     if ((rc = make_map(&mx, x_halo, p.M, kC, kGemmBlockM, kGemmBlockK, true))) return rc;
     const int tiles = (p.M + kGemmBlockM - 1) / kGemmBlockM;
-    const int grid = tiles < sms ? tiles : sms;
-    if (split == 1) {
+    int grid = tiles < sms ? tiles : sms;
+    if (split == 1 && g_conv_pair_tiles) {
+        // two row tiles per weight k-block (RT = 2)
+        constexpr auto kern = &linear_tf32x3_persistent_kernel<256, 1, kGemmProducerWarps, 3, false, true, true, 2>;
+        constexpr int smem = linear_conv2_smem_bytes<256>();
+        if ((rc = ensure_dynamic_smem<kern>(smem, "cudaFuncSetAttribute(conv3x3 smem)"))) return rc;
+        const int pairs = (tiles + 1) / 2;
+        grid = pairs < sms ? pairs : sms;
+        kern<<<grid, kGemmThreadsPersistent, smem, st>>>(p, mh, mh, mx, mx);
+    } else if (split == 1) {
         constexpr auto kern = &linear_tf32x3_persistent_kernel<256, 1, kGemmProducerWarps, 3, false, true, true>;
         constexpr int smem = linear_xtma_smem_bytes<256>();
         if ((rc = ensure_dynamic_smem<kern>(smem, "cudaFuncSetAttribute(conv3x3 smem)"))) return rc;
@@ -87,6 +96,12 @@ int conv_common(const void *x_halo, const void *weight, void *y, void *workspace
 }  // namespace
 
 extern "C" {
+
+int bm2f_conv3x3_set_variant(int pair_tiles)
+{
+    g_conv_pair_tiles = pair_tiles ? 1 : 0;
+    return BM2F_OK;
+}
 
 size_t bm2f_conv3x3_workspace_bytes(int out_channels, int in_channels)
 {

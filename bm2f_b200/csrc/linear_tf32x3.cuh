@@ -460,7 +460,12 @@ constexpr int kXtmaStages = 4;
 // XTMA (single TF32 pass only): the activation tile needs no hi/lo split, so it is TMA-loaded straight into the MMA
 // stage like the weights (the tensor core ignores the low 13 mantissa bits); the producer warps idle and the freed
 // shared memory holds four stages.
-template <int NT, int CL = 1, int PW = kGemmProducerWarps, int XD = 3, bool PAIR = false, bool XTMA = false, bool CONV = false>
+// RT = 2 (XTMA + CONV only): two row tiles share every weight k-block — both accumulators are filled side by side, the
+// weight stream out of L2 and the weight writes into shared memory halve per MMA (the 3 x 3 convolution re-reads 2.4 MB
+// of weights per tile and is bound by exactly that); the epilogue of a tile pair is then not overlapped with MMAs (4 us
+// after a 39 us main loop of 72 k-blocks).
+template <int NT, int CL = 1, int PW = kGemmProducerWarps, int XD = 3, bool PAIR = false, bool XTMA = false, bool CONV = false,
+          int RT = 1>
 __global__ void __launch_bounds__(gemm_threads_persistent(PW), 1)
 linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CUtensorMap tm_whi,
                                 const __grid_constant__ CUtensorMap tm_wlo, const __grid_constant__ CUtensorMap tm_y,
@@ -471,10 +476,11 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
     static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
     static_assert(!XTMA || (CL == 1 && !PAIR), "XTMA: single CTAs");
     static_assert(!CONV || (CL == 1 && !PAIR), "CONV: single CTAs");
-    constexpr int kStages = XTMA ? kXtmaStages : PAIR ? kPairStages : kGemmStages;
+    static_assert(RT == 1 || (RT == 2 && XTMA && CONV), "two row tiles per weight block: TMA-loaded convolution only");
+    constexpr int kStages = RT == 2 ? 3 : XTMA ? kXtmaStages : PAIR ? kPairStages : kGemmStages;
     constexpr int kWBytes = (PAIR ? N / 2 : N) * kGemmBlockK * 4;   // PAIR: this CTA's half of the weight k-block
     constexpr int kSlots = XTMA ? 1 : 2;                            // hi (+ lo) tiles per operand and stage
-    constexpr int kStageBytes = kSlots * kXBytes + kSlots * kWBytes;
+    constexpr int kStageBytes = RT * kSlots * kXBytes + kSlots * kWBytes;
     constexpr uint32_t kTmemCols = (2 * N <= 64) ? 64 : (2 * N <= 128) ? 128 : (2 * N <= 256) ? 256 : 512;
     static_assert(NT % 16 == 0 && NT <= 256, "UMMA N for M = 128, two accumulators in 512 TMEM columns");
 
@@ -491,7 +497,7 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
     // the cluster (CL CTAs) walks virtual tiles = (group of CL row tiles, slice); CTA `crank` owns row tile group * CL + crank
     const int crank = CL > 1 ? static_cast<int>(blockIdx.x) % CL : 0;
     const int cid = static_cast<int>(blockIdx.x) / CL, ncl = static_cast<int>(gridDim.x) / CL;
-    const int row_tiles = (p.M + kGemmBlockM - 1) / kGemmBlockM;
+    const int row_tiles = (p.M + RT * kGemmBlockM - 1) / (RT * kGemmBlockM);      // RT = 2: pairs of row tiles
     const int num_tiles = ((row_tiles + CL - 1) / CL) * slices;   // tile = row_tile_group * slices + slice
     // (row tile, slice) of a tile index advance incrementally: an integer division per tile / k-block in the
     // single-threaded TMA and MMA roles costs ~200 cycles of latency each and made this kernel 1.7x slower (measured)
@@ -545,11 +551,13 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
                     const int s = g % kStages;
                     mbar_wait_bounded(&empty_bar[s], ((g / kStages) & 1) ^ 1);
                     uint64_t *tbar = &full_bar[s];
-                    mbar_arrive_expect_tx(tbar, XTMA ? kWBytes + kXBytes : p.split == 3 ? 2 * kWBytes : kWBytes);
+                    mbar_arrive_expect_tx(tbar, XTMA ? kWBytes + RT * kXBytes : p.split == 3 ? 2 * kWBytes : kWBytes);
                     if (XTMA) {    // rows past M (CONV: also before row 0) are zero-filled by the TMA unit
                         if (CONV) {
-                            tma_load_2d(stage_ptr(s), &tm_x, kc * kGemmBlockK,
-                                        ti.rt * kGemmBlockM + tdy * (p.conv_w + 2) + tdx, tbar);
+#pragma unroll
+                            for (int t = 0; t < RT; ++t)
+                                tma_load_2d(stage_ptr(s) + t * kXBytes, &tm_x, kc * kGemmBlockK,
+                                            (ti.rt * RT + t) * kGemmBlockM + tdy * (p.conv_w + 2) + tdx, tbar);
                             if (++kc == p.ldx / kGemmBlockK) {
                                 kc = 0;
                                 if (++tdx == 2) { tdx = -1; ++tdy; }
@@ -558,7 +566,7 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
                             tma_load_2d(stage_ptr(s), &tm_x, kb * kGemmBlockK, (ti.rt * CL + crank) * kGemmBlockM, tbar);
                         }
                     }
-                    unsigned char *w_hi = stage_ptr(s) + kSlots * kXBytes;
+                    unsigned char *w_hi = stage_ptr(s) + RT * kSlots * kXBytes;
                     if (CL == 1) {
                         tma_load_2d(w_hi, &tm_whi, kb * kGemmBlockK, wrow, tbar);
                         if (p.split == 3) tma_load_2d(w_hi + kWBytes, &tm_wlo, kb * kGemmBlockK, wrow, tbar);
@@ -631,8 +639,13 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
             constexpr uint32_t idesc = umma_idesc_tf32(kGemmBlockM, NT);
             int g = 0, i = 0;
             for (int tile = cid; tile < num_tiles; tile += ncl, ++i) {
-                const int b = i & 1;
-                mbar_wait_bounded(&acc_empty[b], ((i >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
+                const int b = RT == 2 ? 0 : i & 1;
+                if (RT == 2) {                                              // both accumulators belong to this tile pair
+                    mbar_wait_bounded(&acc_empty[0], (i & 1) ^ 1);
+                    mbar_wait_bounded(&acc_empty[1], (i & 1) ^ 1);
+                } else {
+                    mbar_wait_bounded(&acc_empty[b], ((i >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+                }
                 tc_fence_after();
                 const uint32_t d = tmem_base + b * NT;
                 for (int kb = 0; kb < kKBlocks; ++kb, ++g) {
@@ -641,7 +654,7 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
                     tc_fence_after();
                     const uint32_t x_hi = smem_u32(stage_ptr(s));
                     const uint32_t x_lo = x_hi + kXBytes;
-                    const uint32_t w_hi = x_hi + kSlots * kXBytes;
+                    const uint32_t w_hi = x_hi + RT * kSlots * kXBytes;
                     const uint32_t w_lo = w_hi + kWBytes;
 #pragma unroll
                     for (int k = 0; k < kGemmBlockK / 8; ++k) {
@@ -649,6 +662,7 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
                         const uint64_t a_hi = umma_desc_k128(x_hi + koff);
                         const uint64_t b_hi = umma_desc_k128(w_hi + koff);
                         umma_tf32(d, a_hi, b_hi, idesc, (kb | k) ? 1u : 0u);
+                        if (RT == 2) umma_tf32(d + NT, umma_desc_k128(x_hi + kXBytes + koff), b_hi, idesc, (kb | k) ? 1u : 0u);
                         if (p.split == 3) {
                             umma_tf32(d, umma_desc_k128(x_lo + koff), b_hi, idesc, 1u);
                             umma_tf32(d, a_hi, umma_desc_k128(w_lo + koff), idesc, 1u);
@@ -658,6 +672,7 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
                     else umma_commit_multicast(&empty_bar[s], (1u << CL) - 1);
                 }
                 umma_commit(&acc_full[b]);
+                if (RT == 2) umma_commit(&acc_full[1]);
             }
         }
     } else if (warp < 2 + PW) {
@@ -733,8 +748,9 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
         const int q = warp & 3;
         int i = 0, chunk = 0;
         for (TileIter ti = first_tile(); ti.tile < num_tiles; next_tile(ti), ++i) {
-            const int b = i & 1;
-            const int rt_own = ti.rt * CL + crank;              // this CTA's row tile of the group
+          for (int sub = 0; sub < RT; ++sub) {                  // RT = 2: the two row tiles of the pair, one accumulator each
+            const int b = RT == 2 ? sub : i & 1;
+            const int rt_own = RT == 2 ? ti.rt * 2 + sub : ti.rt * CL + crank;      // this CTA's row tile of the group
             // CONV: the 8 rows this lane stores per 32-column chunk, as rows of the dense image (-1: halo or past the end)
             int conv_row[8];
             if (CONV) {
@@ -748,7 +764,7 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
                                        ? (img * p.conv_h + yp - 1) * p.conv_w + xp - 1 : -1;
                 }
             }
-            mbar_wait_bounded(&acc_full[b], (i >> 1) & 1);
+            mbar_wait_bounded(&acc_full[b], RT == 2 ? i & 1 : (i >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
             for (int c0 = 0; c0 < N; c0 += 32, ++chunk) {
@@ -825,6 +841,7 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
                     __syncwarp();
                 }
             }
+          }
         }
         if (lane == 0 && p.store_mode == 0 && !CONV) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
@@ -848,6 +865,13 @@ template <int NT>
 constexpr int linear_xtma_smem_bytes()
 {
     return kXtmaStages * (kGemmBlockM * kGemmBlockK * 4 + NT * kGemmBlockK * 4) + 2 * kGemmBlockM * kGemmBlockK * 4 + 1024;
+}
+
+// RT = 2 convolution: 3 stages of (2 activation tiles + one weight k-block) + the epilogue staging tiles
+template <int NT>
+constexpr int linear_conv2_smem_bytes()
+{
+    return 3 * (2 * kGemmBlockM * kGemmBlockK * 4 + NT * kGemmBlockK * 4) + 2 * kGemmBlockM * kGemmBlockK * 4 + 1024;
 }
 
 template <int NT>

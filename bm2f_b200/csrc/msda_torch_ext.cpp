@@ -723,6 +723,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("groupnorm_tokens_forward", &groupnorm_tokens_forward, "GroupNorm(32, 256) on token rows, written into the encoder input");
     m.def("groupnorm_tokens_backward", &groupnorm_tokens_backward);
     m.def("conv3x3_tokens_forward", &conv3x3_tokens_forward, "3x3 conv (256 -> 256, padding 1) of a zero-haloed token image on tcgen05");
+    m.def("conv3x3_set_variant", [](int pair_tiles) { bm2f_conv3x3_set_variant(pair_tiles); },
+          "A/B: 1 (default) two row tiles per weight k-block, 0 one");
     m.def("conv3x3_tokens_backward_input", &conv3x3_tokens_backward_input);
     m.def("conv3x3_tokens_backward_weight", &conv3x3_tokens_backward_weight);
     m.def("groupnorm_tokens_stats", &groupnorm_tokens_stats);

@@ -317,6 +317,9 @@ int bm2f_sine_position_embedding(void *out, int height, int width, int num_pos_f
  *   bm2f_groupnorm_tokens_workspace_bytes(batch).
  */
 size_t bm2f_conv3x3_workspace_bytes(int out_channels, int in_channels);
+/* A/B only (process-wide, like bm2f_linear_set_tuning): 1 (default) = the single-pass kernel shares every weight k-block
+ * between two row tiles, 0 = one row tile per weight k-block.  Same results. */
+int bm2f_conv3x3_set_variant(int pair_tiles);
 int bm2f_conv3x3_forward(const void *x_halo, const void *weight, void *y, void *workspace, int batch, int height, int width,
                          int out_channels, int in_channels, int split, void *stream);
 int bm2f_conv3x3_backward_input(const void *grad_halo, const void *weight, void *grad_x, void *workspace, int batch,

@@ -117,3 +117,20 @@ def test_groupnorm_relu_tokens(msda, batch, h, w):
     assert frac_ok > 0.999
     assert _rel(gh[:, 1:-1, 1:-1].permute(0, 3, 1, 2), yd.grad) < 1e-3     # a flipped branch changes the group sums slightly
     assert _rel(dgamma, gd.grad) < 1e-3 and _rel(dbeta, bd.grad) < 1e-3
+
+
+@pytest.mark.parametrize("batch,h,w", [(2, 5, 7), (2, 33, 40), (1, 12, 130)])
+def test_conv3x3_tile_pair_variant_is_bit_identical(msda, batch, h, w):
+    """The default single-pass kernel shares each weight k-block between two row tiles (RT = 2); per tile the MMA order is
+    the one of the one-tile kernel, so the results are identical — also when the last pair has only one tile."""
+    dev = torch.device("cuda:0")
+    torch.manual_seed(w)
+    xh = _halo(torch.randn(batch, h, w, 256, device=dev))
+    wgt = torch.randn(256, 256, 3, 3, device=dev) / 48.0
+    y2 = msda.conv3x3_tokens_forward(xh, wgt, 1)
+    msda.conv3x3_set_variant(0)
+    try:
+        y1 = msda.conv3x3_tokens_forward(xh, wgt, 1)
+    finally:
+        msda.conv3x3_set_variant(1)
+    assert torch.equal(y1, y2)

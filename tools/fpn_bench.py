@@ -67,6 +67,31 @@ print("fused vs reference sequence: mask_features %.2e  grad res2 %.2e  grad enc
 tf, tr = timeit(fused), timeit(reference)
 print(f"FPN tail fwd+bwd: fused sm_100a {tf:.2f} ms | reference sequence (cuDNN / ATen) {tr:.2f} ms | x{tr / tf:.2f}")
 
+# the 3x3 convolution alone: two row tiles per weight k-block (default) vs one
+import bm2f_b200
+MSDA = bm2f_b200.load_extension()
+xh = torch.randn(n, H + 2, Wd + 2, 256, device=dev)
+def t_kernel(fn):
+    fn(); fn(); torch.cuda.synchronize(); best = 1e9
+    for _ in range(args.reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize(); best = min(best, a.elapsed_time(b))
+    return best
+flop = 2.0 * n * H * Wd * 256 * 256 * 9
+for sp in (1, 3):
+    t2 = t_kernel(lambda: MSDA.conv3x3_tokens_forward(xh, outc.weight.detach(), sp))
+    MSDA.conv3x3_set_variant(0)
+    t1 = t_kernel(lambda: MSDA.conv3x3_tokens_forward(xh, outc.weight.detach(), sp))
+    MSDA.conv3x3_set_variant(1)
+    print(f"conv3x3 forward split {sp}: default {t2:.3f} ms ({flop / t2 * 1e-9:.0f} TFLOP/s) | one row tile per weight block {t1:.3f} ms")
+tw = t_kernel(lambda: MSDA.conv3x3_tokens_backward_weight(xh, xh, 1))
+print(f"conv3x3 grad_W split 1 (TMA, MN-major): {tw:.3f} ms ({flop / tw * 1e-9:.0f} TFLOP/s)")
+xn = torch.randn(n, 256, H, Wd, device=dev)
+tc = t_kernel(lambda: F.conv2d(xn, outc.weight.detach(), padding=1))
+xcl = xn.contiguous(memory_format=torch.channels_last)
+tcl = t_kernel(lambda: F.conv2d(xcl, outc.weight.detach(), padding=1))
+print(f"cuDNN conv2d forward (allow_tf32={bool(args.tf32)}): NCHW {tc:.3f} ms | channels_last {tcl:.3f} ms")
+
 from torch.profiler import profile, ProfilerActivity
 for name, fn in (("fused", fused), ("reference", reference)):
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
