@@ -16,7 +16,7 @@ constexpr int kCells = 8192;      // 16-bit anchor cells per chunk (16 KB)
 
 std::atomic<long long *> g_prof{nullptr};     // diagnostics: bm2f_msda_debug_phase_profile
 
-template <int L_, int RMAX, int NWARP, int LPP, bool FUSED, int CPS, bool PIPE>
+template <int L_, int RMAX, int NWARP, int LPP, bool FUSED, int CPS, int PIPE>
 int launch(const FastParams &p, int marg, const CUtensorMap &ml, const CUtensorMap &mw, const CUtensorMap &mg, int sms,
            long long est_jobs, cudaStream_t st)
 {
@@ -95,6 +95,11 @@ int pick(const FastParams &p, int marg, int lanes, int variant, const CUtensorMa
         case 44: BM2F_V(12, 4, 1, true, 9);
         case 58: BM2F_V(16, 8, 1, false, 8);
         case 54: BM2F_V(16, 4, 1, false, 8);
+        case 134: BM2F_V(8, 4, 2, 2, RMAX);      // 13..16: phase 2 by cell ownership (PIPE = 2 / 3)
+        case 138: BM2F_V(8, 8, 2, 2, RMAX);
+        case 144: BM2F_V(8, 4, 2, 3, RMAX);
+        case 154: BM2F_V(16, 4, 1, 2, 8);
+        case 164: BM2F_V(16, 4, 1, 3, 8);
         default: break;
         }
     }

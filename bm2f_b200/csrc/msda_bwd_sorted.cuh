@@ -255,7 +255,10 @@ __device__ __forceinline__ int sorted_block_scan(uint32_t *cnt, int n, uint32_t 
 
 constexpr int kSortedSkip = -1;       // record already final ({ga, gx, gy, a}); not in the sorted list
 
-template <int L_, int RMAX, int NWARP, int LPP, bool FUSED, int CELLS_MAX, int CPS, bool PIPE>
+// PIPE: 0 lane groups walk equal ranges of the sorted list, 1 same with the next anchor's lines prefetched,
+// 2 lane group g owns the cells g, g + G, g + 2 G, ... (whole anchor runs; every group gets the same mix of coarse- and
+// fine-level cells, so the groups finish together), 3 same with the next own cell's lines prefetched
+template <int L_, int RMAX, int NWARP, int LPP, bool FUSED, int CELLS_MAX, int CPS, int PIPE>
 __global__ void __launch_bounds__(NWARP * 32, CPS)
 msda_bwd_sorted_kernel(const FastParams p, const int marg, long long *prof_out, const __grid_constant__ CUtensorMap tm_loc,
                        const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_go)
@@ -538,8 +541,12 @@ msda_bwd_sorted_kernel(const FastParams p, const int marg, long long *prof_out, 
             const int g = warp * GPW + lg;
             int i = static_cast<int>((static_cast<long long>(nsorted) * g) / G);
             const int iend = static_cast<int>((static_cast<long long>(nsorted) * (g + 1)) / G);
-            const float *vb = vbm + sub * CH;
-            float *gb = gbm + sub * CH;
+            // channel ownership: the lane's n-th float4 is channels n * 4 * LPP + sub * 4 .. + 3, so that ONE load / RED
+            // instruction of the group covers LPP * 16 contiguous bytes = whole 32-byte sectors (with 8 consecutive channels
+            // per lane every instruction touched all four sectors of the line and filled half of each)
+            constexpr int CSTR = 4 * LPP;
+            const float *vb = vbm + sub * 4;
+            float *gb = gbm + sub * 4;
             int cur = kSortedSkip, cmask = 0, cW = 0;
             long long e00 = 0;
             float acc[4][CH], v[4][CH];
@@ -556,7 +563,7 @@ msda_bwd_sorted_kernel(const FastParams p, const int marg, long long *prof_out, 
 #pragma unroll
                         for (int n = 0; n < NV; ++n) {
                             const float rv[4] = {acc[k][4 * n], acc[k][4 * n + 1], acc[k][4 * n + 2], acc[k][4 * n + 3]};
-                            VecIO<float, 4>::red_add(dst + 4 * n, rv);
+                            VecIO<float, 4>::red_add(dst + CSTR * n, rv);
                         }
                     }
 #pragma unroll
@@ -580,7 +587,7 @@ msda_bwd_sorted_kernel(const FastParams p, const int marg, long long *prof_out, 
 #pragma unroll
                     for (int n = 0; n < NV; ++n) {
                         float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if ((mask >> k) & 1) t4 = __ldg(reinterpret_cast<const float4 *>(srcp) + n);
+                        if ((mask >> k) & 1) t4 = __ldg(reinterpret_cast<const float4 *>(srcp + CSTR * n));
                         dst[k][4 * n] = t4.x; dst[k][4 * n + 1] = t4.y; dst[k][4 * n + 2] = t4.z; dst[k][4 * n + 3] = t4.w;
                     }
                 }
@@ -591,7 +598,7 @@ msda_bwd_sorted_kernel(const FastParams p, const int marg, long long *prof_out, 
                 float go[CH];
 #pragma unroll
                 for (int n = 0; n < NV; ++n) {
-                    const float4 t4 = *reinterpret_cast<const float4 *>(s_go + qi * D + sub * CH + 4 * n);
+                    const float4 t4 = *reinterpret_cast<const float4 *>(s_go + qi * D + sub * 4 + CSTR * n);
                     go[4 * n] = t4.x; go[4 * n + 1] = t4.y; go[4 * n + 2] = t4.z; go[4 * n + 3] = t4.w;
                 }
                 const float a = rec.x, lh = rec.y, lw = rec.z;
@@ -621,7 +628,70 @@ msda_bwd_sorted_kernel(const FastParams p, const int marg, long long *prof_out, 
                 if (sub == 0) s_rec[pt] = make_float4(pa, a * px, a * py, a);
             };
 
-            if constexpr (PIPE) {
+            if constexpr (PIPE == 2 || PIPE == 3) {
+                // cell-strided ownership: the exclusive prefix sums left in the cell table by the scan give every cell's
+                // run [off, end) of the sorted list; all points of a run share one anchor (and its corner mask)
+                auto run_of = [&](int cell, int &off, int &end) {
+                    off = static_cast<int>(cell_offset<NW>(s_cnt, cell));
+                    end = cell + 1 < ncells ? static_cast<int>(cell_offset<NW>(s_cnt, cell + 1)) : nsorted;
+                };
+                if constexpr (PIPE == 2) {
+                    for (int cell = g; cell < ncells; cell += G) {
+                        int off, end;
+                        run_of(cell, off, end);
+                        if (end <= off) continue;
+                        cur = __float_as_int(s_rec[s_perm[off]].w);
+                        decode(cur, cmask, cW, e00);
+                        load_lines(v, cmask, cW, e00);
+                        for (int k = off; k < end; ++k) {
+                            const int pt = s_perm[k];
+                            process(pt, s_rec[pt]);
+                        }
+                        flush();
+                    }
+                } else {
+                    // next non-empty own cell at or after `cell`
+                    auto next_run = [&](int cell, int &off, int &end) {
+                        for (; cell < ncells; cell += G) {
+                            run_of(cell, off, end);
+                            if (end > off) return cell;
+                        }
+                        return ncells;
+                    };
+                    int off, end;
+                    int cell = next_run(g, off, end);
+                    if (cell < ncells) {
+                        cur = __float_as_int(s_rec[s_perm[off]].w);
+                        decode(cur, cmask, cW, e00);
+                        load_lines(v, cmask, cW, e00);
+                    }
+                    while (cell < ncells) {
+                        int noff = 0, nend = 0;
+                        const int ncell = next_run(cell + G, noff, nend);
+                        float vn[4][CH];
+                        int nmask = 0, nW = 0, npacked = kSortedSkip;
+                        long long ne = 0;
+                        if (ncell < ncells) {                 // request the next run's lines before working on this one
+                            npacked = __float_as_int(s_rec[s_perm[noff]].w);
+                            decode(npacked, nmask, nW, ne);
+                            load_lines(vn, nmask, nW, ne);
+                        }
+                        for (int k = off; k < end; ++k) {
+                            const int pt = s_perm[k];
+                            process(pt, s_rec[pt]);
+                        }
+                        flush();
+                        if (ncell < ncells) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                                for (int c = 0; c < CH; ++c) v[k][c] = vn[k][c];
+                            cur = npacked; cmask = nmask; cW = nW; e00 = ne;
+                        }
+                        cell = ncell; off = noff; end = nend;
+                    }
+                }
+            } else if constexpr (PIPE == 1) {
                 // the value lines of the NEXT anchor are requested while the current point is processed: the global
                 // (L2) latency of an anchor change is overlapped instead of stalling the group at every change
                 if (i < iend) {

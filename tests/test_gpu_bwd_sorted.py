@@ -65,7 +65,7 @@ def test_sorted_backward_level_counts_and_ragged_shapes(levels, dist, built):
     check_f32(res, ref, inp["loc"].numpy(), inp["shapes"].numpy(), f"{levels} {dist}")
 
 
-@pytest.mark.parametrize("variant", [0, 6, 8, 9, 10, 11, 12])
+@pytest.mark.parametrize("variant", [0, 6, 8, 9, 10, 11, 12, 13, 14, 15, 16])
 @pytest.mark.parametrize("cfg,batch,dist", [(1, 1, "model"), (1, 1, "uniform"), (2, 2, "model"), (4, 1, "model"),
                                             (5, 4, "model")])
 def test_sorted_backward_config_shapes_vs_oracle(cfg, batch, dist, variant, built):
@@ -76,7 +76,7 @@ def test_sorted_backward_config_shapes_vs_oracle(cfg, batch, dist, variant, buil
     check_f32(res, ref, inp["loc"].numpy(), inp["shapes"].numpy(), f"cfg{cfg} variant {variant}")
 
 
-@pytest.mark.parametrize("variant", [6, 8, 9, 10, 11, 12])
+@pytest.mark.parametrize("variant", [6, 8, 9, 10, 11, 12, 13, 14])
 @pytest.mark.parametrize("margin", [0, 1, 3, 64])
 def test_pixel_owner_backward_vs_oracle(variant, margin, small_problem, built):
     inp, ref = small_problem
@@ -88,7 +88,7 @@ def test_pixel_owner_backward_vs_oracle(variant, margin, small_problem, built):
 @pytest.mark.parametrize("levels", [((1, 1), (3, 2), (25, 38)), ((2, 70), (4, 140), (1, 35)), ((33, 31), (5, 9), (17, 64))],
                          ids=["one_pixel_level", "wide_strips", "unordered_sizes"])
 @pytest.mark.parametrize("dist", ["model", "uniform"])
-@pytest.mark.parametrize("variant", [8, 10])
+@pytest.mark.parametrize("variant", [8, 10, 13, 14])
 def test_pixel_owner_backward_ragged_shapes(levels, dist, variant, built):
     inp = W.make_inputs(levels, 2, seed=400 + levels[0][0], dist=dist)
     ref = oracle_ref(inp)

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--dist", default="model")
+    ap.add_argument("--set", default="owner", help="owner: pixel-owner variants; cells: cell-strided phase 2 (variants 13-16 of the sorted kernel)")
     args = ap.parse_args()
     wl = W.WORKLOADS[args.cfg]
     dev = torch.device("cuda:0")
@@ -47,9 +48,15 @@ def main():
     med, ref = bwd(cabi.make_tuning(bwd=1))
     print(f"per-corner (bwd=1)              {med:7.3f} ms")
     cases = [("sorted lanes=4 margin 6", dict(bwd=2, bwd_lanes=4, bwd_margin=6))]
-    for v in (10, 11):
-        for m in (4, 5, 6):
-            cases.append((f"owner variant {v} margin {m}", dict(bwd=2, bwd_margin=m, variant=v)))
+    if args.set == "owner":
+        for v in (10, 11):
+            for m in (4, 5, 6):
+                cases.append((f"owner variant {v} margin {m}", dict(bwd=2, bwd_margin=m, variant=v)))
+    else:
+        # sorted kernel, phase 2 by cell ownership: 13 = 2 CTAs x 8 warps, 14 = + prefetch, 15 = 1 CTA x 16 warps, 16 = + prefetch
+        for v, lanes in ((13, 4), (13, 8), (14, 4), (15, 4), (16, 4)):
+            for m in ((6, 5, 8) if v in (13, 14) and lanes == 4 else (6,)):
+                cases.append((f"cell-strided v{v} lanes {lanes} margin {m}", dict(bwd=2, bwd_lanes=lanes, bwd_margin=m, variant=v)))
     for name, kw in cases:
         med, got = bwd(cabi.make_tuning(**kw))
         errs = [((a - b).abs().max() / b.abs().max()).item() for a, b in zip(got, ref)]

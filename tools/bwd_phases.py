@@ -51,7 +51,7 @@ def main():
     print(f"# cfg{args.cfg} batch {N} S={S} margin {args.margin}; cycles of thread 0 per CTA, mean over CTAs, in k-cycles")
     print(f"{'variant':>8} {'lanes':>5} {'ms':>7} | " + " ".join(f"{n:>13}" for n in PHASES) + f" {'total':>9} {'pts/CTA':>9}")
     for v in (int(x) for x in args.variants.split(",")):
-        for lanes in ((8, 4) if v < 6 else (0,)):
+        for lanes in ((8, 4) if v < 6 else (4,) if v >= 13 else (0,)):
             t = cabi.make_tuning(bwd=2, bwd_lanes=lanes, bwd_margin=args.margin, variant=v)
             cabi.lib().bm2f_msda_debug_phase_profile(0)
             run(t); run(t)

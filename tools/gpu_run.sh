@@ -13,6 +13,9 @@ case $step in
             timeout 600 python bench.py --batch 2 --no-e2e --no-cpu --no-ref-cuda --steps 10 --warmup 3 --graph 2>/dev/null | tee -a gpurun_out/r02_bench_batch2_n1.jsonl | cut -c1-330 ;;
   decbench) echo "== decoder bench"; timeout 900 python tools/decoder_bench.py 2>&1 | tee gpurun_out/r02_decoder_bench.txt | tail -30 ;;
   fpnbench) echo "== fpn bench"; timeout 900 python tools/fpn_bench.py 2>&1 | tee gpurun_out/r02_fpn_bench.txt | tail -40 ;;
+  bwdcells) echo "== backward: cell-strided phase 2 A/B"; timeout 900 python -m pytest tests/test_gpu_bwd_sorted.py -x -q --timeout 600 2>&1 | tail -3
+            timeout 600 python tools/bwd_ab2.py --set cells --reps 5 2>&1 | tee gpurun_out/r02_bwd_cells_ab.txt
+            timeout 600 python tools/bwd_phases.py --variants 0,13,14,15,16 2>&1 | tee gpurun_out/r02_bwd_cells_phases.txt ;;
   *) echo "unknown step $step" ;;
 esac
 done
