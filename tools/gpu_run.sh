@@ -16,6 +16,14 @@ case $step in
   bwdcells) echo "== backward: cell-strided phase 2 A/B"; timeout 900 python -m pytest tests/test_gpu_bwd_sorted.py -x -q --timeout 600 2>&1 | tail -3
             timeout 600 python tools/bwd_ab2.py --set cells --reps 5 2>&1 | tee gpurun_out/r02_bwd_cells_ab.txt
             timeout 600 python tools/bwd_phases.py --variants 0,13,14,15,16 2>&1 | tee gpurun_out/r02_bwd_cells_phases.txt ;;
+  ncusorted) echo "== ncu --set full: default forward + anchor-sorted backward (cfg 2 x 16)"
+            python tools/ncu_target.py 16 > gpurun_out/ncu_plain_target.log 2>&1 && \
+            ncu --set full --clock-control none --import-source on -k regex:msda_ -s 2 -c 2 -o gpurun_out/prof_r02_final -f python tools/ncu_target.py 16 > gpurun_out/ncu_full.log 2>&1
+            echo "rc=$?"; tail -2 gpurun_out/ncu_full.log ;;
+  launches) echo "== ncu launch list of the bench command"
+            python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-ref-cuda > gpurun_out/ncu_plain_bench.log 2>&1 && \
+            ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-ref-cuda > gpurun_out/ncu_bench.log 2>&1
+            echo "rc=$?" ;;
   *) echo "unknown step $step" ;;
 esac
 done
