@@ -81,16 +81,17 @@ cudaError_t launch_fused(bool bwd, const FastParams &p, const CUtensorMap &ml, c
 
 // Forward with geometry warps (msda_fwd_geo_kernel): 16 consumer warps + TMA warp + kGeoWarps geometry warps.
 constexpr int kGeoWarps = 2, kGeoStages = 4;
-template <typename T, int L_, bool FUSED, bool WIDE = false, int CPS = 1>
+template <typename T, int L_, bool FUSED, bool WIDE = false, int CPS = 1, int NWC = kNWarp, bool LEAN = false, int NGEO = kGeoWarps>
 int launch_geo(const FastParams &p, const CUtensorMap &ml, const CUtensorMap &mw, int grid, cudaStream_t st)
 {
     constexpr int SW = 32;
-    constexpr int threads = (kNWarp + 1 + kGeoWarps) * 32;
+    constexpr int threads = (NWC + 1 + NGEO) * 32;
+    static_assert(threads <= 1024, "consumer + TMA + geometry warps in one CTA");
     constexpr int smem = GeoRing<L_, 4, SW, kGeoStages>::kBytes;
-    int rc = ensure_dynamic_smem<&msda_fwd_geo_kernel<T, L_, 4, SW, kNWarp, kGeoWarps, kGeoStages, FUSED, WIDE, CPS>>(
+    int rc = ensure_dynamic_smem<&msda_fwd_geo_kernel<T, L_, 4, SW, NWC, NGEO, kGeoStages, FUSED, WIDE, CPS, LEAN>>(
         smem, "cudaFuncSetAttribute(geometry-warp forward smem)");
     if (rc) return rc;
-    msda_fwd_geo_kernel<T, L_, 4, SW, kNWarp, kGeoWarps, kGeoStages, FUSED, WIDE, CPS><<<grid, threads, smem, st>>>(p, ml, mw);
+    msda_fwd_geo_kernel<T, L_, 4, SW, NWC, NGEO, kGeoStages, FUSED, WIDE, CPS, LEAN><<<grid, threads, smem, st>>>(p, ml, mw);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "launch msda_fwd_geo_kernel");
     count_launch(1);
@@ -207,9 +208,41 @@ int run_fast(bool bwd, FastParams p, const Dims &d, int dtype, const bm2f_msda_t
         if ((rc = make_map(&mw, p.attn, rows_total, static_cast<uint64_t>(d.M) * LP, c.sw, LP))) return rc;
     }
 
-    // geometry-warp forward (float32, TMA staging, strip 32): opt-in through tuning.geo = 1
+    // DEFAULT forward (float32, TMA staging, strip 32, one CTA per SM, plain entry point): geometry warps with lean records
+    // (msda_fwd_geo_kernel<.., LEAN>): 28 consumer warps + TMA warp + 3 geometry warps = one full CTA.  The consumers
+    // gather unconditionally (dropped corners carry weight 0 and an in-image offset) and are dealt queries round-robin
+    // across stages.  Measured at cfg 2 x 16: 0.89 ms vs 0.97 ms for msda_fwd_fast_kernel (tuning.geo = 2), identical bits.
+    if (!bwd && (t.geo == 0 || t.geo == 11) && c.tma && c.sw == 32 && c.cps == 1 && !c.wide && dtype == BM2F_DTYPE_F32 && !fused) {
+        switch (d.L) {
+        case 1: return launch_geo<float, 1, false, false, 1, 28, true, 3>(p, ml, mw, grid, st);
+        case 2: return launch_geo<float, 2, false, false, 1, 28, true, 3>(p, ml, mw, grid, st);
+        case 3: return launch_geo<float, 3, false, false, 1, 28, true, 3>(p, ml, mw, grid, st);
+        case 4: return launch_geo<float, 4, false, false, 1, 28, true, 3>(p, ml, mw, grid, st);
+        default: break;
+        }
+    }
+    // geometry-warp forward variants kept for A/B (cfg shape, L = 3): tuning.geo = 1 with two CTAs per SM
     if (!bwd && t.geo == 1 && c.tma && c.sw == 32 && c.cps == 2 && dtype == BM2F_DTYPE_F32 && d.L == 3 && !fused)
-        return launch_geo<float, 3, false, false, 2>(p, ml, mw, grid, st);  // two CTAs per SM (cfg shape only)
+        return launch_geo<float, 3, false, false, 2>(p, ml, mw, grid, st);
+#ifdef BM2F_SWEEP
+    // predicated records with 20 / 24 / 28 consumer warps (5 / 6 / 7); lean records with other warp splits (8 .. 16)
+    if (!bwd && t.geo >= 5 && t.geo <= 16 && c.tma && c.sw == 32 && c.cps == 1 && dtype == BM2F_DTYPE_F32 && d.L == 3 && !fused) {
+        switch (t.geo) {
+        case 5: return launch_geo<float, 3, false, false, 1, 20>(p, ml, mw, grid, st);
+        case 6: return launch_geo<float, 3, false, false, 1, 24>(p, ml, mw, grid, st);
+        case 7: return launch_geo<float, 3, false, false, 1, 28>(p, ml, mw, grid, st);
+        case 8: return launch_geo<float, 3, false, false, 1, 16, true>(p, ml, mw, grid, st);
+        case 9: return launch_geo<float, 3, false, false, 1, 24, true>(p, ml, mw, grid, st);
+        case 10: return launch_geo<float, 3, false, false, 1, 28, true>(p, ml, mw, grid, st);
+        case 12: return launch_geo<float, 3, false, false, 1, 26, true, 5>(p, ml, mw, grid, st);
+        case 13: return launch_geo<float, 3, false, false, 1, 24, true, 6>(p, ml, mw, grid, st);
+        case 14: return launch_geo<float, 3, false, false, 1, 24, true, 4>(p, ml, mw, grid, st);
+        case 15: return launch_geo<float, 3, false, false, 1, 20, true, 8>(p, ml, mw, grid, st);
+        case 16: return launch_geo<float, 3, false, false, 1, 16, true, 4>(p, ml, mw, grid, st);
+        default: break;
+        }
+    }
+#endif
     if (!bwd && t.geo == 3 && c.tma && c.sw == 32 && c.cps == 1 && dtype == BM2F_DTYPE_F32 && d.L == 3 && !fused)
         return launch_geo<float, 3, false, true>(p, ml, mw, grid, st);      // + 256-bit gathers (cfg shape only)
     if (!bwd && t.geo == 1 && c.tma && c.sw == 32 && c.cps == 1 && !c.wide && dtype == BM2F_DTYPE_F32) {

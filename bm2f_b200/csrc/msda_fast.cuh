@@ -521,8 +521,12 @@ struct GeoRing {
 // WIDE (fp32): the consumers gather with 256-bit loads — 4 lanes x 32 B per corner, 8 corners (two points) per warp
 // instruction, the access shape with the 1.6x higher measured L1 line rate (profiles/r01_microbench.txt).  The partial
 // sums are partitioned differently across lanes, so the result equals the default kernel to rounding, not bitwise.
+// LEAN: a dropped corner (outside the level, or the point out of range) is recorded with weight 0 and the offset of an
+// in-image pixel instead of -1, so the consumers issue their four gathers unconditionally: no predicates, no zero
+// initialisation of the destination registers — the loop is two shared loads, four address computations, four gathers,
+// sixteen FMAs.  0 * v adds nothing, so the result equals the predicated kernels bit for bit as long as `value` is finite.
 template <typename T, int L_, int P_, int SW, int NWARP, int NGEO, int RSTAGES, bool FUSED = false, bool WIDE = false,
-          int CPS = 1>
+          int CPS = 1, bool LEAN = false>
 __global__ void __launch_bounds__((NWARP + 1 + NGEO) * 32, CPS)
 msda_fwd_geo_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_loc, const __grid_constant__ CUtensorMap tm_w)
 {
@@ -605,6 +609,10 @@ msda_fwd_geo_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_l
             const StageRef<L_> sref(kq, yq, Wf, Hf);
             (void)sref;
             const int npts = nq * LP;
+            // a geometry warp is one dependent chain per point (~100 instructions): two points per trip give it the
+            // instruction-level parallelism to keep up with the consumers (measured: the record ring, not L1, paced the
+            // geometry-warp variants)
+#pragma unroll 2
             for (int idx = gw * 32 + lane; idx < npts; idx += NGEO * 32) {
                 const int qi = idx / LP, j = idx - qi * LP;
                 const float2 xy = ring.loc(slot, qi)[j];
@@ -629,10 +637,18 @@ msda_fwd_geo_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_l
                 }
                 const Footprint f = make_footprint(x, y, Hl, Wl, Hfl, Wfl);
                 const int e00 = (stl + f.y0 * Wl + f.x0) * MD;
+                const float wy0 = a * f.hh, wy1 = a * f.lh;
+                if constexpr (LEAN) {
+                    const int safe = (stl + max(min(max(f.y0, 0), Hl - 1), 0) * Wl + max(min(max(f.x0, 0), Wl - 1), 0)) * MD;   // (empty level: element 0)
+                    ro[idx] = make_int4(f.ok[0] ? e00 : safe, f.ok[1] ? e00 + MD : safe, f.ok[2] ? e00 + Wl * MD : safe,
+                                        f.ok[3] ? e00 + Wl * MD + MD : safe);
+                    rc[idx] = make_float4(f.ok[0] ? wy0 * f.hw : 0.f, f.ok[1] ? wy0 * f.lw : 0.f, f.ok[2] ? wy1 * f.hw : 0.f,
+                                          f.ok[3] ? wy1 * f.lw : 0.f);
+                } else {
                 ro[idx] = make_int4(f.ok[0] ? e00 : -1, f.ok[1] ? e00 + MD : -1, f.ok[2] ? e00 + Wl * MD : -1,
                                     f.ok[3] ? e00 + Wl * MD + MD : -1);
-                const float wy0 = a * f.hh, wy1 = a * f.lh;
                 rc[idx] = make_float4(wy0 * f.hw, wy0 * f.lw, wy1 * f.hw, wy1 * f.lw);
+                }
             }
             if constexpr (FUSED) fence_proxy_async_smem();   // the raw slot (softmax written in place) goes back to TMA
             __syncwarp();
@@ -698,7 +714,11 @@ msda_fwd_geo_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_l
         const int4 *ro = Geo::offs(geo_smem, rslot);
         const float4 *rc = Geo::cws(geo_smem, rslot);
         const T *vlane = value + (static_cast<size_t>(b) * p.S * kHeads + m) * D + sub * VEC;
-        for (int qi = wi; qi < nq; qi += NWARP) {
+        // queries are dealt to the consumer warps round-robin ACROSS stages (flat index s * SW + qi), so that a warp count
+        // that does not divide the stage (24, 28 warps for 32 queries) still keeps every warp equally busy
+        int first = wi - (s * SW) % NWARP;
+        if (first < 0) first += NWARP;
+        for (int qi = first; qi < nq; qi += NWARP) {
             const int q = q_base + qi;
             float acc[VEC];
 #pragma unroll
@@ -712,9 +732,13 @@ msda_fwd_geo_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_l
                 float v[4][VEC];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
+                    if constexpr (LEAN) {
+                        VecIO<T, VEC>::load(vlane + off[k], v[k]);
+                    } else {
 #pragma unroll
-                    for (int c = 0; c < VEC; ++c) v[k][c] = 0.f;
-                    if (off[k] >= 0) VecIO<T, VEC>::load(vlane + off[k], v[k]);
+                        for (int c = 0; c < VEC; ++c) v[k][c] = 0.f;
+                        if (off[k] >= 0) VecIO<T, VEC>::load(vlane + off[k], v[k]);
+                    }
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k)

@@ -261,9 +261,126 @@ int quick_main()
     return 0;
 }
 
+// --lean: L1-resident global gather vs shared-memory gather with the SAME lean loop (LCG row index: 3 integer instructions,
+// one 128-bit load of 8 lanes x 16 B x 4 rows, 4 adds), so that neither is limited by instruction issue: the question is
+// whether a value window staged in shared memory can be read faster than the same window through L1 tags.
+// L1-resident gather of lines that are `stride_lines` x 128 B apart (the value tensor's (N, S, M, D) layout puts the lines
+// of ONE head 8 lines = 1024 B apart): does the tag stage keep its rate when a CTA's lines use every 8th line only?
+__global__ void __launch_bounds__(512) strided_gather_kernel(const float *__restrict__ buf, int iters, int stride_lines,
+                                                             uint32_t rows_log2, float *sink)
+{
+    const int sub = threadIdx.x & 7;
+    const float *base = buf + (size_t)blockIdx.x * ((size_t)32 << rows_log2) * stride_lines;
+    uint32_t h = (blockIdx.x * blockDim.x + threadIdx.x) / 8 * 2654435761u + 12345u;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int i = 0; i < iters; ++i) {
+        h = h * 1664525u + 1013904223u;
+        const uint32_t row = h >> (32 - rows_log2);
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(base + (size_t)row * 32 * stride_lines) + sub);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (acc.x + acc.y + acc.z + acc.w == 123.456f) *sink = acc.x;
+}
+
+template <bool SHARED>
+__global__ void __launch_bounds__(512) lean_gather_kernel(const float *__restrict__ buf, int iters, float *sink)
+{
+    extern __shared__ __align__(128) float win[];
+    constexpr uint32_t kRows = 512;                 // 64 KB window
+    const int lane = threadIdx.x & 31, grp = lane >> 3, sub = lane & 7;
+    const float *base = buf + (size_t)blockIdx.x * kRows * 32;
+    if (SHARED) {
+        for (int i = threadIdx.x; i < (int)kRows * 32; i += blockDim.x) win[i] = base[i];
+        __syncthreads();
+    }
+    uint32_t h = (blockIdx.x * blockDim.x + threadIdx.x) / 8 * 2654435761u + 12345u;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int i = 0; i < iters; ++i) {
+        h = h * 1664525u + 1013904223u;
+        const uint32_t row = h >> 23;
+        float4 v;
+        if (SHARED) v = *reinterpret_cast<const float4 *>(win + row * 32 + sub * 4);
+        else v = __ldg(reinterpret_cast<const float4 *>(base + row * 32) + sub);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (acc.x + acc.y + acc.z + acc.w == 123.456f) *sink = acc.x;
+    (void)grp;
+}
+
+// lean L2-resident gather / reduction: same LCG loop, lines drawn from the whole buffer
+template <bool RED>
+__global__ void __launch_bounds__(512) lean_l2_kernel(float *__restrict__ buf, uint32_t nlines, int iters, float *sink)
+{
+    const int sub = threadIdx.x & 7;
+    uint32_t h = (blockIdx.x * blockDim.x + threadIdx.x) / 8 * 2654435761u + 12345u;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int i = 0; i < iters; ++i) {
+        h = h * 1664525u + 1013904223u;
+        const uint32_t line = (uint32_t)(((uint64_t)h * nlines) >> 32);
+        float *p = buf + (size_t)line * 32 + sub * 4;
+        if (RED) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %1, %1, %1};" ::"l"(p), "f"(0.f) : "memory");
+        } else {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+    if (!RED && acc.x + acc.y + acc.z + acc.w == 123.456f) *sink = acc.x;
+}
+
+int lean_main()
+{
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    const int sms = prop.multiProcessorCount;
+    float *buf, *sink;
+    CK(cudaMalloc(&buf, (size_t)sms * 4 * 65536));
+    CK(cudaMalloc(&sink, 4));
+    CK(cudaMemset(buf, 0, (size_t)sms * 4 * 65536));
+    CK(cudaFuncSetAttribute(lean_gather_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    const int iters = 8192;
+    for (int ctas = 1; ctas <= 2; ++ctas)
+        for (int threads = 256; threads <= 512; threads *= 2) {
+            const double lines = (double)sms * ctas * (threads / 32) * iters * 4;
+            const float t_l1 = time_ms([&] { lean_gather_kernel<false><<<sms * ctas, threads>>>(buf, iters, sink); }, 5);
+            const float t_sm = time_ms([&] { lean_gather_kernel<true><<<sms * ctas, threads, 65536>>>(buf, iters, sink); }, 5);
+            printf("lean gather 8x16B, 64 KB window, %d CTA(s)/SM x %d threads:  L1 (ld.global.nc) %8.1f GB/s = %.3f lines/clk/SM"
+                   "   shared (ld.shared) %8.1f GB/s = %.3f lines/clk/SM\n", ctas, threads, lines * 128 / t_l1 * 1e-6,
+                   lines / (t_l1 * 1e-3) / sms / (prop.clockRate * 1e3), lines * 128 / t_sm * 1e-6,
+                   lines / (t_sm * 1e-3) / sms / (prop.clockRate * 1e3));
+        }
+    float *big;
+    CK(cudaMalloc(&big, 352ull << 20));
+    CK(cudaMemset(big, 0, 352ull << 20));
+    // one head's lines: 512 (64 KB) or 256 (32 KB) or 128 (16 KB) lines per CTA at a stride of 1 / 2 / 4 / 8 lines
+    for (uint32_t rl : {9u, 8u, 7u})
+        for (int stride : {1, 2, 4, 8}) {
+            const double lines = (double)sms * 16 * iters * 4;
+            const float tt = time_ms([&] { strided_gather_kernel<<<sms, 512>>>(big, iters, stride, rl, sink); }, 5);
+            printf("L1 gather 8x16B, %3u lines per CTA at a stride of %d lines (%4d B), 1 CTA/SM x 512 threads: %8.1f GB/s = %.3f lines/clk/SM\n",
+                   1u << rl, stride, stride * 128, lines * 128 / tt * 1e-6, lines / (tt * 1e-3) / sms / (prop.clockRate * 1e3));
+        }
+    for (double mb : {44.0, 352.0}) {
+        const uint32_t nl = (uint32_t)(mb * 1048576.0 / 128);
+        for (int ctas = 1; ctas <= 4; ctas *= 2) {
+            const int it2 = 1024;
+            const double lines = (double)sms * ctas * 16 * it2 * 4;
+            const float tg = time_ms([&] { lean_l2_kernel<false><<<sms * ctas, 512>>>(big, nl, it2, sink); }, 5);
+            const float tr = time_ms([&] { lean_l2_kernel<true><<<sms * ctas, 512>>>(big, nl, it2, sink); }, 5);
+            printf("lean 8x16B over %5.0f MB, %d CTA(s)/SM x 512 threads:  gather %8.1f GB/s   red.v4.f32 %8.1f GB/s\n", mb, ctas,
+                   lines * 128 / tg * 1e-6, lines * 128 / tr * 1e-6);
+        }
+    }
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
     if (argc > 1 && !strcmp(argv[1], "--quick")) return quick_main();
+    if (argc > 1 && !strcmp(argv[1], "--lean")) return lean_main();
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
     printf("# device %s  SMs %d  L2 %.1f MB  smem/SM %zu KB\n", prop.name, prop.multiProcessorCount,

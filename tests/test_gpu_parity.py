@@ -427,9 +427,11 @@ def test_fused_analytic_reference_points_bit_identical(levels, batch, built):
 @pytest.mark.parametrize("levels,batch", [(SMALL_LEVELS, 3), (((1, 1), (3, 2), (25, 38)), 2), (((5, 7), (9, 13)), 1),
                                           (W.WORKLOADS[1].levels, 1), (((32, 32), (64, 64), (16, 16), (8, 8)), 2)])
 def test_geometry_warp_forward_bit_identical(levels, batch, built):
-    """tuning.geo = 1: per-point footprints / weights / corner offsets computed once by geometry warps and handed to the
-    consumers through shared-memory records.  Same operands and FMA order as the default forward, so the output is
-    bit-identical — plain and fused entry points, strip-walked and raster-walked levels, a 1 x 1 level, L = 2, 3, 4."""
+    """Geometry-warp forward kernels: per-point footprints / weights / corner offsets computed once by geometry warps and
+    handed to the consumers through shared-memory records.  The default (lean records: unconditional gathers, weight 0
+    for dropped corners, 28 consumer warps), tuning.geo = 1 (predicated records) and the consumer-lane kernel of round 1
+    (tuning.geo = 2) use the same operands and FMA order, so their outputs are bit-identical — plain and fused entry
+    points, strip-walked and raster-walked levels, a 1 x 1 level, L = 2, 3, 4, a third of the points outside."""
     base, _, offsets, logits = _fused_inputs(levels, batch, 970 + len(levels))
     dev = _dev()
     L = len(levels)
@@ -440,7 +442,7 @@ def test_geometry_warp_forward_bit_identical(levels, batch, built):
     stream = torch.cuda.current_stream().cuda_stream
     geo = cabi.make_tuning(geo=1)
     res = {}
-    for name, tun in (("default", None), ("geo", geo)):
+    for name, tun in (("default", None), ("geo", geo), ("lanes", cabi.make_tuning(geo=2))):
         out_p = torch.full((N, S, M * D), float("nan"), device=dev)
         out_f = torch.full((N, S, M * D), float("nan"), device=dev)
         cabi.forward(v.data_ptr(), sh.data_ptr(), st.data_ptr(), lc.data_ptr(), at.data_ptr(), out_p.data_ptr(), dims,
@@ -452,6 +454,9 @@ def test_geometry_warp_forward_bit_identical(levels, batch, built):
     assert not torch.isnan(res["geo"][0]).any() and not torch.isnan(res["geo"][1]).any()
     assert torch.equal(res["default"][0], res["geo"][0])
     assert torch.equal(res["default"][1], res["geo"][1])
+    assert not torch.isnan(res["default"][0]).any()
+    assert torch.equal(res["default"][0], res["lanes"][0])
+    assert torch.equal(res["default"][1], res["lanes"][1])
     if L == 3:
         # geo = 3: the same records consumed with 256-bit gathers (8 corners per warp instruction); the partial sums
         # are split differently across lanes, so equality is to rounding

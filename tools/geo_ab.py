@@ -20,7 +20,7 @@ logits = torch.randn(batch, S, M, L * P, device=dev)
 norm = torch.stack((shapes[:, 1], shapes[:, 0]), -1).float()
 loc = (ref[:, :, None, :, None, :] + offsets / norm[None, None, None, :, None, :]).contiguous()
 attn = torch.softmax(logits, -1).view(batch, S, M, L, P).contiguous()
-outs = {k: torch.empty(batch, S, M * D, device=dev) for k in ("plain", "plain_geo", "plain_geo_2cta", "plain_geo_wide", "fused", "fused_geo")}
+outs = {k: torch.empty(batch, S, M * D, device=dev) for k in ("plain", "plain_geo", "plain_geo_2cta", "plain_geo_wide", "fused", "fused_geo", "geo_20w", "geo_24w", "geo_28w", "lean_16w", "lean_24w", "lean_28w", "lean_28w_3g", "lean_26w_5g", "lean_24w_6g", "lean_24w_4g", "lean_20w_8g", "lean_16w_4g")}
 dims = (batch, S, M, D, L, S, P); st = torch.cuda.current_stream().cuda_stream
 geo = cabi.make_tuning(geo=1); geow = cabi.make_tuning(geo=3); geo2 = cabi.make_tuning(geo=1, ctas_per_sm=2)
 P_ = lambda t: t.data_ptr()
@@ -29,6 +29,18 @@ fns = {
     "plain_geo": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["plain_geo"]), dims, 0, geo, st),
     "plain_geo_2cta": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["plain_geo_2cta"]), dims, 0, geo2, st),
     "plain_geo_wide": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["plain_geo_wide"]), dims, 0, geow, st),
+    "geo_20w": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["geo_20w"]), dims, 0, cabi.make_tuning(geo=5), st),
+    "geo_24w": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["geo_24w"]), dims, 0, cabi.make_tuning(geo=6), st),
+    "geo_28w": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["geo_28w"]), dims, 0, cabi.make_tuning(geo=7), st),
+    "lean_16w": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["lean_16w"]), dims, 0, cabi.make_tuning(geo=8), st),
+    "lean_24w": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["lean_24w"]), dims, 0, cabi.make_tuning(geo=9), st),
+    "lean_28w": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["lean_28w"]), dims, 0, cabi.make_tuning(geo=10), st),
+    "lean_28w_3g": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["lean_28w_3g"]), dims, 0, cabi.make_tuning(geo=11), st),
+    "lean_26w_5g": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["lean_26w_5g"]), dims, 0, cabi.make_tuning(geo=12), st),
+    "lean_24w_6g": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["lean_24w_6g"]), dims, 0, cabi.make_tuning(geo=13), st),
+    "lean_24w_4g": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["lean_24w_4g"]), dims, 0, cabi.make_tuning(geo=14), st),
+    "lean_20w_8g": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["lean_20w_8g"]), dims, 0, cabi.make_tuning(geo=15), st),
+    "lean_16w_4g": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["lean_16w_4g"]), dims, 0, cabi.make_tuning(geo=16), st),
     "fused": lambda: cabi.fused_forward(P_(value), P_(shapes), P_(start), 0, P_(offsets), P_(logits), P_(outs["fused"]), dims, 0, None, st),
     "fused_geo": lambda: cabi.fused_forward(P_(value), P_(shapes), P_(start), 0, P_(offsets), P_(logits), P_(outs["fused_geo"]), dims, 0, geo, st),
 }
@@ -41,6 +53,8 @@ def t(fn):
     return best
 for k, fn in fns.items():
     print(f"{k:10s} {t(fn):7.3f} ms", flush=True)
+print("geo 20 / 24 / 28 consumer warps == plain:", [bool(torch.equal(outs["plain"], outs[k])) for k in ("geo_20w", "geo_24w", "geo_28w")])
+print("lean variants == plain:", [bool(torch.equal(outs["plain"], outs[k])) for k in outs if k.startswith("lean")])
 print("plain_geo_2cta == plain:", bool(torch.equal(outs["plain"], outs["plain_geo_2cta"])))
 print("plain_geo == plain:", bool(torch.equal(outs["plain"], outs["plain_geo"])),
       " fused_geo == fused:", bool(torch.equal(outs["fused"], outs["fused_geo"])),
