@@ -621,10 +621,13 @@ def run_ours(args, wl):
         # its compulsory HBM bytes at the HBM rate, its gathered corner lines at the L2 gather rate of the same
         # access shape (8 lanes x 16 B), and — backward, as long as every corner is one L2 reduction — its RED lines
         # at the red.global.add.v4.f32 rate
-        l2g, l1g, red = (peaks_run["gather_8x16B_l2_44MB"], peaks_run["gather_8x16B_l1_96KB"],
+        l2g, l1g, red = (peaks_run["gather_8x16B_l2_44MB"], peaks_run["gather_8x16B_l1_64KB"],
                          peaks_run["red_8xv4f32_l2_44MB"])
         corner_bytes = W.gather_bytes(wl.S, "fwd", wl.dtype) * nb         # 48 lines per (query, head), once
         terms = {"hbm": alg_bytes / (peaks["hbm_gbs"] * 1e9) * 1e3, "l2_gather": corner_bytes / (l2g * 1e9) * 1e3}
+        # what the SM itself can take in: one 128-byte line per clock through the L1 data pipe (measured: an L1-resident
+        # gather and a shared-memory gather of this shape both reach it, so a window staged in shared memory is no faster)
+        terms["l1_data_pipe"] = corner_bytes / (l1g * 1e9) * 1e3
         lb = max(terms.values())
         roofline["lower_bound_ms"] = lb
         roofline["lower_bound_terms_ms"] = terms

@@ -233,37 +233,6 @@ __global__ void __launch_bounds__(512) smem_gather_kernel(int iters, float *sink
 }
 
 // --quick: the few peaks bench.py divides by, measured on the GPU and in the run that reports them; one JSON line.
-int quick_main()
-{
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, 0));
-    const size_t bytes_buf = 512ull << 20;
-    float *buf, *sink;
-    CK(cudaMalloc(&buf, bytes_buf));
-    CK(cudaMalloc(&sink, 4));
-    CK(cudaMemset(buf, 0, bytes_buf));
-    const int sms = prop.multiProcessorCount, threads = 512, grid = sms * 4, warps = grid * threads / 32;
-    const uint32_t n44 = (uint32_t)(44.0 * 1048576.0 / 128), n352 = (uint32_t)(352.0 * 1048576.0 / 128);
-    const double gl2 = (double)warps * 512 * 4 * 128.0 /
-                       time_ms([&] { gather_kernel<1><<<grid, threads>>>(buf, n44, 512, 0, sink); }, 5) * 1e-6;
-    const double gl1 = (double)(sms * threads / 32) * 4096 * 4 * 128.0 /
-                       time_ms([&] { gather_kernel<1><<<sms, threads>>>(buf, n352, 4096, 768, sink); }, 5) * 1e-6;
-    const double red = (double)warps * 128 * 4 * 128.0 /
-                       time_ms([&] { red_kernel<1><<<grid, threads>>>(buf, n44, 128, 0); }, 5) * 1e-6;
-    CK(cudaFuncSetAttribute(smem_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 768 * 128));
-    const double lds = (double)(sms * 2 * threads / 32) * 4096 * 4 * 128.0 /
-                       time_ms([&] { smem_gather_kernel<<<sms * 2, threads, 768 * 128>>>(4096, sink); }, 5) * 1e-6;
-    const size_t n = bytes_buf / 2;
-    const double copy = 2.0 * n / time_ms([&] { CK(cudaMemcpyAsync(buf, (char *)buf + n, n, cudaMemcpyDeviceToDevice)); }, 5) * 1e-6;
-    printf("{\"device\": \"%s\", \"sms\": %d, \"unit\": \"GB/s of 128-B lines\", \"gather_8x16B_l2_44MB\": %.1f, "
-           "\"gather_8x16B_l1_96KB\": %.1f, \"red_8xv4f32_l2_44MB\": %.1f, \"lds_8x16B_smem_96KB\": %.1f, \"d2d_copy_rw\": %.1f}\n",
-           prop.name, sms, gl2, gl1, red, lds, copy);
-    return 0;
-}
-
-// --lean: L1-resident global gather vs shared-memory gather with the SAME lean loop (LCG row index: 3 integer instructions,
-// one 128-bit load of 8 lanes x 16 B x 4 rows, 4 adds), so that neither is limited by instruction issue: the question is
-// whether a value window staged in shared memory can be read faster than the same window through L1 tags.
 // L1-resident gather of lines that are `stride_lines` x 128 B apart (the value tensor's (N, S, M, D) layout puts the lines
 // of ONE head 8 lines = 1024 B apart): does the tag stage keep its rate when a CTA's lines use every 8th line only?
 __global__ void __launch_bounds__(512) strided_gather_kernel(const float *__restrict__ buf, int iters, int stride_lines,
@@ -374,6 +343,35 @@ int lean_main()
                    lines * 128 / tg * 1e-6, lines * 128 / tr * 1e-6);
         }
     }
+    return 0;
+}
+
+// --quick: the few peaks bench.py divides by, measured on the GPU and in the run that reports them; one JSON line.
+// Lean loops (an LCG step, one load / reduction of 8 lanes x 16 B x 4 lines, four adds): the round-1 kernels spent ~18
+// instructions per load on index hashing and were issue-bound at roughly half of what L1 delivers.
+int quick_main()
+{
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    const int sms = prop.multiProcessorCount;
+    const size_t bytes_buf = 512ull << 20;
+    float *buf, *sink;
+    CK(cudaMalloc(&buf, bytes_buf));
+    CK(cudaMalloc(&sink, 4));
+    CK(cudaMemset(buf, 0, bytes_buf));
+    const uint32_t n44 = (uint32_t)(44.0 * 1048576.0 / 128);
+    CK(cudaFuncSetAttribute(lean_gather_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    const int it1 = 8192, it2 = 1024;
+    const double l1_lines = (double)sms * 2 * 16 * it1 * 4, l2_lines = (double)sms * 4 * 16 * it2 * 4;
+    const double gl1 = l1_lines * 128 / time_ms([&] { lean_gather_kernel<false><<<sms * 2, 512>>>(buf, it1, sink); }, 5) * 1e-6;
+    const double lds = l1_lines * 128 / time_ms([&] { lean_gather_kernel<true><<<sms * 2, 512, 65536>>>(buf, it1, sink); }, 5) * 1e-6;
+    const double gl2 = l2_lines * 128 / time_ms([&] { lean_l2_kernel<false><<<sms * 4, 512>>>(buf, n44, it2, sink); }, 5) * 1e-6;
+    const double red = l2_lines * 128 / time_ms([&] { lean_l2_kernel<true><<<sms * 4, 512>>>(buf, n44, it2, sink); }, 5) * 1e-6;
+    const size_t n = bytes_buf / 2;
+    const double copy = 2.0 * n / time_ms([&] { CK(cudaMemcpyAsync(buf, (char *)buf + n, n, cudaMemcpyDeviceToDevice)); }, 5) * 1e-6;
+    printf("{\"device\": \"%s\", \"sms\": %d, \"unit\": \"GB/s of 128-B lines\", \"gather_8x16B_l2_44MB\": %.1f, "
+           "\"gather_8x16B_l1_64KB\": %.1f, \"red_8xv4f32_l2_44MB\": %.1f, \"lds_8x16B_smem_64KB\": %.1f, \"d2d_copy_rw\": %.1f}\n",
+           prop.name, sms, gl2, gl1, red, lds, copy);
     return 0;
 }
 
