@@ -81,7 +81,7 @@ cudaError_t launch_fused(bool bwd, const FastParams &p, const CUtensorMap &ml, c
 
 // Forward with geometry warps (msda_fwd_geo_kernel): 16 consumer warps + TMA warp + kGeoWarps geometry warps.
 constexpr int kGeoWarps = 2, kGeoStages = 4;
-template <typename T, int L_, bool FUSED, bool WIDE = false, int CPS = 1, int NWC = kNWarp, bool LEAN = false, int NGEO = kGeoWarps>
+template <typename T, int L_, bool FUSED, bool WIDE = false, int CPS = 1, int NWC = kNWarp, int LEAN = 0, int NGEO = kGeoWarps>
 int launch_geo(const FastParams &p, const CUtensorMap &ml, const CUtensorMap &mw, int grid, cudaStream_t st)
 {
     constexpr int SW = 32;
@@ -212,15 +212,22 @@ int run_fast(bool bwd, FastParams p, const Dims &d, int dtype, const bm2f_msda_t
     // (msda_fwd_geo_kernel<.., LEAN>): 28 consumer warps + TMA warp + 3 geometry warps = one full CTA.  The consumers
     // gather unconditionally (dropped corners carry weight 0 and an in-image offset) and are dealt queries round-robin
     // across stages.  Measured at cfg 2 x 16: 0.89 ms vs 0.97 ms for msda_fwd_fast_kernel (tuning.geo = 2), identical bits.
-    if (!bwd && (t.geo == 0 || t.geo == 11) && c.tma && c.sw == 32 && c.cps == 1 && !c.wide && dtype == BM2F_DTYPE_F32 && !fused) {
+    // DEFAULT forward (float32, TMA staging, strip 32, one CTA per SM, plain entry point): geometry warps with 16-byte
+    // records (msda_fwd_geo_kernel<.., LEAN = 2>): 28 consumer warps + TMA warp + 3 geometry warps = one full CTA.  The
+    // consumers gather unconditionally from a clamped anchor (dropped rows / columns carry weight 0), one shared load per
+    // point, and are dealt queries round-robin across stages.  Measured at cfg 2 x 16: 0.84 ms vs 0.89 ms with 32-byte lean
+    // records (tuning.geo = 11) and 0.97 ms for the consumer-lane kernel msda_fwd_fast_kernel (tuning.geo = 2).
+    if (!bwd && (t.geo == 0 || t.geo == 17) && c.tma && c.sw == 32 && c.cps == 1 && !c.wide && dtype == BM2F_DTYPE_F32 && !fused) {
         switch (d.L) {
-        case 1: return launch_geo<float, 1, false, false, 1, 28, true, 3>(p, ml, mw, grid, st);
-        case 2: return launch_geo<float, 2, false, false, 1, 28, true, 3>(p, ml, mw, grid, st);
-        case 3: return launch_geo<float, 3, false, false, 1, 28, true, 3>(p, ml, mw, grid, st);
-        case 4: return launch_geo<float, 4, false, false, 1, 28, true, 3>(p, ml, mw, grid, st);
+        case 1: return launch_geo<float, 1, false, false, 1, 28, 2, 3>(p, ml, mw, grid, st);
+        case 2: return launch_geo<float, 2, false, false, 1, 28, 2, 3>(p, ml, mw, grid, st);
+        case 3: return launch_geo<float, 3, false, false, 1, 28, 2, 3>(p, ml, mw, grid, st);
+        case 4: return launch_geo<float, 4, false, false, 1, 28, 2, 3>(p, ml, mw, grid, st);
         default: break;
         }
     }
+    if (!bwd && t.geo == 11 && c.tma && c.sw == 32 && c.cps == 1 && !c.wide && dtype == BM2F_DTYPE_F32 && !fused && d.L == 3)
+        return launch_geo<float, 3, false, false, 1, 28, 1, 3>(p, ml, mw, grid, st);      // 32-byte lean records (A/B)
     // geometry-warp forward variants kept for A/B (cfg shape, L = 3): tuning.geo = 1 with two CTAs per SM
     if (!bwd && t.geo == 1 && c.tma && c.sw == 32 && c.cps == 2 && dtype == BM2F_DTYPE_F32 && d.L == 3 && !fused)
         return launch_geo<float, 3, false, false, 2>(p, ml, mw, grid, st);
@@ -231,14 +238,14 @@ int run_fast(bool bwd, FastParams p, const Dims &d, int dtype, const bm2f_msda_t
         case 5: return launch_geo<float, 3, false, false, 1, 20>(p, ml, mw, grid, st);
         case 6: return launch_geo<float, 3, false, false, 1, 24>(p, ml, mw, grid, st);
         case 7: return launch_geo<float, 3, false, false, 1, 28>(p, ml, mw, grid, st);
-        case 8: return launch_geo<float, 3, false, false, 1, 16, true>(p, ml, mw, grid, st);
-        case 9: return launch_geo<float, 3, false, false, 1, 24, true>(p, ml, mw, grid, st);
-        case 10: return launch_geo<float, 3, false, false, 1, 28, true>(p, ml, mw, grid, st);
-        case 12: return launch_geo<float, 3, false, false, 1, 26, true, 5>(p, ml, mw, grid, st);
-        case 13: return launch_geo<float, 3, false, false, 1, 24, true, 6>(p, ml, mw, grid, st);
-        case 14: return launch_geo<float, 3, false, false, 1, 24, true, 4>(p, ml, mw, grid, st);
-        case 15: return launch_geo<float, 3, false, false, 1, 20, true, 8>(p, ml, mw, grid, st);
-        case 16: return launch_geo<float, 3, false, false, 1, 16, true, 4>(p, ml, mw, grid, st);
+        case 8: return launch_geo<float, 3, false, false, 1, 16, 1>(p, ml, mw, grid, st);
+        case 9: return launch_geo<float, 3, false, false, 1, 24, 1>(p, ml, mw, grid, st);
+        case 10: return launch_geo<float, 3, false, false, 1, 28, 1>(p, ml, mw, grid, st);
+        case 12: return launch_geo<float, 3, false, false, 1, 26, 1, 5>(p, ml, mw, grid, st);
+        case 13: return launch_geo<float, 3, false, false, 1, 24, 1, 6>(p, ml, mw, grid, st);
+        case 14: return launch_geo<float, 3, false, false, 1, 24, 1, 4>(p, ml, mw, grid, st);
+        case 15: return launch_geo<float, 3, false, false, 1, 20, 1, 8>(p, ml, mw, grid, st);
+        case 16: return launch_geo<float, 3, false, false, 1, 16, 1, 4>(p, ml, mw, grid, st);
         default: break;
         }
     }

@@ -525,8 +525,14 @@ struct GeoRing {
 // in-image pixel instead of -1, so the consumers issue their four gathers unconditionally: no predicates, no zero
 // initialisation of the destination registers — the loop is two shared loads, four address computations, four gathers,
 // sixteen FMAs.  0 * v adds nothing, so the result equals the predicated kernels bit for bit as long as `value` is finite.
+// LEAN = 2: 16-byte records {anchor offset | x-drop flags, a * wy0, a * wy1, lw}: ONE 128-bit shared load per point
+// instead of two (an LDS.128 costs four L1 data-pipe wavefronts even when the 8 lanes of a group read the same 16 bytes,
+// and that pipe is what bounds this kernel), the other three corner addresses follow from the anchor.  The anchor is
+// clamped into [0, H - 2] x [0, W - 2] so that all four addresses lie inside the level; a border point's surviving row /
+// column moves to the other slot (weights exact in y; in x the surviving weight is stored as hw and read back as
+// 1 - hw, which differs from lw by <= 2^-25 when lw < 0.5).  Single-row / single-column levels use a zero stride.
 template <typename T, int L_, int P_, int SW, int NWARP, int NGEO, int RSTAGES, bool FUSED = false, bool WIDE = false,
-          int CPS = 1, bool LEAN = false>
+          int CPS = 1, int LEAN = 0>
 __global__ void __launch_bounds__((NWARP + 1 + NGEO) * 32, CPS)
 msda_fwd_geo_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_loc, const __grid_constant__ CUtensorMap tm_w)
 {
@@ -566,6 +572,12 @@ msda_fwd_geo_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_l
         Hf[l] = static_cast<float>(H[l]); Wf[l] = static_cast<float>(W[l]);
     }
     constexpr int MD = kHeads * D;
+    // LEAN = 2: a level with a single row or column (never in Mask2Former's pyramids) has no 2 x 2 block to clamp the
+    // anchor into; the whole launch then uses the 32-byte lean records (uniform decision from the device-resident table)
+    bool degenerate = false;
+#pragma unroll
+    for (int l = 0; l < L_; ++l) degenerate = degenerate || H[l] < 2 || W[l] < 2;
+    (void)degenerate;
 
     if (warp > NWARP) {                                    // ---- geometry warps ----
         const int gw = warp - NWARP - 1;
@@ -638,7 +650,21 @@ msda_fwd_geo_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_l
                 const Footprint f = make_footprint(x, y, Hl, Wl, Hfl, Wfl);
                 const int e00 = (stl + f.y0 * Wl + f.x0) * MD;
                 const float wy0 = a * f.hh, wy1 = a * f.lh;
-                if constexpr (LEAN) {
+                if (LEAN == 2 && !degenerate) {
+                    // separable weights: rows (a * hh, a * lh) masked by the row tests, columns (hw, lw) by the column tests
+                    const bool y0ok = f.in_range && f.y0 >= 0, y1ok = f.in_range && f.y0 + 1 <= Hl - 1;
+                    float r0 = y0ok ? wy0 : 0.f, r1 = y1ok ? wy1 : 0.f;
+                    int ay = f.y0, ax = f.x0;
+                    if (!f.in_range) { ay = 0; ax = 0; }
+                    if (ay < 0) { ay = 0; r0 = r1; r1 = 0.f; }                        // row y = 0 is the footprint's lower row
+                    else if (ay > Hl - 2) { ay = Hl - 2; r1 = r0; r0 = 0.f; }         // row y = H - 1 is its upper row
+                    float lwf = f.lw;
+                    int flags = 0;
+                    if (ax < 0) { ax = 0; lwf = f.hw; flags = 2; }                    // column 0 carries lw: stored as hw, read as 1 - hw
+                    else if (ax > Wl - 2) { ax = Wl - 2; lwf = f.hw; flags = 1; }     // column W - 1 carries hw in slot 1
+                    const int e = (stl + ay * Wl + ax) * MD;
+                    rc[idx] = make_float4(__int_as_float(e | flags), r0, r1, lwf);
+                } else if constexpr (LEAN >= 1) {
                     const int safe = (stl + max(min(max(f.y0, 0), Hl - 1), 0) * Wl + max(min(max(f.x0, 0), Wl - 1), 0)) * MD;   // (empty level: element 0)
                     ro[idx] = make_int4(f.ok[0] ? e00 : safe, f.ok[1] ? e00 + MD : safe, f.ok[2] ? e00 + Wl * MD : safe,
                                         f.ok[3] ? e00 + Wl * MD + MD : safe);
@@ -708,53 +734,74 @@ msda_fwd_geo_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_l
         });
         return;
     }
-    for_each_stage<L_, SW>(tabs, p, [&](int s, int b, int m, int q_base, int nq, int, int, int) {
-        const int rslot = s % RSTAGES;
-        mbar_wait(&rec_full[rslot], (s / RSTAGES) & 1);
-        const int4 *ro = Geo::offs(geo_smem, rslot);
-        const float4 *rc = Geo::cws(geo_smem, rslot);
-        const T *vlane = value + (static_cast<size_t>(b) * p.S * kHeads + m) * D + sub * VEC;
-        // queries are dealt to the consumer warps round-robin ACROSS stages (flat index s * SW + qi), so that a warp count
-        // that does not divide the stage (24, 28 warps for 32 queries) still keeps every warp equally busy
-        int first = wi - (s * SW) % NWARP;
-        if (first < 0) first += NWARP;
-        for (int qi = first; qi < nq; qi += NWARP) {
-            const int q = q_base + qi;
-            float acc[VEC];
-#pragma unroll
-            for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
-#pragma unroll
-            for (int it = 0; it < NIT; ++it) {
-                const int4 o = ro[qi * LP + it * LG + lg];
-                const float4 cw4 = rc[qi * LP + it * LG + lg];
-                const int off[4] = {o.x, o.y, o.z, o.w};
-                const float cw[4] = {cw4.x, cw4.y, cw4.z, cw4.w};
-                float v[4][VEC];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if constexpr (LEAN) {
-                        VecIO<T, VEC>::load(vlane + off[k], v[k]);
+    // MODE = record format of this launch (LEAN, or 1 when LEAN = 2 meets a degenerate level): separate loop bodies
+    auto consume = [&](auto mode_c) {
+        constexpr int MODE = decltype(mode_c)::value;
+        for_each_stage<L_, SW>(tabs, p, [&](int s, int b, int m, int q_base, int nq, int, int, int) {
+            const int rslot = s % RSTAGES;
+            mbar_wait(&rec_full[rslot], (s / RSTAGES) & 1);
+            const int4 *ro = Geo::offs(geo_smem, rslot);
+            const float4 *rc = Geo::cws(geo_smem, rslot);
+            const T *vlane = value + (static_cast<size_t>(b) * p.S * kHeads + m) * D + sub * VEC;
+            // queries are dealt to the consumer warps round-robin ACROSS stages (flat index s * SW + qi), so that a warp count
+            // that does not divide the stage (24, 28 warps for 32 queries) still keeps every warp equally busy
+            int first = wi - (s * SW) % NWARP;
+            if (first < 0) first += NWARP;
+            for (int qi = first; qi < nq; qi += NWARP) {
+                const int q = q_base + qi;
+                float acc[VEC];
+    #pragma unroll
+                for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
+    #pragma unroll
+                for (int it = 0; it < NIT; ++it) {
+                    int off[4];
+                    float cw[4];
+                    if constexpr (MODE == 2) {
+                        static_assert(MODE != 2 || LG == P_, "one iteration = the four points of one level");
+                        const float4 r = rc[qi * LP + it * LG + lg];
+                        const int o = __float_as_int(r.x);
+                        const float hwf = 1.f - r.w;
+                        const float wx0 = (o & 1) ? 0.f : hwf, wx1 = (o & 2) ? 0.f : r.w;
+                        cw[0] = r.y * wx0; cw[1] = r.y * wx1; cw[2] = r.z * wx0; cw[3] = r.z * wx1;
+                        off[0] = o & ~3;
+                        off[1] = off[0] + MD;
+                        off[2] = off[0] + W[it] * MD;
+                        off[3] = off[2] + MD;
                     } else {
-#pragma unroll
-                        for (int c = 0; c < VEC; ++c) v[k][c] = 0.f;
-                        if (off[k] >= 0) VecIO<T, VEC>::load(vlane + off[k], v[k]);
+                        const int4 o = ro[qi * LP + it * LG + lg];
+                        const float4 cw4 = rc[qi * LP + it * LG + lg];
+                        off[0] = o.x; off[1] = o.y; off[2] = o.z; off[3] = o.w;
+                        cw[0] = cw4.x; cw[1] = cw4.y; cw[2] = cw4.z; cw[3] = cw4.w;
                     }
+                    float v[4][VEC];
+    #pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if constexpr (MODE >= 1) {
+                            VecIO<T, VEC>::load(vlane + off[k], v[k]);
+                        } else {
+    #pragma unroll
+                            for (int c = 0; c < VEC; ++c) v[k][c] = 0.f;
+                            if (off[k] >= 0) VecIO<T, VEC>::load(vlane + off[k], v[k]);
+                        }
+                    }
+    #pragma unroll
+                    for (int k = 0; k < 4; ++k)
+    #pragma unroll
+                        for (int c = 0; c < VEC; ++c) acc[c] = fmaf(cw[k], v[k][c], acc[c]);
                 }
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-#pragma unroll
-                    for (int c = 0; c < VEC; ++c) acc[c] = fmaf(cw[k], v[k][c], acc[c]);
+    #pragma unroll
+                for (int o = LPC; o < 32; o <<= 1)
+    #pragma unroll
+                    for (int c = 0; c < VEC; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+                if (lg == 0)
+                    VecIO<T, VEC>::store(out + ((static_cast<size_t>(b) * p.Lq + q) * kHeads + m) * D + sub * VEC, acc);
             }
-#pragma unroll
-            for (int o = LPC; o < 32; o <<= 1)
-#pragma unroll
-                for (int c = 0; c < VEC; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
-            if (lg == 0)
-                VecIO<T, VEC>::store(out + ((static_cast<size_t>(b) * p.Lq + q) * kHeads + m) * D + sub * VEC, acc);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&rec_empty[rslot]);
-    });
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&rec_empty[rslot]);
+        });
+    };
+    if (LEAN == 2 && degenerate) consume(std::integral_constant<int, 1>{});
+    else consume(std::integral_constant<int, LEAN>{});
 }
 
 

@@ -86,10 +86,12 @@ typedef struct {
     int order;      /* 0 = default; 1 = 1-D query order (ignore level geometry)                  */
     int merge;      /* backward: 1 = merge equal-pixel corners in-warp before the REDs; 0/2 = off
                        (default: measured slower on B200)                          */
-    int geo;        /* forward kernel (same results): 0 = default: geometry warps with lean records
-                       (28 consumer + 3 geometry warps; float32, TMA staging, strip 32), else the consumer-lane kernel;
-                       2 = consumer-lane geometry kernel msda_fwd_fast_kernel (the round-1 default); 1 = geometry warps
-                       with predicated records (16 consumer warps); 3 = geometry warps + 256-bit gathers (L = 3)   */
+    int geo;        /* forward kernel: 0 = default: geometry warps with 16-byte records (28 consumer + 3
+                       geometry warps; float32, TMA staging, strip 32), else the consumer-lane kernel;
+                       2 = consumer-lane geometry kernel msda_fwd_fast_kernel (the round-1 default); 11 = geometry warps
+                       with 32-byte lean records; 1 = with predicated records (16 consumer warps); 3 = + 256-bit
+                       gathers (L = 3).  All equal bit for bit, except that 0 may differ by one rounding of a bilinear
+                       weight (2^-25) for points whose footprint crosses the left border of a level   */
     int bwd;        /* backward kernel: 0 = default (anchor-sorted when it applies — float32, D = 32, M = 8, P = 4, L <= 4,
                        num_query == spatial_size, order == 0 — and batch * num_query >= 65536; per-corner otherwise),
                        1 = per-corner vector REDs (msda_bwd_fast_kernel), 2 = anchor-sorted, error if it does not apply

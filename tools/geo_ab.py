@@ -20,7 +20,7 @@ logits = torch.randn(batch, S, M, L * P, device=dev)
 norm = torch.stack((shapes[:, 1], shapes[:, 0]), -1).float()
 loc = (ref[:, :, None, :, None, :] + offsets / norm[None, None, None, :, None, :]).contiguous()
 attn = torch.softmax(logits, -1).view(batch, S, M, L, P).contiguous()
-outs = {k: torch.empty(batch, S, M * D, device=dev) for k in ("plain", "plain_geo", "plain_geo_2cta", "plain_geo_wide", "fused", "fused_geo", "geo_20w", "geo_24w", "geo_28w", "lean_16w", "lean_24w", "lean_28w", "lean_28w_3g", "lean_26w_5g", "lean_24w_6g", "lean_24w_4g", "lean_20w_8g", "lean_16w_4g")}
+outs = {k: torch.empty(batch, S, M * D, device=dev) for k in ("plain", "plain_geo", "plain_geo_2cta", "plain_geo_wide", "fused", "fused_geo", "geo_20w", "geo_24w", "geo_28w", "lean_16w", "lean_24w", "lean_28w", "lean_28w_3g", "lean_26w_5g", "lean_24w_6g", "lean_24w_4g", "lean_20w_8g", "lean_16w_4g", "rec16_28w_3g", "rec16_26w_5g")}
 dims = (batch, S, M, D, L, S, P); st = torch.cuda.current_stream().cuda_stream
 geo = cabi.make_tuning(geo=1); geow = cabi.make_tuning(geo=3); geo2 = cabi.make_tuning(geo=1, ctas_per_sm=2)
 P_ = lambda t: t.data_ptr()
@@ -41,6 +41,8 @@ fns = {
     "lean_24w_4g": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["lean_24w_4g"]), dims, 0, cabi.make_tuning(geo=14), st),
     "lean_20w_8g": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["lean_20w_8g"]), dims, 0, cabi.make_tuning(geo=15), st),
     "lean_16w_4g": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["lean_16w_4g"]), dims, 0, cabi.make_tuning(geo=16), st),
+    "rec16_28w_3g": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["rec16_28w_3g"]), dims, 0, cabi.make_tuning(geo=17), st),
+    "rec16_26w_5g": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["rec16_26w_5g"]), dims, 0, cabi.make_tuning(geo=17), st),
     "fused": lambda: cabi.fused_forward(P_(value), P_(shapes), P_(start), 0, P_(offsets), P_(logits), P_(outs["fused"]), dims, 0, None, st),
     "fused_geo": lambda: cabi.fused_forward(P_(value), P_(shapes), P_(start), 0, P_(offsets), P_(logits), P_(outs["fused_geo"]), dims, 0, geo, st),
 }
@@ -51,10 +53,15 @@ def t(fn):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record(); torch.cuda.synchronize(); best = min(best, a.elapsed_time(b))
     return best
-for k, fn in fns.items():
-    print(f"{k:10s} {t(fn):7.3f} ms", flush=True)
+for k, fn in list(fns.items()):
+    try:
+        print(f"{k:10s} {t(fn):7.3f} ms", flush=True)
+    except Exception as e:          # sweep-only variants (BM2F_SWEEP build) fall through to the default kernel or raise
+        print(f"{k:10s} not in this build: {e}", flush=True)
 print("geo 20 / 24 / 28 consumer warps == plain:", [bool(torch.equal(outs["plain"], outs[k])) for k in ("geo_20w", "geo_24w", "geo_28w")])
 print("lean variants == plain:", [bool(torch.equal(outs["plain"], outs[k])) for k in outs if k.startswith("lean")])
+print("16-byte records: max |diff| vs plain", [float((outs[k] - outs["plain"]).abs().max()) for k in ("rec16_28w_3g", "rec16_26w_5g")],
+      "fraction of entries that differ", float((outs["rec16_28w_3g"] != outs["plain"]).float().mean()))
 print("plain_geo_2cta == plain:", bool(torch.equal(outs["plain"], outs["plain_geo_2cta"])))
 print("plain_geo == plain:", bool(torch.equal(outs["plain"], outs["plain_geo"])),
       " fused_geo == fused:", bool(torch.equal(outs["fused"], outs["fused_geo"])),
