@@ -585,104 +585,110 @@ msda_fwd_geo_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_l
 #pragma unroll
         for (int l = 0; l < L_; ++l) { rW[l] = 1.f / Wf[l]; rH[l] = 1.f / Hf[l]; }
         (void)rW; (void)rH;
-        for_each_stage<L_, SW>(tabs, p, [&](int s, int b, int, int q_base, int nq, int kq, int yq, int x0q) {
-            const int slot = s % kStages, rslot = s % RSTAGES;
-            mbar_wait(&ring.full[slot], (s / kStages) & 1);
-            if constexpr (FUSED) {
-                // softmax over each query's logits, lane = query (this warp's share of the stage's queries)
-                for (int qi = gw * 32 + lane; qi < nq; qi += NGEO * 32) {
-                    float4 *sw = reinterpret_cast<float4 *>(ring.w_rw(slot, qi));
-                    float4 w[L_];
-#pragma unroll
-                    for (int l = 0; l < L_; ++l) w[l] = sw[l];
-                    float mx = fmaxf(fmaxf(w[0].x, w[0].y), fmaxf(w[0].z, w[0].w));
-#pragma unroll
-                    for (int l = 1; l < L_; ++l) mx = fmaxf(mx, fmaxf(fmaxf(w[l].x, w[l].y), fmaxf(w[l].z, w[l].w)));
-                    float sum = 0.f;
-#pragma unroll
-                    for (int l = 0; l < L_; ++l) {
-                        w[l].x = __expf(w[l].x - mx); w[l].y = __expf(w[l].y - mx);
-                        w[l].z = __expf(w[l].z - mx); w[l].w = __expf(w[l].w - mx);
-                        sum += (w[l].x + w[l].y) + (w[l].z + w[l].w);
-                    }
-                    const float inv = __frcp_rn(sum);
-#pragma unroll
-                    for (int l = 0; l < L_; ++l)
-                        sw[l] = make_float4(w[l].x * inv, w[l].y * inv, w[l].z * inv, w[l].w * inv);
-                }
-                // every geometry warp normalises the queries it reads below only if the split matches; with NGEO > 1 the
-                // point loop crosses queries of the other warp, so all geometry warps meet here first
-                if (NGEO > 1) asm volatile("bar.sync 2, %0;" ::"n"(NGEO * 32) : "memory");
-                else __syncwarp();
-            }
-            mbar_wait(&rec_empty[rslot], ((s / RSTAGES) & 1) ^ 1);
-            int4 *ro = Geo::offs(geo_smem, rslot);
-            float4 *rc = Geo::cws(geo_smem, rslot);
-            const StageRef<L_> sref(kq, yq, Wf, Hf);
-            (void)sref;
-            const int npts = nq * LP;
-            // a geometry warp is one dependent chain per point (~100 instructions): two points per trip give it the
-            // instruction-level parallelism to keep up with the consumers (measured: the record ring, not L1, paced the
-            // geometry-warp variants)
-#pragma unroll 2
-            for (int idx = gw * 32 + lane; idx < npts; idx += NGEO * 32) {
-                const int qi = idx / LP, j = idx - qi * LP;
-                const float2 xy = ring.loc(slot, qi)[j];
-                const float a = ring.w(slot, qi)[j];
-                int l = 0;
-#pragma unroll
-                for (int k = 1; k < L_; ++k) l = (j >= k * P_) ? k : l;
-                int Hl = H[0], Wl = W[0], stl = st[0];
-                float Hfl = Hf[0], Wfl = Wf[0], rWl = rW[0], rHl = rH[0];
-#pragma unroll
-                for (int k = 1; k < L_; ++k)
-                    if (l == k) { Hl = H[k]; Wl = W[k]; stl = st[k]; Hfl = Hf[k]; Wfl = Wf[k]; rWl = rW[k]; rHl = rH[k]; }
-                (void)rWl; (void)rHl;
-                float x = xy.x, y = xy.y;
+        // GMODE = record format of this launch (see the consumers): separate loop bodies keep the two-point unrolling tight
+        auto produce = [&](auto mode_c) {
+            constexpr int GMODE = decltype(mode_c)::value;
+            for_each_stage<L_, SW>(tabs, p, [&](int s, int b, int, int q_base, int nq, int kq, int yq, int x0q) {
+                const int slot = s % kStages, rslot = s % RSTAGES;
+                mbar_wait(&ring.full[slot], (s / kStages) & 1);
                 if constexpr (FUSED) {
-                    const int q = q_base + qi;
-                    float2 r;
-                    if (p.ref) r = __ldg(reinterpret_cast<const float2 *>(p.ref) + (static_cast<size_t>(b) * p.Lq + q) * L_ + l);
-                    else r = sref.centre(q, x0q + qi, st, W, Wf, Hf);
-                    x = fmaf(x, rWl, r.x);
-                    y = fmaf(y, rHl, r.y);
+                    // softmax over each query's logits, lane = query (this warp's share of the stage's queries)
+                    for (int qi = gw * 32 + lane; qi < nq; qi += NGEO * 32) {
+                        float4 *sw = reinterpret_cast<float4 *>(ring.w_rw(slot, qi));
+                        float4 w[L_];
+    #pragma unroll
+                        for (int l = 0; l < L_; ++l) w[l] = sw[l];
+                        float mx = fmaxf(fmaxf(w[0].x, w[0].y), fmaxf(w[0].z, w[0].w));
+    #pragma unroll
+                        for (int l = 1; l < L_; ++l) mx = fmaxf(mx, fmaxf(fmaxf(w[l].x, w[l].y), fmaxf(w[l].z, w[l].w)));
+                        float sum = 0.f;
+    #pragma unroll
+                        for (int l = 0; l < L_; ++l) {
+                            w[l].x = __expf(w[l].x - mx); w[l].y = __expf(w[l].y - mx);
+                            w[l].z = __expf(w[l].z - mx); w[l].w = __expf(w[l].w - mx);
+                            sum += (w[l].x + w[l].y) + (w[l].z + w[l].w);
+                        }
+                        const float inv = __frcp_rn(sum);
+    #pragma unroll
+                        for (int l = 0; l < L_; ++l)
+                            sw[l] = make_float4(w[l].x * inv, w[l].y * inv, w[l].z * inv, w[l].w * inv);
+                    }
+                    // every geometry warp normalises the queries it reads below only if the split matches; with NGEO > 1 the
+                    // point loop crosses queries of the other warp, so all geometry warps meet here first
+                    if (NGEO > 1) asm volatile("bar.sync 2, %0;" ::"n"(NGEO * 32) : "memory");
+                    else __syncwarp();
                 }
-                const Footprint f = make_footprint(x, y, Hl, Wl, Hfl, Wfl);
-                const int e00 = (stl + f.y0 * Wl + f.x0) * MD;
-                const float wy0 = a * f.hh, wy1 = a * f.lh;
-                if (LEAN == 2 && !degenerate) {
-                    // separable weights: rows (a * hh, a * lh) masked by the row tests, columns (hw, lw) by the column tests
-                    const bool y0ok = f.in_range && f.y0 >= 0, y1ok = f.in_range && f.y0 + 1 <= Hl - 1;
-                    float r0 = y0ok ? wy0 : 0.f, r1 = y1ok ? wy1 : 0.f;
-                    int ay = f.y0, ax = f.x0;
-                    if (!f.in_range) { ay = 0; ax = 0; }
-                    if (ay < 0) { ay = 0; r0 = r1; r1 = 0.f; }                        // row y = 0 is the footprint's lower row
-                    else if (ay > Hl - 2) { ay = Hl - 2; r1 = r0; r0 = 0.f; }         // row y = H - 1 is its upper row
-                    float lwf = f.lw;
-                    int flags = 0;
-                    if (ax < 0) { ax = 0; lwf = f.hw; flags = 2; }                    // column 0 carries lw: stored as hw, read as 1 - hw
-                    else if (ax > Wl - 2) { ax = Wl - 2; lwf = f.hw; flags = 1; }     // column W - 1 carries hw in slot 1
-                    const int e = (stl + ay * Wl + ax) * MD;
-                    rc[idx] = make_float4(__int_as_float(e | flags), r0, r1, lwf);
-                } else if constexpr (LEAN >= 1) {
-                    const int safe = (stl + max(min(max(f.y0, 0), Hl - 1), 0) * Wl + max(min(max(f.x0, 0), Wl - 1), 0)) * MD;   // (empty level: element 0)
-                    ro[idx] = make_int4(f.ok[0] ? e00 : safe, f.ok[1] ? e00 + MD : safe, f.ok[2] ? e00 + Wl * MD : safe,
-                                        f.ok[3] ? e00 + Wl * MD + MD : safe);
-                    rc[idx] = make_float4(f.ok[0] ? wy0 * f.hw : 0.f, f.ok[1] ? wy0 * f.lw : 0.f, f.ok[2] ? wy1 * f.hw : 0.f,
-                                          f.ok[3] ? wy1 * f.lw : 0.f);
-                } else {
-                ro[idx] = make_int4(f.ok[0] ? e00 : -1, f.ok[1] ? e00 + MD : -1, f.ok[2] ? e00 + Wl * MD : -1,
-                                    f.ok[3] ? e00 + Wl * MD + MD : -1);
-                rc[idx] = make_float4(wy0 * f.hw, wy0 * f.lw, wy1 * f.hw, wy1 * f.lw);
+                mbar_wait(&rec_empty[rslot], ((s / RSTAGES) & 1) ^ 1);
+                int4 *ro = Geo::offs(geo_smem, rslot);
+                float4 *rc = Geo::cws(geo_smem, rslot);
+                const StageRef<L_> sref(kq, yq, Wf, Hf);
+                (void)sref;
+                const int npts = nq * LP;
+                // a geometry warp is one dependent chain per point (~100 instructions): two points per trip give it the
+                // instruction-level parallelism to keep up with the consumers (measured: the record ring, not L1, paced the
+                // geometry-warp variants)
+    #pragma unroll 2
+                for (int idx = gw * 32 + lane; idx < npts; idx += NGEO * 32) {
+                    const int qi = idx / LP, j = idx - qi * LP;
+                    const float2 xy = ring.loc(slot, qi)[j];
+                    const float a = ring.w(slot, qi)[j];
+                    int l = 0;
+    #pragma unroll
+                    for (int k = 1; k < L_; ++k) l = (j >= k * P_) ? k : l;
+                    int Hl = H[0], Wl = W[0], stl = st[0];
+                    float Hfl = Hf[0], Wfl = Wf[0], rWl = rW[0], rHl = rH[0];
+    #pragma unroll
+                    for (int k = 1; k < L_; ++k)
+                        if (l == k) { Hl = H[k]; Wl = W[k]; stl = st[k]; Hfl = Hf[k]; Wfl = Wf[k]; rWl = rW[k]; rHl = rH[k]; }
+                    (void)rWl; (void)rHl;
+                    float x = xy.x, y = xy.y;
+                    if constexpr (FUSED) {
+                        const int q = q_base + qi;
+                        float2 r;
+                        if (p.ref) r = __ldg(reinterpret_cast<const float2 *>(p.ref) + (static_cast<size_t>(b) * p.Lq + q) * L_ + l);
+                        else r = sref.centre(q, x0q + qi, st, W, Wf, Hf);
+                        x = fmaf(x, rWl, r.x);
+                        y = fmaf(y, rHl, r.y);
+                    }
+                    const Footprint f = make_footprint(x, y, Hl, Wl, Hfl, Wfl);
+                    const int e00 = (stl + f.y0 * Wl + f.x0) * MD;
+                    const float wy0 = a * f.hh, wy1 = a * f.lh;
+                    if constexpr (GMODE == 2) {
+                        // separable weights: rows (a * hh, a * lh) masked by the row tests, columns (hw, lw) by the column tests
+                        const bool y0ok = f.in_range && f.y0 >= 0, y1ok = f.in_range && f.y0 + 1 <= Hl - 1;
+                        float r0 = y0ok ? wy0 : 0.f, r1 = y1ok ? wy1 : 0.f;
+                        int ay = f.y0, ax = f.x0;
+                        if (!f.in_range) { ay = 0; ax = 0; }
+                        if (ay < 0) { ay = 0; r0 = r1; r1 = 0.f; }                        // row y = 0 is the footprint's lower row
+                        else if (ay > Hl - 2) { ay = Hl - 2; r1 = r0; r0 = 0.f; }         // row y = H - 1 is its upper row
+                        float lwf = f.lw;
+                        int flags = 0;
+                        if (ax < 0) { ax = 0; lwf = f.hw; flags = 2; }                    // column 0 carries lw: stored as hw, read as 1 - hw
+                        else if (ax > Wl - 2) { ax = Wl - 2; lwf = f.hw; flags = 1; }     // column W - 1 carries hw in slot 1
+                        const int e = (stl + ay * Wl + ax) * MD;
+                        rc[idx] = make_float4(__int_as_float(e | flags), r0, r1, lwf);
+                    } else if constexpr (GMODE == 1) {
+                        const int safe = (stl + max(min(max(f.y0, 0), Hl - 1), 0) * Wl + max(min(max(f.x0, 0), Wl - 1), 0)) * MD;   // (empty level: element 0)
+                        ro[idx] = make_int4(f.ok[0] ? e00 : safe, f.ok[1] ? e00 + MD : safe, f.ok[2] ? e00 + Wl * MD : safe,
+                                            f.ok[3] ? e00 + Wl * MD + MD : safe);
+                        rc[idx] = make_float4(f.ok[0] ? wy0 * f.hw : 0.f, f.ok[1] ? wy0 * f.lw : 0.f, f.ok[2] ? wy1 * f.hw : 0.f,
+                                              f.ok[3] ? wy1 * f.lw : 0.f);
+                    } else {
+                    ro[idx] = make_int4(f.ok[0] ? e00 : -1, f.ok[1] ? e00 + MD : -1, f.ok[2] ? e00 + Wl * MD : -1,
+                                        f.ok[3] ? e00 + Wl * MD + MD : -1);
+                    rc[idx] = make_float4(wy0 * f.hw, wy0 * f.lw, wy1 * f.hw, wy1 * f.lw);
+                    }
                 }
-            }
-            if constexpr (FUSED) fence_proxy_async_smem();   // the raw slot (softmax written in place) goes back to TMA
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&ring.empty[slot]);
-                mbar_arrive(&rec_full[rslot]);
-            }
-        });
+                if constexpr (FUSED) fence_proxy_async_smem();   // the raw slot (softmax written in place) goes back to TMA
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&ring.empty[slot]);
+                    mbar_arrive(&rec_full[rslot]);
+                }
+            });
+        };
+        if (LEAN == 2 && degenerate) produce(std::integral_constant<int, 1>{});
+        else produce(std::integral_constant<int, LEAN>{});
         return;
     }
 
