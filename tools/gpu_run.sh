@@ -16,6 +16,7 @@ case $step in
   bwdcells) echo "== backward: cell-strided phase 2 A/B"; timeout 900 python -m pytest tests/test_gpu_bwd_sorted.py -x -q --timeout 600 2>&1 | tail -3
             timeout 600 python tools/bwd_ab2.py --set cells --reps 5 2>&1 | tee gpurun_out/r02_bwd_cells_ab.txt
             timeout 600 python tools/bwd_phases.py --variants 0,13,14,15,16 2>&1 | tee gpurun_out/r02_bwd_cells_phases.txt ;;
+  sass)     echo "== SASS census of the shipped default kernels"; python tools/sass_census.py > gpurun_out/r02_sass_main_kernels.txt 2>&1; head -40 gpurun_out/r02_sass_main_kernels.txt ;;
   ncusorted) echo "== ncu --set full: default forward + anchor-sorted backward (cfg 2 x 16)"
             python tools/ncu_target.py 16 > gpurun_out/ncu_plain_target.log 2>&1 && \
             ncu --set full --clock-control none --import-source on -k regex:msda_ -s 2 -c 2 -o gpurun_out/prof_r02_final -f python tools/ncu_target.py 16 > gpurun_out/ncu_full.log 2>&1
