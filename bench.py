@@ -178,10 +178,23 @@ def reference_cpu_function():
     return (lambda v, sh, loc, aw: O.torch_port_forward(v, sh, loc, aw)), "port"
 
 
-def workload_config(wl, world, nb, scaling):
-    """config keys shared by both arms (the driver compares them)"""
+def workload_config(wl, world, nb, scaling, tuning="default", cuda_graph=False):
+    """`config` of the JSON line, identical in both arms (the driver compares them key by key): the workload, how it is
+    partitioned, and the L2 policy, which is a property of the workload (its per-layer inputs exceed L2).  What is
+    specific to an arm (the CPU sample size, notes) goes into `cpu_baseline.sample` / top-level keys instead."""
+    esz = 2 if wl.dtype == "bf16" else 4
+    in_bytes = nb * (wl.S * 8 * 32 * esz * (2 if wl.mode == "fwd+bwd" else 1) + wl.S * 8 * wl.L * 4 * 3 * 4)
+    has_collective = wl.mode == "fwd+bwd" and wl.dtype == "f32" and world > 1
     return {"workload": wl.name, "cfg": wl.cfg, "levels": wl.levels, "global_batch": nb * world if scaling == "weak" else wl.batch,
-            "layers": wl.n_layers, "heads": 8, "head_dim": 32, "points": 4, "mode": wl.mode, "parallelism": f"dp{world}"}
+            "layers": wl.n_layers, "heads": 8, "head_dim": 32, "points": 4, "mode": wl.mode, "parallelism": f"dp{world}",
+            "batch_per_gpu": nb,
+            "l2_policy": (f"inputs larger than L2: {in_bytes / 1e6:.0f} MB of inputs per layer, {wl.n_layers} distinct "
+                          "layer input sets, no flush needed") if in_bytes > 126e6 else
+                         (f"{in_bytes / 1e6:.0f} MB of inputs per layer, {wl.n_layers} distinct layer input sets rotate "
+                          "(smaller than L2: launch-bound configuration, no explicit flush)"),
+            "collective": ("all-reduce of the 4.93 MB projection-gradient bucket per step (real gradients of six "
+                           "MSDeformAttn modules), side stream") if has_collective else "none",
+            "tuning": tuning, "cuda_graph": bool(cuda_graph)}
 
 
 def cpu_model():
@@ -225,6 +238,11 @@ def cpu_sample_images(wl):
 # --------------------------------------------------------------------------------------------
 # reference arm: the reference's CPU implementation of the path, host cores only
 # --------------------------------------------------------------------------------------------
+def b200_shard(batch, world):
+    """images of rank 0 when `batch` is split over `world` ranks (bm2f_b200.dist.shard_batch without importing torch.distributed)"""
+    return batch // world + (1 if batch % world else 0)
+
+
 def run_reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -245,14 +263,16 @@ def run_reference_arm(args, wl):
     ips = n_img / step_s
     sample = (f"each step = {n_img} image(s) of the batch x {wl.n_layers} layers {wl.mode} ({kind}: "
               f"ms_deform_attn_core_pytorch, F.grid_sample), {threads} torch threads; images/s = {n_img} / step time")
-    cfg = workload_config(wl, world, wl.batch, "strong")
-    cfg.update({"sample_images_per_step": n_img,
-                "note": "the reference has no native CPU kernel: its CPU path is ms_deform_attn_core_pytorch"})
+    scaling = args.scaling or ("strong" if world > 1 else "weak")
+    nb = b200_shard(wl.batch, world) if scaling == "strong" else wl.batch
+    cfg = workload_config(wl, world, nb, scaling, args.tuning or "default", args.graph)
     line = {
         "impl": "reference", "metric": "MSDeformAttn %s images/s" % wl.mode, "value": ips, "unit": "images/s",
         "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * step_s,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": cfg,
+        "reference_note": "the reference has no native CPU kernel: its CPU path is ms_deform_attn_core_pytorch "
+                          f"(ops/functions/ms_deform_attn_func.py:52-72); each step is a bounded sample of {n_img} image(s)",
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": kind, "sample": sample,
                          "cpu": cpu_model()},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -692,13 +712,8 @@ def run_ours(args, wl):
                "sample": f"{n_img} image(s) of the batch x {wl.n_layers} layers {wl.mode} per step, median of 3 steps "
                          f"(1 warm-up), step {step_s * 1e3:.0f} ms; torch {torch.__version__} {torch.get_num_threads()} threads"}
 
-    cfg = workload_config(wl, world, nb, scaling)
-    cfg.update({"batch_per_gpu": nb,
-                "l2_policy": f"inputs larger than L2: {in_bytes / 1e6:.0f} MB of inputs per layer, 6 distinct "
-                             "layer input sets, no flush needed",
-                "collective": ("all-reduce of the 4.93 MB projection-gradient bucket per step (real gradients of six "
-                               "MSDeformAttn modules), side stream") if grad_bucket is not None else "none",
-                "tuning": args.tuning or "default", "cuda_graph": graph is not None})
+    cfg = workload_config(wl, world, nb, scaling, args.tuning or "default", graph is not None)
+    assert (cfg["collective"] != "none") == (grad_bucket is not None)
     line = {
         "metric": "MSDeformAttn %s images/s" % wl.mode, "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,

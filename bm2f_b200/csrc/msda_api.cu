@@ -226,6 +226,13 @@ int run_fast(bool bwd, FastParams p, const Dims &d, int dtype, const bm2f_msda_t
         default: break;
         }
     }
+    // fused entry point on the same kernel (A/B, tuning.geo = 21 / 22 / 23: 28 + 3, 26 + 5, 24 + 7 warps): the geometry
+    // warps also do the softmax and the location arithmetic
+    if (!bwd && fused && t.geo >= 21 && t.geo <= 23 && c.tma && dtype == BM2F_DTYPE_F32 && d.L == 3) {
+        if (t.geo == 21) return launch_geo<float, 3, true, false, 1, 28, 2, 3>(p, ml, mw, grid, st);
+        if (t.geo == 22) return launch_geo<float, 3, true, false, 1, 26, 2, 5>(p, ml, mw, grid, st);
+        return launch_geo<float, 3, true, false, 1, 24, 2, 7>(p, ml, mw, grid, st);
+    }
     if (!bwd && t.geo == 11 && c.tma && c.sw == 32 && c.cps == 1 && !c.wide && dtype == BM2F_DTYPE_F32 && !fused && d.L == 3)
         return launch_geo<float, 3, false, false, 1, 28, 1, 3>(p, ml, mw, grid, st);      // 32-byte lean records (A/B)
     // geometry-warp forward variants kept for A/B (cfg shape, L = 3): tuning.geo = 1 with two CTAs per SM

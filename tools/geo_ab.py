@@ -20,7 +20,7 @@ logits = torch.randn(batch, S, M, L * P, device=dev)
 norm = torch.stack((shapes[:, 1], shapes[:, 0]), -1).float()
 loc = (ref[:, :, None, :, None, :] + offsets / norm[None, None, None, :, None, :]).contiguous()
 attn = torch.softmax(logits, -1).view(batch, S, M, L, P).contiguous()
-outs = {k: torch.empty(batch, S, M * D, device=dev) for k in ("plain", "plain_geo", "plain_geo_2cta", "plain_geo_wide", "fused", "fused_geo", "geo_20w", "geo_24w", "geo_28w", "lean_16w", "lean_24w", "lean_28w", "lean_28w_3g", "lean_26w_5g", "lean_24w_6g", "lean_24w_4g", "lean_20w_8g", "lean_16w_4g", "rec16_28w_3g", "rec16_26w_5g")}
+outs = {k: torch.empty(batch, S, M * D, device=dev) for k in ("plain", "plain_geo", "plain_geo_2cta", "plain_geo_wide", "fused", "fused_geo", "geo_20w", "geo_24w", "geo_28w", "lean_16w", "lean_24w", "lean_28w", "lean_28w_3g", "lean_26w_5g", "lean_24w_6g", "lean_24w_4g", "lean_20w_8g", "lean_16w_4g", "rec16_28w_3g", "rec16_26w_5g", "fused_rec16_28_3", "fused_rec16_26_5", "fused_rec16_24_7")}
 dims = (batch, S, M, D, L, S, P); st = torch.cuda.current_stream().cuda_stream
 geo = cabi.make_tuning(geo=1); geow = cabi.make_tuning(geo=3); geo2 = cabi.make_tuning(geo=1, ctas_per_sm=2)
 P_ = lambda t: t.data_ptr()
@@ -44,6 +44,9 @@ fns = {
     "rec16_28w_3g": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["rec16_28w_3g"]), dims, 0, cabi.make_tuning(geo=17), st),
     "rec16_26w_5g": lambda: cabi.forward(P_(value), P_(shapes), P_(start), P_(loc), P_(attn), P_(outs["rec16_26w_5g"]), dims, 0, cabi.make_tuning(geo=17), st),
     "fused": lambda: cabi.fused_forward(P_(value), P_(shapes), P_(start), 0, P_(offsets), P_(logits), P_(outs["fused"]), dims, 0, None, st),
+    "fused_rec16_28_3": lambda: cabi.fused_forward(P_(value), P_(shapes), P_(start), 0, P_(offsets), P_(logits), P_(outs["fused_rec16_28_3"]), dims, 0, cabi.make_tuning(geo=21), st),
+    "fused_rec16_26_5": lambda: cabi.fused_forward(P_(value), P_(shapes), P_(start), 0, P_(offsets), P_(logits), P_(outs["fused_rec16_26_5"]), dims, 0, cabi.make_tuning(geo=22), st),
+    "fused_rec16_24_7": lambda: cabi.fused_forward(P_(value), P_(shapes), P_(start), 0, P_(offsets), P_(logits), P_(outs["fused_rec16_24_7"]), dims, 0, cabi.make_tuning(geo=23), st),
     "fused_geo": lambda: cabi.fused_forward(P_(value), P_(shapes), P_(start), 0, P_(offsets), P_(logits), P_(outs["fused_geo"]), dims, 0, geo, st),
 }
 def t(fn):
@@ -62,6 +65,7 @@ print("geo 20 / 24 / 28 consumer warps == plain:", [bool(torch.equal(outs["plain
 print("lean variants == plain:", [bool(torch.equal(outs["plain"], outs[k])) for k in outs if k.startswith("lean")])
 print("16-byte records: max |diff| vs plain", [float((outs[k] - outs["plain"]).abs().max()) for k in ("rec16_28w_3g", "rec16_26w_5g")],
       "fraction of entries that differ", float((outs["rec16_28w_3g"] != outs["plain"]).float().mean()))
+print("fused 16-byte records: max |diff| vs fused", [float((outs[k] - outs["fused"]).abs().max()) for k in ("fused_rec16_28_3", "fused_rec16_26_5", "fused_rec16_24_7")])
 print("plain_geo_2cta == plain:", bool(torch.equal(outs["plain"], outs["plain_geo_2cta"])))
 print("plain_geo == plain:", bool(torch.equal(outs["plain"], outs["plain_geo"])),
       " fused_geo == fused:", bool(torch.equal(outs["fused"], outs["fused_geo"])),
