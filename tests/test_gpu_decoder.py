@@ -242,3 +242,48 @@ def test_fused_fpn_tail_runs_on_own_kernels(msda):
     # branch, so single entries of the gradients may differ by O(1): compare in the L2 norm
     for a, b, tol in zip(got, want, (5e-3, 2e-2, 2e-2, 2e-2)):
         assert ((a - b).norm() / b.norm()).item() <= tol
+
+
+def test_fused_fpn_tail_two_levels_and_unsupported_configuration(msda, fp32_convs):
+    """Two top-down FPN levels (transformer on res4 / res5 only): the second level upsamples the first level's token rows.
+    Compared with the reference op sequence on the same weights in fp32-grade arithmetic, forward and gradients.  A
+    decoder without GroupNorm (norm = "", conv biases) is outside the fused tail and must run the reference sequence."""
+    from bm2f_b200.pixel_decoder import MSDeformAttnPixelDecoder, ShapeSpec
+    from bm2f_b200.ops.functions import fpn_func
+    torch.manual_seed(11)
+    chans = {"res2": 256, "res3": 512, "res4": 1024, "res5": 2048}
+    shapes = {k: ShapeSpec(channels=c, stride=4 * 2 ** i) for i, (k, c) in enumerate(chans.items())}
+    sizes = {"res5": (3, 4), "res4": (6, 8), "res3": (12, 16), "res2": (24, 32)}
+
+    def build(norm):
+        torch.manual_seed(12)
+        return MSDeformAttnPixelDecoder(shapes, transformer_dropout=0.0, transformer_nheads=8, transformer_dim_feedforward=1024,
+                                        transformer_enc_layers=1, conv_dim=256, mask_dim=256, norm=norm,
+                                        transformer_in_features=["res4", "res5"], common_stride=4).to(DEV).train()
+
+    dec = build("GN")
+    assert dec.num_fpn_levels == 2
+    feats = {k: torch.randn(2, chans[k], *sizes[k], device=DEV, requires_grad=True) for k in chans}
+    assert fpn_func.supported([feats["res3"], feats["res2"]], dec.lateral_convs, dec.output_convs, dec.mask_features)
+
+    def run(d):
+        for v in feats.values():
+            v.grad = None
+        d.zero_grad(set_to_none=True)
+        mf, out0, multi = d.forward_features(feats)
+        assert len(multi) == 3 and multi[2].shape[-2:] == sizes["res3"]          # the first FPN level is the third scale
+        (mf.square().mean() + sum(m.square().mean() for m in multi)).backward()
+        return [mf.detach().clone(), multi[2].detach().clone(), feats["res2"].grad.clone(), feats["res3"].grad.clone(),
+                feats["res5"].grad.clone(), d.layer_1.weight.grad.clone(), d.layer_2.weight.grad.clone(),
+                d.adapter_2.weight.grad.clone(), d.mask_features.bias.grad.clone()]
+
+    got = run(dec)
+    dec.fused = False
+    want = run(dec)
+    for a, b in zip(got, want):
+        assert a.shape == b.shape
+        assert ((a - b).norm() / b.norm()).item() <= 2e-4          # tf32x3 at K = 2304 on one side, cuDNN fp32 on the other
+    plain = build("")
+    assert not fpn_func.supported([feats["res3"], feats["res2"]], plain.lateral_convs, plain.output_convs, plain.mask_features)
+    mf, _, _ = plain.forward_features(feats)
+    assert mf.shape == (2, 256, 24, 32)

@@ -26,6 +26,8 @@ case $step in
             ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-ref-cuda > gpurun_out/ncu_bench.log 2>&1
             echo "rc=$?" ;;
   geoab)    echo "== forward: geometry warps with 16 / 20 / 24 / 28 consumer warps"; timeout 600 python tools/geo_ab.py 16 5 2>&1 | tee gpurun_out/r02_fwd_geo_warps_ab.txt ;;
+  modbench) echo "== module / encoder benches"; timeout 600 python tools/module_bench.py 2>&1 | tee gpurun_out/r02_module_bench.txt | tail -12
+            timeout 900 python tools/encoder_bench.py 2>&1 | tee gpurun_out/r02_encoder_bench.txt | tail -8 ;;
   *) echo "unknown step $step" ;;
 esac
 done
