@@ -624,7 +624,7 @@ def run_ours(args, wl):
     alg_bytes = W.hbm_bytes(wl.S, dom, wl.dtype) * nb          # per launch (SURVEY §8d per image-layer x images)
     achieved = alg_bytes / (kms[dom] * 1e-3) / 1e9
     traffic = facts.get("dram_bytes_per_launch", {}).get(f"cfg{wl.cfg}_{dom}") if nb == wl.batch else None
-    sorted_bwd = (bwd and wl.dtype == "f32" and nb * wl.S >= 65536 and "bwd=" not in (args.tuning or ""))   # msda_api.cu:choose_bwd_sorted
+    sorted_bwd = (bwd and wl.dtype == "f32" and nb * wl.S >= 32768 and "bwd=" not in (args.tuning or ""))   # msda_api.cu:choose_bwd_sorted
     kname = ("msda_bwd_sorted_kernel" if sorted_bwd else "msda_bwd_fast_kernel") + " (+grad_value zero-fill)" if bwd else "msda_fwd_fast_kernel"
     roofline = {"bound": "hbm", "kernel": kname,
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],

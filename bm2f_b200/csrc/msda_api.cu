@@ -38,9 +38,10 @@ int choose_bwd_sorted(const Dims &d, int dtype, const bm2f_msda_tuning_t &t, boo
     if (t.bwd == 2 && !ok)
         return fail(BM2F_ERR_UNSUPPORTED, "anchor-sorted backward needs float32, D=32, M=8, P=4, L<=4, num_query == spatial_size "
                     "and order == 0 (got D=%d M=%d P=%d L=%d Lq=%d S=%d dtype=%d)", d.D, d.M, d.P, d.L, d.Lq, d.S, dtype);
-    // default: only where it was measured faster — enough (image, query) rows to fill the machine with whole chunks
-    // (a single 512^2 image is launch / tail bound and stays on the per-corner kernel)
-    const bool big = static_cast<long long>(d.N) * d.Lq >= 65536;
+    // default: only where it was measured faster — enough (image, query) rows to fill the machine with whole chunks:
+    // cfg 2 at 2 / 3 / 4 images (43 008+ rows) 0.338 / 0.490 / 0.649 ms vs 0.369 / 0.540 / 0.713 per-corner; a single
+    // 512^2 image (5 376 rows) is launch / tail bound and stays on the per-corner kernel (0.065 vs 0.100 ms)
+    const bool big = static_cast<long long>(d.N) * d.Lq >= 32768;
     *sorted = ok && t.bwd != 1 && (t.bwd == 2 || (BM2F_BWD_SORTED_DEFAULT && big));
     return BM2F_OK;
 }

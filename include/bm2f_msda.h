@@ -93,7 +93,7 @@ typedef struct {
                        gathers (L = 3).  All equal bit for bit, except that 0 may differ by one rounding of a bilinear
                        weight (2^-25) for points whose footprint crosses the left border of a level   */
     int bwd;        /* backward kernel: 0 = default (anchor-sorted when it applies — float32, D = 32, M = 8, P = 4, L <= 4,
-                       num_query == spatial_size, order == 0 — and batch * num_query >= 65536; per-corner otherwise),
+                       num_query == spatial_size, order == 0 — and batch * num_query >= 32768; per-corner otherwise),
                        1 = per-corner vector REDs (msda_bwd_fast_kernel), 2 = anchor-sorted, error if it does not apply
                         */
     int bwd_margin; /* anchor-sorted backward: window margin around a query tile in pixels of the sampled level; points
