@@ -238,6 +238,11 @@ def cpu_sample_images(wl):
 # --------------------------------------------------------------------------------------------
 # reference arm: the reference's CPU implementation of the path, host cores only
 # --------------------------------------------------------------------------------------------
+def graph_enabled(args, wl, nb):
+    """CUDA-graph replay of the step: explicit --graph / --no-graph, else on for launch-bound per-GPU steps"""
+    return bool(args.graph) if args.graph is not None else nb * wl.S < 100000
+
+
 def b200_shard(batch, world):
     """images of rank 0 when `batch` is split over `world` ranks (bm2f_b200.dist.shard_batch without importing torch.distributed)"""
     return batch // world + (1 if batch % world else 0)
@@ -265,7 +270,7 @@ def run_reference_arm(args, wl):
               f"ms_deform_attn_core_pytorch, F.grid_sample), {threads} torch threads; images/s = {n_img} / step time")
     scaling = args.scaling or ("strong" if world > 1 else "weak")
     nb = b200_shard(wl.batch, world) if scaling == "strong" else wl.batch
-    cfg = workload_config(wl, world, nb, scaling, args.tuning or "default", args.graph)
+    cfg = workload_config(wl, world, nb, scaling, args.tuning or "default", graph_enabled(args, wl, nb))
     line = {
         "impl": "reference", "metric": "MSDeformAttn %s images/s" % wl.mode, "value": ips, "unit": "images/s",
         "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * step_s,
@@ -522,7 +527,7 @@ def run_ours(args, wl):
     sync_all()
 
     graph, graph_launches = None, 0
-    if args.graph:
+    if graph_enabled(args, wl, nb):
         # every launch of a step goes through the C ABI on the current stream: tensor maps are encoded on the host and
         # passed by value, the zero-fill is a memset node, nothing synchronises -> the whole step is capturable
         l0 = cabi.launch_count()
@@ -777,9 +782,11 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="override images per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--tuning", default="", help="e.g. vec=4,staging=1,strip_w=16,rows=32,ctas_per_sm=2")
-    ap.add_argument("--graph", action="store_true",
-                    help="replay one step (all layers, fwd+bwd) from a CUDA graph in the timed loop: for launch-bound "
-                         "configs (cfg 1: one 512^2 image, 35 us of launch overhead per layer)")
+    ap.add_argument("--graph", dest="graph", action="store_const", const=True, default=None,
+                    help="replay one step (all layers, fwd+bwd) from a CUDA graph in the timed loop.  Default: on when "
+                         "the per-GPU step is launch-bound (fewer than 100 000 (image, query) rows per GPU: cfg 1, or "
+                         "2-4 images per GPU in a strong-scaling run), off otherwise")
+    ap.add_argument("--no-graph", dest="graph", action="store_const", const=False)
     ap.add_argument("--scaling", default="", choices=["", "strong", "weak"],
                     help="N > 1: strong (default) splits the config's global batch over the ranks (SURVEY section 8e: "
                          "16/8/4/2 images per GPU); weak keeps the config's batch on every GPU")

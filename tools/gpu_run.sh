@@ -9,8 +9,8 @@ case $step in
   smoke)    echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 ;;
   bench)    echo "== bench"; timeout 900 python bench.py > gpurun_out/r02_bench_n1.jsonl 2> gpurun_out/bench_n1.err; tail -2 gpurun_out/bench_n1.err; cut -c1-300 gpurun_out/r02_bench_n1.jsonl ;;
   benchref) echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null > gpurun_out/r02_bench_reference.jsonl; cut -c1-200 gpurun_out/r02_bench_reference.jsonl ;;
-  batch2)   echo "== bench batch 2 on one GPU (what a rank of the N=8 strong run executes)"; timeout 600 python bench.py --batch 2 --no-e2e --no-cpu --no-ref-cuda --steps 10 --warmup 3 2>/dev/null | tee gpurun_out/r02_bench_batch2_n1.jsonl | cut -c1-330
-            timeout 600 python bench.py --batch 2 --no-e2e --no-cpu --no-ref-cuda --steps 10 --warmup 3 --graph 2>/dev/null | tee -a gpurun_out/r02_bench_batch2_n1.jsonl | cut -c1-330 ;;
+  batch2)   echo "== bench batch 2 on one GPU (what a rank of the N=8 strong run executes)"; timeout 600 python bench.py --batch 2 --no-e2e --no-cpu --no-ref-cuda --steps 10 --warmup 3 --no-graph 2>/dev/null | tee gpurun_out/r02_bench_batch2_n1.jsonl | cut -c1-330
+            timeout 600 python bench.py --batch 2 --no-e2e --no-cpu --no-ref-cuda --steps 10 --warmup 3 2>/dev/null | tee -a gpurun_out/r02_bench_batch2_n1.jsonl | cut -c1-330 ;;
   decbench) echo "== decoder bench"; timeout 900 python tools/decoder_bench.py 2>&1 | tee gpurun_out/r02_decoder_bench.txt | tail -30 ;;
   fpnbench) echo "== fpn bench"; timeout 900 python tools/fpn_bench.py 2>&1 | tee gpurun_out/r02_fpn_bench.txt | tail -40 ;;
   bwdcells) echo "== backward: cell-strided phase 2 A/B"; timeout 900 python -m pytest tests/test_gpu_bwd_sorted.py -x -q --timeout 600 2>&1 | tail -3
