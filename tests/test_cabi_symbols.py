@@ -80,3 +80,62 @@ def test_extension_surface_and_cpu_error(built):
     with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
         m.ms_deform_attn_backward(v, torch.tensor([[2, 2]]), torch.tensor([0]), torch.zeros(1, 4, 8, 1, 4, 2),
                                   torch.zeros(1, 4, 8, 1, 4), torch.zeros(1, 4, 256), 128)
+
+
+def test_fpn_entry_points_check_arguments_without_gpu(built):
+    """FPN-tail entry points (include/bm2f_msda.h, msdeformattn.py:341-358): sizes and argument checks that run before
+    anything touches a device; the torch-facing wrappers refuse CPU tensors like the rest of the module."""
+    import ctypes
+
+    import torch
+
+    import bm2f_b200
+    from bm2f_b200 import cabi
+    L = cabi.lib()
+    L.bm2f_conv3x3_workspace_bytes.restype = ctypes.c_size_t
+    assert L.bm2f_conv3x3_workspace_bytes(256, 256) == 2 * 256 * 256 * 9 * 4      # hi + lo halves of the GEMM weights
+    assert L.bm2f_conv3x3_workspace_bytes(0, 256) == 0
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    L.bm2f_conv3x3_forward.argtypes = [vp] * 4 + [ci] * 6 + [vp]
+    L.bm2f_conv3x3_forward.restype = ci
+    assert L.bm2f_conv3x3_forward(None, None, None, None, 1, 4, 4, 256, 256, 1, None) == -1          # BM2F_ERR_INVALID
+    assert "null" in cabi.last_error()
+    assert L.bm2f_conv3x3_forward(16, 16, 16, 16, 1, 4, 4, 128, 256, 1, None) == -2                  # BM2F_ERR_UNSUPPORTED
+    assert "256 -> 256" in cabi.last_error()
+    assert L.bm2f_conv3x3_forward(16, 16, 16, 16, 0, 4, 4, 256, 256, 1, None) == -1
+    assert L.bm2f_conv3x3_forward(16, 16, 16, 16, 1, 4, 4, 256, 256, 2, None) == -1
+    assert "split" in cabi.last_error()
+    L.bm2f_conv3x3_set_variant.argtypes = [ci]
+    assert L.bm2f_conv3x3_set_variant(1) == 0
+    m = bm2f_b200.load_extension()
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        m.conv3x3_tokens_forward(torch.zeros(1, 6, 6, 256), torch.zeros(256, 256, 3, 3), 1)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        m.groupnorm_tokens_stats(torch.zeros(1, 4, 4, 256), 1e-5)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        m.fpn_upsample_backward(torch.zeros(1, 4, 4, 256), 2, 2)
+
+
+def test_fused_fpn_tail_is_selected_only_for_the_standard_configuration(built):
+    """Host logic of ops/functions/fpn_func.supported: GroupNorm(32) convs without bias, 256 channels, ReLU after the 3x3."""
+    import torch
+
+    from bm2f_b200.ops.functions import fpn_func
+    from bm2f_b200.pixel_decoder import MSDeformAttnPixelDecoder, ShapeSpec
+    shapes = {k: ShapeSpec(channels=c, stride=4 * 2 ** i) for i, (k, c) in enumerate(
+        {"res2": 256, "res3": 512, "res4": 1024, "res5": 2048}.items())}
+    kw = dict(transformer_dropout=0.0, transformer_nheads=8, transformer_dim_feedforward=1024, transformer_enc_layers=1,
+              conv_dim=256, mask_dim=256, transformer_in_features=["res3", "res4", "res5"], common_stride=4)
+    gn = MSDeformAttnPixelDecoder(shapes, norm="GN", **kw)
+    plain = MSDeformAttnPixelDecoder(shapes, norm="", **kw)
+    x = torch.zeros(1, 256, 8, 8)
+    # CPU tensors are never eligible (no CPU path); the same modules with a CUDA tensor are checked in the GPU suite
+    assert not fpn_func.supported([x], gn.lateral_convs, gn.output_convs, gn.mask_features)
+
+    class FakeCuda:
+        is_cuda, dtype = True, torch.float32
+    assert fpn_func.supported([FakeCuda()], gn.lateral_convs, gn.output_convs, gn.mask_features)
+    assert not fpn_func.supported([FakeCuda()], plain.lateral_convs, plain.output_convs, plain.mask_features)
+    half = FakeCuda()
+    half.dtype = torch.float16
+    assert not fpn_func.supported([half], gn.lateral_convs, gn.output_convs, gn.mask_features)

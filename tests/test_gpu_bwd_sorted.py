@@ -28,6 +28,18 @@ def _pyramid(z):
     return z["value"].shape[2:] == (8, 32) and z["loc"].shape[4] == 4 and z["loc"].shape[1] == z["value"].shape[1]
 
 
+_CONFIG_PROBLEMS = {}
+
+
+def _config_problem(cfg, batch, dist):
+    """inputs + CPU-oracle results of a BASELINE config shape, computed once per (cfg, batch, dist) for all kernel variants"""
+    key = (cfg, batch, dist)
+    if key not in _CONFIG_PROBLEMS:
+        inp = W.workload_inputs(cfg, batch=batch, dist=dist)
+        _CONFIG_PROBLEMS[key] = (inp, oracle_ref(inp))
+    return _CONFIG_PROBLEMS[key]
+
+
 @pytest.fixture(scope="module")
 def small_problem():
     inp = W.make_inputs(SMALL_LEVELS, 3, seed=77)
@@ -69,8 +81,7 @@ def test_sorted_backward_level_counts_and_ragged_shapes(levels, dist, built):
 @pytest.mark.parametrize("cfg,batch,dist", [(1, 1, "model"), (1, 1, "uniform"), (2, 2, "model"), (4, 1, "model"),
                                             (5, 4, "model")])
 def test_sorted_backward_config_shapes_vs_oracle(cfg, batch, dist, variant, built):
-    inp = W.workload_inputs(cfg, batch=batch, dist=dist)
-    ref = oracle_ref(inp)
+    inp, ref = _config_problem(cfg, batch, dist)
     res = run_cabi(inp["value"], inp["shapes"], inp["start"], inp["loc"], inp["attn"], inp["grad_out"],
                    tuning=cabi.make_tuning(bwd=2, variant=variant))
     check_f32(res, ref, inp["loc"].numpy(), inp["shapes"].numpy(), f"cfg{cfg} variant {variant}")
