@@ -566,7 +566,7 @@ def run_ours(args, wl):
     launches = cabi.launch_count() - launches0
     if graph is not None:
         launches = graph_launches * args.steps      # replayed launches do not pass through the launch counter
-        for _ in range(3):                          # per-kernel times for the roofline: separate, un-graphed pass
+        for _ in range(6):                          # per-kernel times for the roofline: separate, un-graphed passes
             step(record=True, collective=False)
         torch.cuda.synchronize()
     # keep the GPU busy a little longer so the sampler certainly has samples under load
@@ -583,7 +583,10 @@ def run_ours(args, wl):
     ms_per_step = elapsed_ms / args.steps
     value = images_total / (ms_per_step * 1e-3)
 
-    kms = {k: statistics.mean(a.elapsed_time(b) for a, b in v) for k, v in kernel_events.items() if v}
+    # un-graphed passes of a launch-bound step: the GPU waits for the host between launches, so single event pairs can
+    # include host gaps -> median there; mean over the timed loop otherwise
+    agg = statistics.median if graph is not None else statistics.mean
+    kms = {k: agg([a.elapsed_time(b) for a, b in v]) for k, v in kernel_events.items() if v}
 
     # ---- end to end through the C ABI host entry (every rank drives its own GPU) -------------------
     e2e = None

@@ -28,6 +28,8 @@ case $step in
   geoab)    echo "== forward: geometry warps with 16 / 20 / 24 / 28 consumer warps"; timeout 600 python tools/geo_ab.py 16 5 2>&1 | tee gpurun_out/r02_fwd_geo_warps_ab.txt ;;
   modbench) echo "== module / encoder benches"; timeout 600 python tools/module_bench.py 2>&1 | tee gpurun_out/r02_module_bench.txt | tail -12
             timeout 900 python tools/encoder_bench.py 2>&1 | tee gpurun_out/r02_encoder_bench.txt | tail -8 ;;
+  allcfg)   echo "== bench lines of the other BASELINE configs"; rm -f gpurun_out/r02_bench_lines_final.jsonl
+            for c in 1 3 4 5; do timeout 600 python bench.py --cfg $c --no-e2e --steps 10 --warmup 3 2>/dev/null | tee -a gpurun_out/r02_bench_lines_final.jsonl | cut -c1-200; done ;;
   *) echo "unknown step $step" ;;
 esac
 done
