@@ -276,6 +276,7 @@ def run_reference_arm(args, wl):
         "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * step_s,
         "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": cfg,
+        "sample_images_per_step": n_img,
         "reference_note": "the reference has no native CPU kernel: its CPU path is ms_deform_attn_core_pytorch "
                           f"(ops/functions/ms_deform_attn_func.py:52-72); each step is a bounded sample of {n_img} image(s)",
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": kind, "sample": sample,

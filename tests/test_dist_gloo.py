@@ -99,7 +99,16 @@ def test_reference_arm_under_torchrun_only_rank0_works():
     assert d["cpu_baseline"]["kind"] == ("reference" if staged else "port")
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["n_gpus"] == 2
     # a real, bounded step: value = sample images / measured step time, and the step list fits the run
-    n = d["config"]["sample_images_per_step"]
+    n = d["sample_images_per_step"]
     assert abs(d["value"] - n / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
-    for k in ("workload", "cfg", "levels", "global_batch", "layers", "heads", "head_dim", "points", "mode", "parallelism"):
-        assert k in d["config"], k
+    # `config` is built by the function the GPU arm uses: same keys, same values for the same command line
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench_mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench_mod)
+    from bm2f_b200 import workloads as W
+    import types
+    graph = bench_mod.graph_enabled(types.SimpleNamespace(graph=None), W.WORKLOADS[5], 16)     # launch-bound rule of both arms
+    want = bench_mod.workload_config(W.WORKLOADS[5], 2, 16, "strong", "default", graph)
+    assert json.loads(json.dumps(want)) == d["config"]
+    assert d["config"]["parallelism"] == "dp2" and d["config"]["batch_per_gpu"] == 16 and d["scaling"] == "strong"
