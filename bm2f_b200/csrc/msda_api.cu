@@ -234,6 +234,9 @@ int run_fast(bool bwd, FastParams p, const Dims &d, int dtype, const bm2f_msda_t
         if (t.geo == 22) return launch_geo<float, 3, true, false, 1, 26, 2, 5>(p, ml, mw, grid, st);
         return launch_geo<float, 3, true, false, 1, 24, 2, 7>(p, ml, mw, grid, st);
     }
+    // the same kernel on bf16 values (cfg 3: Swin-L, bf16 forward): 64-byte corner lines, fp32 records and accumulation
+    if (!bwd && (t.geo == 0 || t.geo == 17) && c.tma && c.sw == 32 && c.cps == 1 && !c.wide && dtype == BM2F_DTYPE_BF16 && !fused && d.L == 3)
+        return launch_geo<__nv_bfloat16, 3, false, false, 1, 28, 2, 3>(p, ml, mw, grid, st);
     if (!bwd && t.geo == 11 && c.tma && c.sw == 32 && c.cps == 1 && !c.wide && dtype == BM2F_DTYPE_F32 && !fused && d.L == 3)
         return launch_geo<float, 3, false, false, 1, 28, 1, 3>(p, ml, mw, grid, st);      // 32-byte lean records (A/B)
     // geometry-warp forward variants kept for A/B (cfg shape, L = 3): tuning.geo = 1 with two CTAs per SM
