@@ -140,24 +140,6 @@ __device__ __forceinline__ void pixel_window(PixelWin &w, const SortedTabs &t, c
     w.ncells = base;
 }
 
-// packed fp32 pairs: FFMA2 (fma.rn.f32x2) does two FMAs per issue slot on sm_100a
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi)
-{
-    unsigned long long d;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
-    return d;
-}
-__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi)
-{
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c)
-{
-    unsigned long long d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-
 template <int L_, int RMAX, int NWARP, bool FUSED, int CELLS_MAX, int CPS, bool F2 = true>
 __global__ void __launch_bounds__(NWARP * 32, CPS)
 msda_bwd_pixel_kernel(const FastParams p, const int marg, long long *prof_out, const __grid_constant__ CUtensorMap tm_loc,

@@ -253,6 +253,24 @@ __device__ __forceinline__ int sorted_block_scan(uint32_t *cnt, int n, uint32_t 
     return static_cast<int>(carry);
 }
 
+// packed fp32 pairs: FFMA2 (fma.rn.f32x2) does two FMAs per issue slot on sm_100a
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi)
+{
+    unsigned long long d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 constexpr int kSortedSkip = -1;       // record already final ({ga, gx, gy, a}); not in the sorted list
 
 // PIPE: 0 lane groups walk equal ranges of the sorted list, 1 same with the next anchor's lines prefetched,
@@ -604,12 +622,29 @@ msda_bwd_sorted_kernel(const FastParams p, const int marg, long long *prof_out, 
                 const float a = rec.x, lh = rec.y, lw = rec.z;
                 const float hh = 1.f - lh, hw = 1.f - lw;
                 float t[4];
+#ifdef BM2F_SORTED_F2      // A/B: measured neutral (2.55 vs 2.54 ms: the kernel is latency-bound, not issue-bound)
+                // packed pairs: the 64 FMAs of a point (4 dot products + 4 accumulator updates over CH channels) issue as
+                // 32 FFMA2; a dot product becomes two interleaved partial sums
+                unsigned long long go2[CH / 2];
+#pragma unroll
+                for (int c = 0; c < CH / 2; ++c) go2[c] = pack2(go[2 * c], go[2 * c + 1]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    unsigned long long t2 = pack2(0.f, 0.f);
+#pragma unroll
+                    for (int c = 0; c < CH / 2; ++c) t2 = ffma2(go2[c], pack2(v[k][2 * c], v[k][2 * c + 1]), t2);
+                    float lo, hi;
+                    unpack2(t2, lo, hi);
+                    t[k] = lo + hi;
+                }
+#else
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     t[k] = 0.f;
 #pragma unroll
                     for (int c = 0; c < CH; ++c) t[k] = fmaf(go[c], v[k][c], t[k]);
                 }
+#endif
                 float pa = hh * (hw * t[0] + lw * t[1]) + lh * (hw * t[2] + lw * t[3]);
                 float px = hh * (t[1] - t[0]) + lh * (t[3] - t[2]);
                 float py = hw * (t[2] - t[0]) + lw * (t[3] - t[1]);
@@ -621,10 +656,22 @@ msda_bwd_sorted_kernel(const FastParams p, const int marg, long long *prof_out, 
                 }
                 const float wy0 = a * hh, wy1 = a * lh;
                 const float cw[4] = {wy0 * hw, wy0 * lw, wy1 * hw, wy1 * lw};
+#ifdef BM2F_SORTED_F2      // A/B: measured neutral (2.55 vs 2.54 ms: the kernel is latency-bound, not issue-bound)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned long long cw2 = pack2(cw[k], cw[k]);
+#pragma unroll
+                    for (int c = 0; c < CH / 2; ++c) {
+                        const unsigned long long a2 = ffma2(cw2, go2[c], pack2(acc[k][2 * c], acc[k][2 * c + 1]));
+                        unpack2(a2, acc[k][2 * c], acc[k][2 * c + 1]);
+                    }
+                }
+#else
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
 #pragma unroll
                     for (int c = 0; c < CH; ++c) acc[k][c] = fmaf(cw[k], go[c], acc[k][c]);
+#endif
                 if (sub == 0) s_rec[pt] = make_float4(pa, a * px, a * py, a);
             };
 
