@@ -100,6 +100,7 @@ int pick(const FastParams &p, int marg, int lanes, int variant, const CUtensorMa
         case 144: BM2F_V(8, 4, 2, 3, RMAX);
         case 154: BM2F_V(16, 4, 1, 2, 8);
         case 164: BM2F_V(16, 4, 1, 3, 8);
+        case 174: BM2F_V(8, 4, 2, 0, 4);        // 17: 128-query chunks (78 KB per CTA, more of the SM's memory left to L1): 2.70 ms
         default: break;
         }
     }

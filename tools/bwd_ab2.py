@@ -54,7 +54,7 @@ def main():
                 cases.append((f"owner variant {v} margin {m}", dict(bwd=2, bwd_margin=m, variant=v)))
     else:
         # sorted kernel, phase 2 by cell ownership: 13 = 2 CTAs x 8 warps, 14 = + prefetch, 15 = 1 CTA x 16 warps, 16 = + prefetch
-        for v, lanes in ((13, 4), (13, 8), (14, 4), (15, 4), (16, 4)):
+        for v, lanes in ((17, 4), (13, 4), (13, 8), (14, 4), (15, 4), (16, 4)):
             for m in ((6, 5, 8) if v in (13, 14) and lanes == 4 else (6,)):
                 cases.append((f"cell-strided v{v} lanes {lanes} margin {m}", dict(bwd=2, bwd_lanes=lanes, bwd_margin=m, variant=v)))
     for name, kw in cases:
