@@ -19,7 +19,8 @@ SYMBOLS = (
     "bm2f_msda_abi_version", "bm2f_msda_build_info", "bm2f_msda_last_error", "bm2f_msda_launch_count",
     "bm2f_msda_set_default_tuning", "bm2f_msda_debug_phase_profile", "bm2f_msda_check_im2col_step", "bm2f_msda_forward",
     "bm2f_msda_backward", "bm2f_msda_forward_backward_host", "bm2f_msda_release_host_workspace", "bm2f_msda_fused_supported",
-    "bm2f_msda_fused_forward", "bm2f_msda_fused_backward", "bm2f_linear_workspace_bytes", "bm2f_linear_set_tuning",
+    "bm2f_msda_fused_forward", "bm2f_msda_fused_backward", "bm2f_msda_fused_forward_packed",
+    "bm2f_msda_fused_backward_packed", "bm2f_linear_workspace_bytes", "bm2f_linear_set_tuning",
     "bm2f_linear_forward",
     "bm2f_linear_backward_input", "bm2f_linear_backward_weight", "bm2f_linear_relu_forward",
     "bm2f_linear_backward_input_masked", "bm2f_linear_backward_input_accumulate", "bm2f_add_layernorm_forward",

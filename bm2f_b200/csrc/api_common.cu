@@ -82,12 +82,12 @@ int device_info(int *sms, int *cc_major)
 
 // 2-D fp32 matrix (rows x cols, row-major) -> boxes of (box_rows x box_cols).
 int make_map(CUtensorMap *map, const float *base, uint64_t rows, uint64_t cols, uint32_t box_rows,
-             uint32_t box_cols, int swizzle)
+             uint32_t box_cols, int swizzle, uint64_t ld_elems)
 {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(BM2F_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
     const cuuint64_t gdim[2] = {cols, rows};
-    const cuuint64_t gstride[1] = {cols * sizeof(float)};
+    const cuuint64_t gstride[1] = {(ld_elems ? ld_elems : cols) * sizeof(float)};
     const cuuint32_t box[2] = {box_cols, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstride, box,

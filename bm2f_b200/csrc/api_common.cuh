@@ -41,8 +41,9 @@ int ensure_dynamic_smem(int bytes, const char *what)
 
 // 2-D fp32 matrix (rows x cols, row-major) -> boxes of (box_rows x box_cols).
 // swizzle: 0 none, 1 (true) SWIZZLE_128B, 2 SWIZZLE_128B_ATOM_32B (32-byte swizzle units: MN-major TF32 MMA operands)
+// ld_elems: row stride in elements when the matrix is a column block of a wider one (0 = cols)
 int make_map(CUtensorMap *map, const float *base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols,
-             int swizzle = 0);
+             int swizzle = 0, uint64_t ld_elems = 0);
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

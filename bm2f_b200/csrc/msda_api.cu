@@ -205,8 +205,8 @@ int run_fast(bool bwd, FastParams p, const Dims &d, int dtype, const bm2f_msda_t
     if (c.tma) {
         const int LP = d.L * d.P;
         const uint64_t rows_total = static_cast<uint64_t>(d.N) * d.Lq;
-        if ((rc = make_map(&ml, p.loc, rows_total, static_cast<uint64_t>(d.M) * LP * 2, c.sw, LP * 2))) return rc;
-        if ((rc = make_map(&mw, p.attn, rows_total, static_cast<uint64_t>(d.M) * LP, c.sw, LP))) return rc;
+        if ((rc = make_map(&ml, p.loc, rows_total, static_cast<uint64_t>(d.M) * LP * 2, c.sw, LP * 2, 0, p.ld_packed))) return rc;
+        if ((rc = make_map(&mw, p.attn, rows_total, static_cast<uint64_t>(d.M) * LP, c.sw, LP, 0, p.ld_packed))) return rc;
     }
 
     // DEFAULT forward (float32, TMA staging, strip 32, one CTA per SM, plain entry point): geometry warps with lean records
@@ -412,10 +412,11 @@ int bm2f_msda_fused_supported(int num_heads, int channels, int num_levels, int n
     return 0;
 }
 
-int bm2f_msda_fused_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
-                            const void *reference_points, const void *sampling_offsets, const void *attn_logits,
-                            void *output, int batch, int spatial_size, int num_heads, int channels, int num_levels,
-                            int num_query, int num_point, int dtype, const bm2f_msda_tuning_t *tuning, void *stream)
+static int fused_forward_impl(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                              const void *reference_points, const void *sampling_offsets, const void *attn_logits,
+                              void *output, int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                              int num_query, int num_point, int dtype, const bm2f_msda_tuning_t *tuning, void *stream,
+                              int ld_packed)
 {
     const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
     int rc = check_common(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, d, dtype);
@@ -437,15 +438,42 @@ int bm2f_msda_fused_forward(const void *value, const int64_t *spatial_shapes, co
     p.ref = static_cast<const float *>(reference_points);
     p.out = output;
     p.N = d.N; p.S = d.S; p.M = d.M; p.Lq = d.Lq;
+    p.ld_packed = ld_packed;
+    if (ld_packed && t.staging != 0 && t.staging != 1)
+        return fail(BM2F_ERR_UNSUPPORTED, "packed offsets||logits are read through TMA tensor maps only (tuning.staging = %d)", t.staging);
     return run_fast(false, p, d, dtype, t, static_cast<cudaStream_t>(stream), true);
 }
 
-int bm2f_msda_fused_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
-                             const void *reference_points, const void *sampling_offsets, const void *attn_logits,
-                             const void *grad_output, void *grad_value, void *grad_sampling_offsets,
-                             void *grad_attn_logits, int batch, int spatial_size, int num_heads, int channels,
-                             int num_levels, int num_query, int num_point, int dtype,
-                             const bm2f_msda_tuning_t *tuning, void *stream)
+int bm2f_msda_fused_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                            const void *reference_points, const void *sampling_offsets, const void *attn_logits,
+                            void *output, int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                            int num_query, int num_point, int dtype, const bm2f_msda_tuning_t *tuning, void *stream)
+{
+    return fused_forward_impl(value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attn_logits, output,
+                              batch, spatial_size, num_heads, channels, num_levels, num_query, num_point, dtype, tuning,
+                              stream, 0);
+}
+
+int bm2f_msda_fused_forward_packed(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                                   const void *reference_points, const void *offsets_logits, void *output, int batch,
+                                   int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                                   int num_point, int dtype, const bm2f_msda_tuning_t *tuning, void *stream)
+{
+    // row r of offsets_logits: [M * L * P * 2 offsets | M * L * P logits], as written by ONE projection GEMM
+    if (!offsets_logits) return fail(BM2F_ERR_INVALID, "null tensor pointer");
+    const int lp = num_levels * num_point;
+    const float *oa = static_cast<const float *>(offsets_logits);
+    return fused_forward_impl(value, spatial_shapes, level_start_index, reference_points, oa, oa + static_cast<size_t>(num_heads) * lp * 2,
+                              output, batch, spatial_size, num_heads, channels, num_levels, num_query, num_point, dtype, tuning,
+                              stream, num_heads * lp * 3);
+}
+
+static int fused_backward_impl(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                               const void *reference_points, const void *sampling_offsets, const void *attn_logits,
+                               const void *grad_output, void *grad_value, void *grad_sampling_offsets,
+                               void *grad_attn_logits, int batch, int spatial_size, int num_heads, int channels,
+                               int num_levels, int num_query, int num_point, int dtype,
+                               const bm2f_msda_tuning_t *tuning, void *stream, int ld_packed)
 {
     const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
     int rc = check_common(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, d, dtype);
@@ -471,10 +499,40 @@ int bm2f_msda_fused_backward(const void *value, const int64_t *spatial_shapes, c
     p.grad_out = grad_output; p.grad_value = grad_value;
     p.grad_loc = static_cast<float *>(grad_sampling_offsets); p.grad_attn = static_cast<float *>(grad_attn_logits);
     p.N = d.N; p.S = d.S; p.M = d.M; p.Lq = d.Lq;
+    p.ld_packed = ld_packed;
+    if (ld_packed && t.staging != 0 && t.staging != 1)
+        return fail(BM2F_ERR_UNSUPPORTED, "packed offsets||logits are read through TMA tensor maps only (tuning.staging = %d)", t.staging);
     bool sorted = false;
     if ((rc = choose_bwd_sorted(d, dtype, t, &sorted))) return rc;
     if (sorted) return run_bwd_sorted(p, d, t, true, st);
     return run_fast(true, p, d, dtype, t, st, true);
+}
+
+int bm2f_msda_fused_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                             const void *reference_points, const void *sampling_offsets, const void *attn_logits,
+                             const void *grad_output, void *grad_value, void *grad_sampling_offsets,
+                             void *grad_attn_logits, int batch, int spatial_size, int num_heads, int channels,
+                             int num_levels, int num_query, int num_point, int dtype,
+                             const bm2f_msda_tuning_t *tuning, void *stream)
+{
+    return fused_backward_impl(value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attn_logits,
+                               grad_output, grad_value, grad_sampling_offsets, grad_attn_logits, batch, spatial_size, num_heads,
+                               channels, num_levels, num_query, num_point, dtype, tuning, stream, 0);
+}
+
+int bm2f_msda_fused_backward_packed(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                                    const void *reference_points, const void *offsets_logits, const void *grad_output,
+                                    void *grad_value, void *grad_offsets_logits, int batch, int spatial_size, int num_heads,
+                                    int channels, int num_levels, int num_query, int num_point, int dtype,
+                                    const bm2f_msda_tuning_t *tuning, void *stream)
+{
+    if (!offsets_logits || !grad_offsets_logits) return fail(BM2F_ERR_INVALID, "null tensor pointer");
+    const size_t split_at = static_cast<size_t>(num_heads) * num_levels * num_point * 2;
+    const float *oa = static_cast<const float *>(offsets_logits);
+    float *goa = static_cast<float *>(grad_offsets_logits);
+    return fused_backward_impl(value, spatial_shapes, level_start_index, reference_points, oa, oa + split_at, grad_output,
+                               grad_value, goa, goa + split_at, batch, spatial_size, num_heads, channels, num_levels, num_query,
+                               num_point, dtype, tuning, stream, num_heads * num_levels * num_point * 3);
 }
 
 }  // extern "C"

@@ -130,8 +130,8 @@ int run_bwd_sorted(FastParams p, const Dims &d, const bm2f_msda_tuning_t &t, boo
     const int LP = d.L * d.P;
     const uint64_t rows_total = static_cast<uint64_t>(d.N) * d.Lq;
     CUtensorMap ml, mw, mg;
-    if ((rc = make_map(&ml, p.loc, rows_total, static_cast<uint64_t>(d.M) * LP * 2, 32, LP * 2))) return rc;
-    if ((rc = make_map(&mw, p.attn, rows_total, static_cast<uint64_t>(d.M) * LP, 32, LP))) return rc;
+    if ((rc = make_map(&ml, p.loc, rows_total, static_cast<uint64_t>(d.M) * LP * 2, 32, LP * 2, 0, p.ld_packed))) return rc;
+    if ((rc = make_map(&mw, p.attn, rows_total, static_cast<uint64_t>(d.M) * LP, 32, LP, 0, p.ld_packed))) return rc;
     if ((rc = make_map(&mg, static_cast<const float *>(p.grad_out), rows_total, static_cast<uint64_t>(d.M) * d.D, 32, d.D)))
         return rc;
     // lower bound on the chunk count (tiles hold at most 32 x RMAX queries); the kernel enumerates the exact tiles

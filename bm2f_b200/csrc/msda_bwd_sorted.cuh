@@ -810,8 +810,10 @@ msda_bwd_sorted_kernel(const FastParams p, const int marg, long long *prof_out, 
             float4 rc[LP];
 #pragma unroll
             for (int k = 0; k < LP; ++k) rc[k] = s_rec[qi * LP + k];
-            float4 *ga4 = reinterpret_cast<float4 *>(p.grad_attn + qm * LP);
-            float4 *gl4 = reinterpret_cast<float4 *>(p.grad_loc + qm * LP * 2);
+            // packed fused layout: gradients of offsets / logits are column blocks of one (N * Lq, ld_packed) matrix
+            const size_t row = static_cast<size_t>(job.b) * p.Lq + q;
+            float4 *ga4 = reinterpret_cast<float4 *>(p.grad_attn + (p.ld_packed ? row * p.ld_packed + job.m * LP : qm * LP));
+            float4 *gl4 = reinterpret_cast<float4 *>(p.grad_loc + (p.ld_packed ? row * p.ld_packed + job.m * LP * 2 : qm * LP * 2));
             if constexpr (FUSED) {
                 // softmax backward: grad_logit_i = a_i * (ga_i - sum_j a_j ga_j); d loc / d offset = 1 / (W, H) cancels
                 float dot = 0.f;

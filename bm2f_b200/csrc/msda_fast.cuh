@@ -40,6 +40,10 @@ struct FastParams {
     int N, S, M, Lq;
     int rows;                    // strip rows per job
     int order;                   // 1 = force 1-D query order
+    // packed fused layout (bm2f_msda_fused_*_packed): offsets and logits (and their gradients) are column blocks of ONE
+    // (N * Lq, ld_packed) matrix — the output of a single offsets||logits projection.  0 = separate contiguous tensors.
+    // The kernels read both through TMA tensor maps (row stride = ld_packed); only the gradient stores index memory.
+    int ld_packed;
 };
 
 struct QLevel {
@@ -1114,10 +1118,14 @@ msda_bwd_fast_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_
                 for (int o = LPC; o < 32; o <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
                 if (sub == 0) {
 #pragma unroll
+                    // contiguous: element (row * M + m) * LP + j of grad_attn / float2 of grad_loc; packed: row * ld (+ m * LP + j)
+                    const size_t row = static_cast<size_t>(b) * p.Lq + q;
+                    const size_t ka = p.ld_packed ? row * p.ld_packed + m * LP : qm * LP;
+                    const size_t kl = p.ld_packed ? row * (p.ld_packed / 2) + m * LP : qm * LP;
+#pragma unroll
                     for (int it = 0; it < NIT; ++it) {
-                        const size_t k = qm * LP + it * LG + lg;
-                        p.grad_attn[k] = ws[it] * (ga_keep[it] - dot);
-                        reinterpret_cast<float2 *>(p.grad_loc)[k] = make_float2(gx_keep[it], gy_keep[it]);
+                        p.grad_attn[ka + it * LG + lg] = ws[it] * (ga_keep[it] - dot);
+                        reinterpret_cast<float2 *>(p.grad_loc)[kl + it * LG + lg] = make_float2(gx_keep[it], gy_keep[it]);
                     }
                 }
             }

@@ -240,6 +240,80 @@ std::vector<at::Tensor> ms_deform_attn_fused_backward(const at::Tensor &value, c
 }
 
 
+// ---- packed fused op: offsets_logits (N, Lq, M*L*P*3) = [offsets | logits] per row, the output of ONE projection ----
+namespace {
+FusedChecked check_fused_packed(const at::Tensor &value, const at::Tensor &spatial_shapes, const at::Tensor &level_start_index,
+                                const c10::optional<at::Tensor> &reference_points_opt, const at::Tensor &oa, int64_t num_point)
+{
+    TORCH_CHECK(value.is_cuda(), "Not implemented on the CPU");
+    for (const at::Tensor *t : {&value, &spatial_shapes, &level_start_index, &oa}) {
+        TORCH_CHECK(t->is_cuda(), "all tensors must be CUDA tensors");
+        TORCH_CHECK(t->is_contiguous(), "all tensors have to be contiguous");
+    }
+    TORCH_CHECK(spatial_shapes.scalar_type() == at::kLong && level_start_index.scalar_type() == at::kLong,
+                "spatial_shapes / level_start_index must be int64");
+    TORCH_CHECK(value.dim() == 4 && oa.dim() == 3 && oa.scalar_type() == at::kFloat,
+                "value must be (N,S,M,D), offsets_logits float32 (N,Lq,M*L*P*3)");
+    FusedChecked c;
+    c.N = static_cast<int>(value.size(0)); c.S = static_cast<int>(value.size(1));
+    c.M = static_cast<int>(value.size(2)); c.D = static_cast<int>(value.size(3));
+    c.L = static_cast<int>(spatial_shapes.size(0)); c.Lq = static_cast<int>(oa.size(1));
+    c.P = static_cast<int>(num_point);
+    TORCH_CHECK(oa.size(0) == c.N && oa.size(2) == static_cast<int64_t>(c.M) * c.L * c.P * 3,
+                "offsets_logits must be (N,Lq,M*L*P*3)");
+    if (reference_points_opt.has_value()) {
+        const at::Tensor &r = *reference_points_opt;
+        TORCH_CHECK(r.is_cuda() && r.is_contiguous() && r.scalar_type() == at::kFloat && r.dim() == 4 && r.size(3) == 2 &&
+                        r.size(0) == c.N && r.size(1) == c.Lq && r.size(2) == c.L,
+                    "reference_points must be a contiguous float32 CUDA tensor (N,Lq,L,2)");
+    } else {
+        TORCH_CHECK(c.Lq == c.S, "reference_points=None (pixel-centre reference points) needs Lq == S");
+    }
+    c.dtype = dtype_code(value);
+    return c;
+}
+}  // namespace
+
+at::Tensor ms_deform_attn_fused_forward_packed(const at::Tensor &value, const at::Tensor &spatial_shapes,
+                                               const at::Tensor &level_start_index,
+                                               const c10::optional<at::Tensor> &reference_points,
+                                               const at::Tensor &offsets_logits, int64_t num_point)
+{
+    const FusedChecked c = check_fused_packed(value, spatial_shapes, level_start_index, reference_points, offsets_logits, num_point);
+    const c10::cuda::CUDAGuard guard(value.device());
+    auto output = at::empty({c.N, c.Lq, c.M * c.D}, value.options());
+    const int rc = bm2f_msda_fused_forward_packed(value.data_ptr(), spatial_shapes.data_ptr<int64_t>(),
+                                                  level_start_index.data_ptr<int64_t>(),
+                                                  reference_points.has_value() ? reference_points->data_ptr() : nullptr,
+                                                  offsets_logits.data_ptr(), output.data_ptr(), c.N, c.S, c.M, c.D, c.L, c.Lq,
+                                                  c.P, c.dtype, nullptr, at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == BM2F_OK, "ms_deform_attn_fused_forward_packed: ", bm2f_msda_last_error());
+    return output;
+}
+
+std::vector<at::Tensor> ms_deform_attn_fused_backward_packed(const at::Tensor &value, const at::Tensor &spatial_shapes,
+                                                             const at::Tensor &level_start_index,
+                                                             const c10::optional<at::Tensor> &reference_points,
+                                                             const at::Tensor &offsets_logits, int64_t num_point,
+                                                             const at::Tensor &grad_output)
+{
+    const FusedChecked c = check_fused_packed(value, spatial_shapes, level_start_index, reference_points, offsets_logits, num_point);
+    TORCH_CHECK(grad_output.is_cuda() && grad_output.is_contiguous(), "grad_output must be a contiguous CUDA tensor");
+    TORCH_CHECK(grad_output.scalar_type() == value.scalar_type(), "grad_output must have the dtype of value");
+    const c10::cuda::CUDAGuard guard(value.device());
+    auto grad_value = at::empty(value.sizes(), value.options().dtype(at::kFloat));
+    auto grad_oa = at::empty_like(offsets_logits);
+    const int rc = bm2f_msda_fused_backward_packed(value.data_ptr(), spatial_shapes.data_ptr<int64_t>(),
+                                                   level_start_index.data_ptr<int64_t>(),
+                                                   reference_points.has_value() ? reference_points->data_ptr() : nullptr,
+                                                   offsets_logits.data_ptr(), grad_output.data_ptr(), grad_value.data_ptr(),
+                                                   grad_oa.data_ptr(), c.N, c.S, c.M, c.D, c.L, c.Lq, c.P, c.dtype, nullptr,
+                                                   at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == BM2F_OK, "ms_deform_attn_fused_backward_packed: ", bm2f_msda_last_error());
+    if (grad_value.scalar_type() != value.scalar_type()) grad_value = grad_value.to(value.scalar_type());
+    return {grad_value, grad_oa};
+}
+
 // ---- tcgen05 projection GEMM (forward of nn.Linear, fp32) -------------------------------------------------
 bool linear_tf32x3_supported(int64_t in_features, int64_t out_features)
 {
@@ -701,6 +775,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("ms_deform_attn_fused_supported", &ms_deform_attn_fused_supported);
     m.def("ms_deform_attn_fused_forward", &ms_deform_attn_fused_forward, "fused softmax + location prologue + sampling");
     m.def("ms_deform_attn_fused_backward", &ms_deform_attn_fused_backward, "backward of the fused op");
+    m.def("ms_deform_attn_fused_forward_packed", &ms_deform_attn_fused_forward_packed,
+          "fused op on packed offsets||logits (N, Lq, M*L*P*3): the output of one 256 -> 288 projection");
+    m.def("ms_deform_attn_fused_backward_packed", &ms_deform_attn_fused_backward_packed);
     m.def("linear_tf32x3", &linear_tf32x3, "tcgen05 projection GEMM (y = x W^T + b), split=3: tf32x3, 1: tf32");
     m.def("linear_tf32x3_supported", &linear_tf32x3_supported);
     m.def("linear_set_tuning", [](int variant, int dw_row_cap) {

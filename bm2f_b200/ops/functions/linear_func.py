@@ -127,3 +127,48 @@ class SelfAttnProjectionsFunction(Function):
         gwo, gbo = MSDA.linear_tf32x3_backward_weight(go2, q2, sp, True)
         gwa, gba = MSDA.linear_tf32x3_backward_weight(gl2, q2, sp, True)
         return g_src, g_pos, gwv, gbv, gwo, gbo, gwa, gba, None, None
+
+
+class SelfAttnProjectionsPackedFunction(Function):
+    """`SelfAttnProjectionsFunction` with `sampling_offsets` and `attention_weights` as ONE 256 -> 288 projection
+    (reference: ops/modules/ms_deform_attn.py:101-102 read `query` twice): `query = src + pos` is read once, the result
+    (N, S, 288) = [offsets | logits] goes to the packed fused attention op as it is, and in backward the gradient of
+    `query` is one GEMM over K = 288 and the two weight gradients one grad_W launch.  The module keeps its two nn.Linear
+    layers (state-dict keys); their weights are stacked here per call (295 KB)."""
+
+    @staticmethod
+    def forward(ctx, src, pos, wv, bv, wo, bo, wa, ba, split, row_mask):
+        q = src + pos
+        value = MSDA.linear_tf32x3(src, wv, bv, split)
+        if row_mask is not None:
+            MSDA.zero_masked_rows_(value, row_mask)          # consumer zeroes the masked rows of grad_value
+        woa = torch.cat((wo, wa), 0)
+        oa = MSDA.linear_tf32x3(q, woa, torch.cat((bo, ba), 0), split)
+        ctx.save_for_backward(src, q, wv, woa)
+        ctx.split = split
+        ctx.pos_shape = pos.shape
+        ctx.n_off = wo.shape[0]
+        return value, oa
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_value, g_oa):
+        src, q, wv, woa = ctx.saved_tensors
+        sp = ctx.split
+        rows = src.numel() // src.shape[-1]
+        gv2 = g_value.reshape(rows, -1).contiguous()
+        goa2 = g_oa.reshape(rows, -1).contiguous()
+        g_src = g_pos = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            g_q = MSDA.linear_tf32x3_backward_input(goa2, woa, sp)
+            if ctx.needs_input_grad[0]:
+                g_src = MSDA.linear_tf32x3_backward_input_accumulate(gv2, wv, g_q, False, sp).view_as(src)
+            if ctx.needs_input_grad[1]:
+                g_pos = g_q.view_as(src)
+                if tuple(ctx.pos_shape) != tuple(src.shape):
+                    g_pos = g_pos.sum_to_size(ctx.pos_shape)
+        x2, q2 = src.reshape(rows, -1), q.reshape(rows, -1)
+        gwv, gbv = MSDA.linear_tf32x3_backward_weight(gv2, x2, sp, True)
+        gwoa, gboa = MSDA.linear_tf32x3_backward_weight(goa2, q2, sp, True)
+        n = ctx.n_off
+        return g_src, g_pos, gwv, gbv, gwoa[:n], gboa[:n], gwoa[n:], gboa[n:], None, None

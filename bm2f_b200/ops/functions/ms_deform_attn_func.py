@@ -73,3 +73,34 @@ class MSDeformAttnFusedFunction(Function):
         elif ctx.value_padding_mask is not None:
             grad_value = grad_value.masked_fill(ctx.value_padding_mask[..., None, None], 0)
         return grad_value, None, None, None, grad_off, grad_logits, None
+
+
+class MSDeformAttnFusedPackedFunction(Function):
+    """`MSDeformAttnFusedFunction` on the output of ONE offsets||logits projection: `offsets_logits` (N, Lq, M*L*P*3) holds
+    per row the M*L*P*2 raw sampling offsets, then the M*L*P raw attention logits (ops/modules/ms_deform_attn.py:101-102
+    with the two weight matrices stacked).  The kernels read the two column blocks through tensor maps whose row stride is
+    the packed width and write their gradients into one tensor of the same layout, so the projection's input gradient is
+    one GEMM too.  Bit-identical to the unpacked function."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, reference_points, offsets_logits, n_points,
+                value_padding_mask=None):
+        output = MSDA.ms_deform_attn_fused_forward_packed(value, value_spatial_shapes, value_level_start_index,
+                                                          reference_points, offsets_logits, n_points)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, reference_points, offsets_logits)
+        ctx.n_points = n_points
+        ctx.value_padding_mask = value_padding_mask
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, start, ref, oa = ctx.saved_tensors
+        grad_value, grad_oa = MSDA.ms_deform_attn_fused_backward_packed(value, shapes, start, ref, oa, ctx.n_points,
+                                                                        grad_output.contiguous())
+        if ctx.value_padding_mask is not None and grad_value.dtype == torch.float32:
+            MSDA.zero_masked_rows_(grad_value.view(-1, grad_value.shape[-2] * grad_value.shape[-1]),
+                                   ctx.value_padding_mask)
+        elif ctx.value_padding_mask is not None:
+            grad_value = grad_value.masked_fill(ctx.value_padding_mask[..., None, None], 0)
+        return grad_value, None, None, None, grad_oa, None, None

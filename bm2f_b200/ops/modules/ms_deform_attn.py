@@ -22,7 +22,7 @@ import torch.nn.functional as F
 from torch import nn
 from torch.nn.init import constant_, xavier_uniform_
 
-from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction
+from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction, MSDeformAttnFusedPackedFunction
 from ..functions.ms_deform_attn_func import MSDA
 from ..functions import linear_func
 
@@ -49,6 +49,9 @@ class MSDeformAttn(nn.Module):
         self.fuse_prologue = True
         # forward GEMMs of the four projections on tcgen05 (tf32x3, fp32-grade); False = torch / cuBLAS
         self.tcgen05_linear = True
+        # encoder self-attention: sampling_offsets || attention_weights as ONE 256 -> 288 projection feeding the packed fused
+        # op; False = two projections (192 and 96 wide), same results
+        self.packed_projections = True
 
         self.d_model = d_model
         self.n_levels = n_levels
@@ -103,6 +106,19 @@ class MSDeformAttn(nn.Module):
         input projections as one autograd node (`SelfAttnProjectionsFunction`): the gradients of `src + pos` and `src`
         are accumulated in GEMM epilogues instead of element-wise passes.  Same result as `forward`."""
         N, Len, _ = src.shape
+        analytic = getattr(reference_points, "pixel_centres", False)
+        if self.packed_projections and self.n_heads * self.n_levels * self.n_points * 3 == 288:
+            # ONE offsets||logits projection (256 -> 288) feeding the packed fused op: `query` is read once, its gradient
+            # is one GEMM (ops/functions/linear_func.py:SelfAttnProjectionsPackedFunction)
+            value, oa = linear_func.SelfAttnProjectionsPackedFunction.apply(
+                src, pos, self.value_proj.weight, self.value_proj.bias, self.sampling_offsets.weight,
+                self.sampling_offsets.bias, self.attention_weights.weight, self.attention_weights.bias,
+                linear_func.matmul_split(), input_padding_mask)
+            output = MSDeformAttnFusedPackedFunction.apply(
+                value.view(N, Len, self.n_heads, self.d_model // self.n_heads), input_spatial_shapes,
+                input_level_start_index, None if analytic else reference_points.contiguous(), oa, self.n_points,
+                input_padding_mask)
+            return self._proj(self.output_proj, output)
         value, offsets, logits = linear_func.SelfAttnProjectionsFunction.apply(
             src, pos, self.value_proj.weight, self.value_proj.bias, self.sampling_offsets.weight,
             self.sampling_offsets.bias, self.attention_weights.weight, self.attention_weights.bias,
@@ -110,7 +126,6 @@ class MSDeformAttn(nn.Module):
         value = value.view(N, Len, self.n_heads, self.d_model // self.n_heads)
         offsets = offsets.view(N, Len, self.n_heads, self.n_levels, self.n_points, 2)
         logits = logits.view(N, Len, self.n_heads, self.n_levels * self.n_points)
-        analytic = getattr(reference_points, "pixel_centres", False)
         output = MSDeformAttnFusedFunction.apply(
             value, input_spatial_shapes, input_level_start_index, None if analytic else reference_points.contiguous(),
             offsets, logits, input_padding_mask)

@@ -188,6 +188,24 @@ int bm2f_msda_fused_backward(const void *value, const int64_t *spatial_shapes,
                              int dtype, const bm2f_msda_tuning_t *tuning, void *stream);
 
 /*
+ * Packed variants: sampling offsets and attention logits are the column blocks of ONE matrix
+ * offsets_logits (batch * num_query, num_heads * num_levels * num_point * 3) — row = [M*L*P*2 offsets | M*L*P logits] —
+ * i.e. the output of a single projection with the weights of `sampling_offsets` and `attention_weights` stacked
+ * (ops/modules/ms_deform_attn.py:101-102 as one 256 -> 288 GEMM); grad_offsets_logits has the same layout, so the input
+ * gradient of both projections is one GEMM as well.  Same kernels and bit-identical results as the unpacked entry points
+ * (the matrices are read through TMA tensor maps whose row stride is the packed width; tuning.staging must be 0 or 1).
+ */
+int bm2f_msda_fused_forward_packed(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                                   const void *reference_points, const void *offsets_logits, void *output, int batch,
+                                   int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                                   int num_point, int dtype, const bm2f_msda_tuning_t *tuning, void *stream);
+int bm2f_msda_fused_backward_packed(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                                    const void *reference_points, const void *offsets_logits, const void *grad_output,
+                                    void *grad_value, void *grad_offsets_logits, int batch, int spatial_size, int num_heads,
+                                    int channels, int num_levels, int num_query, int num_point, int dtype,
+                                    const bm2f_msda_tuning_t *tuning, void *stream);
+
+/*
  * Projection GEMM on the 5th-generation tensor cores (tcgen05 + TMEM), for the four nn.Linear layers of
  * MSDeformAttn (ops/modules/ms_deform_attn.py:59-62; applied at :98, :101, :102, :124):
  *     y[rows, out_features] = x[rows, in_features] * weight[out_features, in_features]^T + bias
