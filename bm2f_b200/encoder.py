@@ -58,11 +58,12 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
         self.dropout3 = nn.Dropout(dropout)
         self.norm2 = nn.LayerNorm(d_model)
         self.fused = True          # False: always the reference op sequence in torch
-        # value / offset / logit projections of self-attention as ONE autograd node with the gradient sums in GEMM
-        # epilogues (MSDeformAttn.forward_self_attention).  Measured neutral (92.5 vs 92.7 ms per encoder pass) to
-        # slightly slower with TF32 allowed (85.4 vs 84.1 ms): the epilogue's per-row addend loads are no better than the
-        # autograd engine's coalesced adds.  Off by default; kept selectable and tested.
-        self.fuse_projections = False
+        # value / offset / logit projections of self-attention as ONE autograd node (MSDeformAttn.forward_self_attention):
+        # with the packed 256 -> 288 offsets||logits projection the node is the fastest variant (alternating A/B at cfg 2 x
+        # 16, fwd+bwd: 87.9 ms per encoder pass vs 88.4 with separate projection nodes and 89.3 with one node and two
+        # projections, profiles/r02_encoder_bench.txt).  With TF32 matmuls allowed the separate nodes measured faster in
+        # round 1 (84.1 vs 85.4 ms), so the node is used for fp32-grade (default) precision only.
+        self.fuse_projections = True
 
     @staticmethod
     def with_pos_embed(tensor, pos):
@@ -83,7 +84,7 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
         return self.norm2(src)
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
-        if (self.fuse_projections and self._fast_ok(src)
+        if (self.fuse_projections and not torch.backends.cuda.matmul.allow_tf32 and self._fast_ok(src)
                 and self.self_attn.self_attention_supported(src, pos, reference_points)):
             # query = src + pos, input = src: the three input projections run as one autograd node
             src2 = self.self_attn.forward_self_attention(src, pos, reference_points, spatial_shapes, level_start_index,

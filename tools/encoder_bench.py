@@ -41,3 +41,22 @@ for name, fused in (("fused_sm100a", True), ("fused_sm100a, separate projection 
     print(f"{name:42s} {best:9.2f} ms / encoder fwd+bwd (6 layers, batch {args.batch}) -> {args.batch / (best * 1e-3):8.1f} images/s, "
           f"peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB", flush=True)
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", f"encoder_bench_cfg{args.cfg}.json"), "w"))
+
+# alternating A/B of the projection variants (the lines above run one after the other on a warming, power-capped GPU)
+set_mode(True)
+variants = (("one node, packed 256 -> 288 projection", True, True), ("one node, two projections", True, False),
+            ("separate projection nodes", False, False))
+acc = {n: [] for n, _, _ in variants}
+for rnd in range(4):
+    for n, fuse, packed in variants:
+        for m in enc.modules():
+            if hasattr(m, "fuse_projections"): m.fuse_projections = fuse
+            if hasattr(m, "packed_projections"): m.packed_projections = packed
+        run(); torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(2):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); run(); b.record(); torch.cuda.synchronize(); best = min(best, a.elapsed_time(b))
+        acc[n].append(best)
+for n, v in acc.items():
+    print(f"A/B {n:42s} " + "  ".join(f"{x:7.2f}" for x in v) + f"   median {sorted(v)[len(v) // 2]:7.2f} ms", flush=True)
