@@ -202,7 +202,17 @@ int linear_common(const void *x, const void *weight, const void *bias, void *y, 
                  if (xvar == 4) return launch_linear_pair<96>(p, w_hi, w_lo, sms, st);
                  return cluster2 ? launch_linear_persistent<96, 2>(p, w_hi, w_lo, sms, st)
                                  : launch_linear_persistent<96, 1>(p, w_hi, w_lo, sms, st);
-        default: break;      // 288 = 2 x 144 columns does not fit two accumulators: one-tile kernel
+        case 288:            // offsets || logits: two 144-column slices of the same row tile run on neighbouring CTAs (the
+                             // activation tile is read from HBM once, from L2 the second time); 144 = 4.5 x 32 columns:
+                             // coalesced-store epilogue with a column predicate (a 32-wide TMA store box would spill
+                             // into the other slice)
+            if (!relu && !mask && !addend && xvar == 0 && !cluster2) {
+                p.slices = 2;
+                p.store_mode = 1;
+                return launch_linear_persistent<144, 1>(p, w_hi, w_lo, sms, st);
+            }
+            break;
+        default: break;
         }
     }
     if (relu || mask || addend)

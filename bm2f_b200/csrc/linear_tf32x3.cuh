@@ -787,7 +787,7 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
 #pragma unroll
                 for (int c = 0; c < 32; c += 4) {
                     float4 o = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
-                    if (p.bias) {
+                    if (p.bias && (NT % 32 == 0 || c0 + c < NT)) {      // NT = 144: the last chunk has 16 columns
                         const float4 bb = __ldg(reinterpret_cast<const float4 *>(p.bias + ti.sl * NT + c0 + c));
                         o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
                     }
@@ -835,7 +835,7 @@ linear_tf32x3_persistent_kernel(const LinearParams p, const __grid_constant__ CU
                     for (int it = 0; it < 8; ++it) {
                         const int row = it * 4 + (lane >> 3);
                         const float4 v = *reinterpret_cast<const float4 *>(stg + row * 128 + ((ch ^ (row & 7)) << 4));
-                        if (rt_own * kGemmBlockM + q * 32 + row < p.M)
+                        if (rt_own * kGemmBlockM + q * 32 + row < p.M && (NT % 32 == 0 || c0 + ch * 4 < NT))
                             *reinterpret_cast<float4 *>(ybase + static_cast<size_t>(row) * p.N) = v;
                     }
                     __syncwarp();
