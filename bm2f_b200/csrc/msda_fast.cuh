@@ -665,7 +665,7 @@ msda_fwd_geo_kernel(const FastParams p, const __grid_constant__ CUtensorMap tm_l
                         if (!f.in_range) { ay = 0; ax = 0; }
                         if (ay < 0) { ay = 0; r0 = r1; r1 = 0.f; }                        // row y = 0 is the footprint's lower row
                         else if (ay > Hl - 2) { ay = Hl - 2; r1 = r0; r0 = 0.f; }         // row y = H - 1 is its upper row
-                        float lwf = f.lw;
+                        float lwf = f.in_range ? f.lw : 0.f;      // a non-finite location has a NaN fraction: keep it out of 0 * w
                         int flags = 0;
                         if (ax < 0) { ax = 0; lwf = f.hw; flags = 2; }                    // column 0 carries lw: stored as hw, read as 1 - hw
                         else if (ax > Wl - 2) { ax = Wl - 2; lwf = f.hw; flags = 1; }     // column W - 1 carries hw in slot 1

@@ -479,3 +479,31 @@ def test_geometry_warp_forward_bit_identical(levels, batch, built):
                      cabi.DTYPE_F32, cabi.make_tuning(geo=1, ctas_per_sm=2), stream)
         torch.cuda.synchronize()
         assert torch.equal(out_2, res["default"][0])
+
+
+def test_default_forward_skips_non_finite_locations(built):
+    """The reference's range test (`h_im > -1 && w_im > -1 && h_im < H && w_im < W`, ms_deform_im2col_cuda.cuh:264) is false
+    for NaN / infinite sampling locations, so such points contribute nothing.  The default forward (unconditional gathers
+    with zero weights) must not turn them into 0 * NaN: same bits as with a finite out-of-range location."""
+    inp = W.make_inputs(SMALL_LEVELS, 2, seed=5)
+    dev = _dev()
+    N, S, M, D = inp["value"].shape
+    L = len(SMALL_LEVELS)
+    dims = (N, S, M, D, L, S, 4)
+    stream = torch.cuda.current_stream().cuda_stream
+    sh, st = inp["shapes"].to(dev), inp["start"].to(dev)
+    v, at = inp["value"].to(dev).contiguous(), inp["attn"].to(dev).contiguous()
+    outs = []
+    for bad in ((5.0, 5.0), (float("inf"), 0.3), (0.4, float("nan")), (float("-inf"), float("inf"))):
+        loc = inp["loc"].clone()
+        flat = loc.view(-1, 2)
+        flat[3::97] = torch.tensor(bad)
+        lc = loc.to(dev).contiguous()
+        out = torch.full((N, S, M * D), float("nan"), device=dev)
+        cabi.forward(v.data_ptr(), sh.data_ptr(), st.data_ptr(), lc.data_ptr(), at.data_ptr(), out.data_ptr(), dims,
+                     cabi.DTYPE_F32, None, stream)
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert not torch.isnan(outs[0]).any()
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
