@@ -101,3 +101,35 @@ def test_encoder_mirror_surface(built):
     assert layer.linear1.out_features == 1024 and layer.self_attn.n_levels == 4 and layer.dropout1.p == 0.1
     ref = MSDeformAttnTransformerEncoder.get_reference_points([(2, 3)], torch.ones(1, 1, 2), "cpu")
     assert torch.allclose(ref, W.reference_points(((2, 3),), 1))
+
+
+def test_bench_host_logic_config_shard_and_graph_rule():
+    """bench.py host logic shared by both arms: the config builder, the strong-scaling shard size and the rule that turns
+    CUDA-graph replay on for launch-bound per-GPU steps."""
+    import importlib.util
+    import os
+    import types
+
+    from bm2f_b200 import dist as D
+    from bm2f_b200 import workloads as W
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod_host", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    wl = W.WORKLOADS[2]
+    for world in (1, 2, 4, 8, 3, 16):
+        assert bench.b200_shard(wl.batch, world) == D.shard_batch(wl.batch, world, 0)[1]
+    cfg1 = bench.workload_config(wl, 1, 16, "weak")
+    assert cfg1["global_batch"] == 16 and cfg1["batch_per_gpu"] == 16 and cfg1["collective"] == "none"
+    assert cfg1["l2_policy"].startswith("inputs larger than L2: 1101 MB")
+    cfg8 = bench.workload_config(wl, 8, 2, "strong", "default", True)
+    assert cfg8["global_batch"] == 16 and cfg8["parallelism"] == "dp8" and cfg8["collective"] != "none" and cfg8["cuda_graph"]
+    assert bench.workload_config(wl, 8, 16, "weak")["global_batch"] == 128
+    auto = types.SimpleNamespace(graph=None)
+    assert not bench.graph_enabled(auto, wl, 16) and not bench.graph_enabled(auto, wl, 8)
+    assert bench.graph_enabled(auto, wl, 4) and bench.graph_enabled(auto, wl, 2)          # 86 016 / 43 008 rows per GPU
+    assert bench.graph_enabled(auto, W.WORKLOADS[1], 1)                                    # one 512^2 image: launch-bound
+    assert not bench.graph_enabled(types.SimpleNamespace(graph=False), wl, 2)
+    assert bench.graph_enabled(types.SimpleNamespace(graph=True), wl, 16)
+    small = bench.workload_config(W.WORKLOADS[1], 1, 1, "weak")
+    assert "smaller than L2" in small["l2_policy"]
